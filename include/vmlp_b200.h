@@ -1,0 +1,158 @@
+/*
+ * vmlp_b200.h -- C ABI of the B200-native vision-MLP block library (libvmlp_b200.so).
+ *
+ * Drop-in boundary for the per-block bodies of liuruiyang98/Jittor-MLP `models_pytorch`.
+ * The reference has exactly one custom-operator boundary, `_shift.forward/backward`
+ * (models_pytorch/utils/shift_cuda.py:106-162): a torch.autograd.Function that receives
+ * contiguous device tensors, allocates its output on the Python side, and launches a raw
+ * kernel on `torch.cuda.current_stream()` with `data_ptr()` arguments.  Every entry point
+ * below follows that same convention, generalised to whole blocks:
+ *
+ *   - plain pointers, sizes and a stream handle; no torch / C++ types in any signature;
+ *   - all device memory (inputs, outputs, saved activations, workspace) is caller-owned;
+ *     the library never allocates, frees or retains a pointer past return;
+ *   - asynchronous on the given stream, no host synchronisation, re-entrant;
+ *   - every function returns 0 on success or a negative VMLP_E* code; nothing falls back
+ *     to a CPU or library path.
+ *
+ * Element type is bf16 (device `__nv_bfloat16`, passed as `void*`) unless a parameter is
+ * declared `float*`.  All row strides ("ld") and batch strides are in ELEMENTS and must be
+ * multiples of 8 (16 bytes) because tiles are moved by TMA.
+ */
+#ifndef VMLP_B200_H_
+#define VMLP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vmlp_stream_t; /* cudaStream_t */
+
+enum {
+  VMLP_OK = 0,
+  VMLP_EINVAL = -1,      /* bad shape / null pointer / unsupported hyper-parameter */
+  VMLP_EALIGN = -2,      /* pointer or stride not 16-byte aligned                  */
+  VMLP_EARCH = -3,       /* device is not sm_100 (no fallback path exists)         */
+  VMLP_ELAUNCH = -4,     /* CUDA launch / driver error (see vmlp_last_error)       */
+  VMLP_EWORKSPACE = -5   /* caller-provided workspace too small                     */
+};
+
+/* Library / device introspection. */
+int vmlp_abi_version(void);
+const char* vmlp_last_error(void);          /* thread-local message for the last failing call */
+int vmlp_device_check(void);                /* VMLP_OK iff current device is compute capability 10.x */
+int vmlp_sm_count(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Generic fused GEMM (the building block of every mixing MLP):
+ *     D[b][m, n] = epilogue( sum_k A[b][m, k] * B[b][n, k] )
+ * A matrix operand is described by a dense 2-D view plus an optional batch:
+ *     major = 0  "K-major":  rows = M (or N), cols = K   (a row-major weight `[out, in]`)
+ *     major = 1  "MN-major": rows = K,        cols = M/N (a `[tokens, channels]` activation used
+ *                                                          as the contraction-over-tokens operand)
+ * batch_stride == 0 means the operand is shared by all batches.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* ptr;      /* bf16 */
+  int64_t rows, cols;   /* logical extent of the 2-D view */
+  int64_t ld;           /* row stride, elements */
+  int64_t batch_stride; /* elements; 0 = shared */
+  int32_t major;        /* 0 = K-major, 1 = MN-major */
+} vmlp_operand;
+
+enum {
+  VMLP_EPI_STORE = 0,     /* D = acc (+bias)                                  */
+  VMLP_EPI_GELU = 1,      /* D = acc + bias ; D2 = gelu_erf(D)                */
+  VMLP_EPI_RESID = 2,     /* D = (acc + bias) * colscale + aux                */
+  VMLP_EPI_DGELU = 3,     /* D = acc * gelu_erf'(aux)                         */
+  VMLP_EPI_ATOMIC = 4,    /* out_f32 += acc   (split-K, weight gradients)     */
+  VMLP_EPI_MUL = 5,       /* D = (acc + bias) * aux                           */
+  VMLP_EPI_GELU_ONLY = 6  /* D = gelu_erf(acc + bias)                         */
+};
+
+typedef struct {
+  int32_t M, N, K;         /* per-batch logical GEMM extents */
+  int32_t batch;           /* number of batches (>= 1) */
+  int32_t contract_batch;  /* 1: the contraction also runs over the batch (one output matrix) */
+  vmlp_operand A, B;
+  int32_t epilogue;        /* VMLP_EPI_* */
+  void* D;  int64_t d_ld, d_bs;    /* bf16 output [batch][M, N] */
+  void* D2; int64_t d2_ld, d2_bs;  /* second output (VMLP_EPI_GELU) */
+  const void* bias; int32_t bias_mode; /* 0 none, 1 per column n, 2 per row m */
+  const void* colscale;                /* optional per-column scale (VMLP_EPI_RESID) */
+  const void* aux; int64_t aux_ld, aux_bs;
+  float* out_f32; int64_t out_ld;      /* VMLP_EPI_ATOMIC destination [M, N] (caller zero-fills) */
+  int32_t split_k;                     /* 0 = choose automatically */
+  int32_t block_n;                     /* 0 = choose automatically (256 or 128) */
+} vmlp_gemm_args;
+
+int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Row-wise operators (HBM-bound glue between the GEMMs)
+ * ------------------------------------------------------------------------------------------ */
+/* torch.nn.LayerNorm(C) over the last axis -- PreNormResidual.norm, models_pytorch/mlp_mixer.py:10-13 */
+int vmlp_layernorm_fwd(const void* x, int64_t x_ld, const void* gamma, const void* beta, void* y, int64_t y_ld,
+                       float* mean, float* rstd, int64_t rows, int32_t C, float eps, vmlp_stream_t stream);
+/* dx = add + LN'(dy); dgamma/dbeta are fp32 accumulators (+=) */
+int vmlp_layernorm_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const float* mean,
+                       const float* rstd, const void* gamma, const void* add, int64_t add_ld, void* dx,
+                       int64_t dx_ld, float* dgamma, float* dbeta, int64_t rows, int32_t C, vmlp_stream_t stream);
+/* Aff: y = x * alpha + beta -- models_pytorch/res_mlp.py:11-19 */
+int vmlp_affine_fwd(const void* x, const void* alpha, const void* beta, void* y, int64_t rows, int32_t C,
+                    vmlp_stream_t stream);
+int vmlp_affine_bwd(const void* dy, const void* x, const void* alpha, const void* add, void* dx, float* dalpha,
+                    float* dbeta, int64_t rows, int32_t C, vmlp_stream_t stream);
+/* out[c] += sum_r a[r, c] * (b ? b[r, c] : 1) */
+int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t rows, int32_t C,
+                vmlp_stream_t stream);
+/* out[m] += sum_{b, c} a[b, m, c] */
+int vmlp_rowsum_batched(const void* a, float* out, int64_t batch, int32_t rows_per_batch, int32_t C,
+                        vmlp_stream_t stream);
+int vmlp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vmlp_stream_t stream);
+int vmlp_add_bf16(const void* a, const void* b, void* dst, int64_t n, vmlp_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
+ * MLP-Mixer block: models_pytorch/mlp_mixer.py:35-40
+ *     u = x + TokenFF(LN1(x))   (FeedForward with Conv1d(k=1) over tokens, :16-27,:37)
+ *     y = u + ChanFF(LN2(u))    (FeedForward with Linear over channels,    :38)
+ * Shapes: x, y, u : [B, N, C];  token weights W1t [Ds, N], W2t [N, Ds] (Conv1d weight[:, :, 0]);
+ * channel weights W1c [Dc, C], W2c [C, Dc].  C % 64 == 0, Dc % 64 == 0, Ds % 8 == 0.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t B, N, C, Ds, Dc;
+  float eps;
+  /* parameters (bf16) */
+  const void *ln1_w, *ln1_b, *w1t, *b1t, *w2t, *b2t;
+  const void *ln2_w, *ln2_b, *w1c, *b1c, *w2c, *b2c;
+} vmlp_mixer_params;
+
+/* Activations the forward pass keeps for backward (caller-allocated, bf16 unless noted):
+ *   xhat1 [B,N,C]  z1,h1 [B,Ds,C]  u [B,N,C]  xhat2 [B,N,C]  z2,h2 [B*N,Dc]
+ *   stats: fp32 [4][B*N] = mean1, rstd1, mean2, rstd2
+ *   w1t_pad: bf16 [Ds, ceil8(N)] scratch for the 16-byte-pitch copy of W1t */
+typedef struct {
+  void *xhat1, *z1, *h1, *u, *xhat2, *z2, *h2;
+  float* stats;
+  void* w1t_pad;
+} vmlp_mixer_saved;
+
+int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, const vmlp_mixer_saved* s,
+                         vmlp_stream_t stream);
+
+/* Backward.  grads_f32 is one flat fp32 accumulator (caller zero-fills) laid out in the order of
+ * vmlp_mixer_params: ln1_w[C] ln1_b[C] w1t[Ds*N] b1t[Ds] w2t[N*Ds] b2t[N] ln2_w[C] ln2_b[C]
+ * w1c[Dc*C] b1c[Dc] w2c[C*Dc] b2c[C]  (vmlp_mixer_grad_elems gives the total).
+ * workspace: bf16, vmlp_mixer_bwd_workspace_elems(...) elements. */
+int64_t vmlp_mixer_grad_elems(const vmlp_mixer_params* p);
+int64_t vmlp_mixer_bwd_workspace_elems(const vmlp_mixer_params* p);
+int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* dy, void* dx,
+                         const vmlp_mixer_saved* s, float* grads_f32, void* workspace, int64_t workspace_elems,
+                         vmlp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMLP_B200_H_ */

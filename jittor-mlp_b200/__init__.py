@@ -1,0 +1,4 @@
+"""B200-native vision-MLP blocks behind the `models_pytorch` module signatures of
+liuruiyang98/Jittor-MLP.  Import as ``jittor_mlp_b200`` (see jittor_mlp_b200.py at the repo root)."""
+from . import _lib, ops  # noqa: F401
+from .mlp_mixer import MLPMixer, MLPMixerForImageClassification  # noqa: F401

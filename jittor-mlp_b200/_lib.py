@@ -1,0 +1,144 @@
+"""ctypes binding of libvmlp_b200.so (C ABI declared in include/vmlp_b200.h).
+
+The library is the product: if it is missing or the device is not sm_100 every
+operator raises -- there is no eager / CPU fallback behind this module.  The
+binding style mirrors the reference's only custom operator, which hands raw
+``data_ptr()`` values and the current CUDA stream to a kernel
+(/root/reference/models_pytorch/utils/shift_cuda.py:115-125).
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libvmlp_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(_ROOT, "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "vmlp_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into one in-tree shared library (nvcc cross-compiles
+    without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + _sources()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+c_void_p, c_int32, c_int64, c_float = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+
+
+class Operand(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("rows", c_int64), ("cols", c_int64), ("ld", c_int64),
+                ("batch_stride", c_int64), ("major", c_int32)]
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [("M", c_int32), ("N", c_int32), ("K", c_int32), ("batch", c_int32),
+                ("contract_batch", c_int32), ("A", Operand), ("B", Operand), ("epilogue", c_int32),
+                ("D", c_void_p), ("d_ld", c_int64), ("d_bs", c_int64),
+                ("D2", c_void_p), ("d2_ld", c_int64), ("d2_bs", c_int64),
+                ("bias", c_void_p), ("bias_mode", c_int32), ("colscale", c_void_p),
+                ("aux", c_void_p), ("aux_ld", c_int64), ("aux_bs", c_int64),
+                ("out_f32", c_void_p), ("out_ld", c_int64), ("split_k", c_int32), ("block_n", c_int32)]
+
+
+class MixerParams(ctypes.Structure):
+    _fields_ = [("B", c_int32), ("N", c_int32), ("C", c_int32), ("Ds", c_int32), ("Dc", c_int32),
+                ("eps", c_float)] + [(n, c_void_p) for n in (
+                    "ln1_w", "ln1_b", "w1t", "b1t", "w2t", "b2t", "ln2_w", "ln2_b", "w1c", "b1c", "w2c", "b2c")]
+
+
+class MixerSaved(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("xhat1", "z1", "h1", "u", "xhat2", "z2", "h2", "stats", "w1t_pad")]
+
+
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ATOMIC, EPI_MUL, EPI_GELU_ONLY = range(7)
+
+# Every symbol include/vmlp_b200.h declares: (name, restype, argtypes).
+_P = ctypes.POINTER
+SYMBOLS = [
+    ("vmlp_abi_version", c_int32, []),
+    ("vmlp_last_error", ctypes.c_char_p, []),
+    ("vmlp_device_check", c_int32, []),
+    ("vmlp_sm_count", c_int32, []),
+    ("vmlp_gemm_bf16", c_int32, [_P(GemmArgs), c_void_p]),
+    ("vmlp_layernorm_fwd", c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_int64, c_int32, c_float, c_void_p]),
+    ("vmlp_layernorm_bwd", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    ("vmlp_affine_fwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    ("vmlp_affine_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int32, c_void_p]),
+    ("vmlp_colsum", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]),
+    ("vmlp_rowsum_batched", c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    ("vmlp_cast_f32_to_bf16", c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    ("vmlp_add_bf16", c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    ("vmlp_mixer_block_fwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, _P(MixerSaved), c_void_p]),
+    ("vmlp_mixer_grad_elems", c_int64, [_P(MixerParams)]),
+    ("vmlp_mixer_bwd_workspace_elems", c_int64, [_P(MixerParams)]),
+    ("vmlp_mixer_block_bwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, c_void_p, _P(MixerSaved), c_void_p,
+                                       c_void_p, c_int64, c_void_p]),
+]
+
+_lib = None
+
+
+class VmlpError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (building it if the sources are newer).  Raises if unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            build()
+        except Exception as e:  # no nvcc on the box and no prebuilt .so: hard error, never a fallback
+            raise VmlpError(f"libvmlp_b200.so is missing and could not be built: {e}") from e
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(handle, name)  # AttributeError if the header and the library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = handle
+    return handle
+
+
+_ERRORS = {-1: ValueError, -2: ValueError, -3: VmlpError, -4: VmlpError, -5: ValueError}
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().vmlp_last_error().decode(errors="replace")
+        raise _ERRORS.get(rc, VmlpError)(f"vmlp error {rc}: {msg}")
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,545 @@
+// Host side of libvmlp_b200.so: TMA descriptor encoding, kernel launchers, and the block-level
+// orchestration (which GEMM consumes which operand in which major-ness).  C ABI in include/vmlp_b200.h.
+#include "../../include/vmlp_b200.h"
+#include "gemm_sm100.cuh"
+#include "rowwise.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+using namespace vmlp;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_OK(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) return fail(VMLP_ELAUNCH, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct DeviceInfo {
+  int sms = 0, cc_major = 0, cc_minor = 0;
+  bool ok = false;
+};
+const DeviceInfo& device_info() {
+  static DeviceInfo info[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    static DeviceInfo bad;
+    return bad;
+  }
+  DeviceInfo& d = info[dev];
+  if (!d.ok) {
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+    d.ok = d.sms > 0;
+  }
+  return d;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// 3-D bf16 tensor map: dims (inner, rows, batch), 128B swizzle, zero OOB fill.
+int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t rows, int64_t batch, int64_t ld,
+             int64_t bstride, int box_inner, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(VMLP_ELAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!aligned16(ptr) || (ld % 8) != 0 || (batch > 1 && (bstride % 8) != 0))
+    return fail(VMLP_EALIGN, "operand %p ld %lld bs %lld must be 16-byte aligned", ptr, (long long)ld,
+                (long long)bstride);
+  if (batch <= 1 || bstride == 0) { batch = 1; bstride = rows * ld; }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VMLP_EINVAL, "cuTensorMapEncodeTiled failed (%d): inner %lld rows %lld batch %lld ld %lld", (int)r,
+                (long long)inner, (long long)rows, (long long)batch, (long long)ld);
+  return VMLP_OK;
+}
+
+template <int BN, int EPI>
+int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
+                  const GemmParams& p, int grid, cudaStream_t st) {
+  auto kern = gemm_bf16_sm100<BN, EPI>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+    attr_set[dev & 63] = true;
+  }
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(ta, tb, td, td2, p);
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+template <int BN>
+int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
+                   const CUtensorMap& td2, const GemmParams& p, int grid, cudaStream_t st) {
+  switch (epi) {
+    case EPI_STORE: return launch_gemm_t<BN, EPI_STORE>(ta, tb, td, td2, p, grid, st);
+    case EPI_GELU: return launch_gemm_t<BN, EPI_GELU>(ta, tb, td, td2, p, grid, st);
+    case EPI_RESID: return launch_gemm_t<BN, EPI_RESID>(ta, tb, td, td2, p, grid, st);
+    case EPI_DGELU: return launch_gemm_t<BN, EPI_DGELU>(ta, tb, td, td2, p, grid, st);
+    case EPI_ATOMIC: return launch_gemm_t<BN, EPI_ATOMIC>(ta, tb, td, td2, p, grid, st);
+    case EPI_MUL: return launch_gemm_t<BN, EPI_MUL>(ta, tb, td, td2, p, grid, st);
+    case EPI_GELU_ONLY: return launch_gemm_t<BN, EPI_GELU_ONLY>(ta, tb, td, td2, p, grid, st);
+  }
+  return fail(VMLP_EINVAL, "unknown epilogue %d", epi);
+}
+
+int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
+  const DeviceInfo& dv = device_info();
+  if (!dv.ok || dv.cc_major != 10)
+    return fail(VMLP_EARCH, "device compute capability %d.%d is not sm_100 (no fallback)", dv.cc_major, dv.cc_minor);
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return fail(VMLP_EINVAL, "empty GEMM %d %d %d %d", g.M, g.N, g.K, g.batch);
+  if (!g.A.ptr || !g.B.ptr) return fail(VMLP_EINVAL, "null operand");
+  const int epi = g.epilogue;
+  if (epi != EPI_ATOMIC && (g.N % 8) != 0) return fail(VMLP_EINVAL, "N=%d must be a multiple of 8", g.N);
+  int bn = g.block_n;
+  if (bn == 0) bn = (g.N <= 128) ? 128 : 256;
+  if (bn != 128 && bn != 256) return fail(VMLP_EINVAL, "block_n must be 128 or 256");
+
+  // operand views
+  const bool a_mn = g.A.major != 0, b_mn = g.B.major != 0;
+  if (!a_mn ? (g.A.rows != g.M || g.A.cols != g.K) : (g.A.rows != g.K || g.A.cols != g.M))
+    return fail(VMLP_EINVAL, "A view %lldx%lld does not match M=%d K=%d major=%d", (long long)g.A.rows,
+                (long long)g.A.cols, g.M, g.K, g.A.major);
+  if (!b_mn ? (g.B.rows != g.N || g.B.cols != g.K) : (g.B.rows != g.K || g.B.cols != g.N))
+    return fail(VMLP_EINVAL, "B view %lldx%lld does not match N=%d K=%d major=%d", (long long)g.B.rows,
+                (long long)g.B.cols, g.N, g.K, g.B.major);
+  const bool a_batched = g.A.batch_stride != 0 && g.batch > 1;
+  const bool b_batched = g.B.batch_stride != 0 && g.batch > 1;
+
+  CUtensorMap ta, tb, td, td2;
+  memset(&td, 0, sizeof(td));
+  memset(&td2, 0, sizeof(td2));
+  int rc;
+  // K-major: inner = K, box (64, 128 | BN).  MN-major: inner = M/N, box (64, 64) per swizzle atom.
+  rc = make_map(&ta, g.A.ptr, g.A.cols, g.A.rows, a_batched ? g.batch : 1, g.A.ld, g.A.batch_stride, 64,
+                a_mn ? GEMM_BK : GEMM_BM);
+  if (rc) return rc;
+  rc = make_map(&tb, g.B.ptr, g.B.cols, g.B.rows, b_batched ? g.batch : 1, g.B.ld, g.B.batch_stride, 64,
+                b_mn ? GEMM_BK : bn);
+  if (rc) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = g.M;
+  p.N = g.N;
+  p.tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_n = (g.N + bn - 1) / bn;
+  p.kbatch = g.contract_batch ? 1 : 0;
+  p.batch = p.kbatch ? 1 : g.batch;
+  p.kpb = (g.K + GEMM_BK - 1) / GEMM_BK;
+  p.k_blocks = p.kpb * (p.kbatch ? g.batch : 1);
+  const int krem = g.K - (p.kpb - 1) * GEMM_BK;
+  p.last_ksteps = (krem + 15) / 16;
+  p.a_mn = a_mn;
+  p.b_mn = b_mn;
+  p.a_batched = a_batched;
+  p.b_batched = b_batched;
+  p.bias_mode = g.bias ? g.bias_mode : 0;
+  p.bias = static_cast<const __nv_bfloat16*>(g.bias);
+  p.colscale = static_cast<const __nv_bfloat16*>(g.colscale);
+  p.aux = static_cast<const __nv_bfloat16*>(g.aux);
+  p.aux_ld = g.aux_ld;
+  p.aux_bs = g.aux_bs;
+  p.out_f32 = g.out_f32;
+  p.out_ld = g.out_ld;
+  if (p.bias_mode == 1 && !aligned16(g.bias)) return fail(VMLP_EALIGN, "bias must be 16-byte aligned");
+  if (p.colscale && !aligned16(p.colscale)) return fail(VMLP_EALIGN, "colscale must be 16-byte aligned");
+  const bool needs_aux = (epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_MUL);
+  if (needs_aux) {
+    if (!g.aux) return fail(VMLP_EINVAL, "epilogue %d needs aux", epi);
+    if (!aligned16(g.aux) || (g.aux_ld % 8) || (g.aux_bs % 8)) return fail(VMLP_EALIGN, "aux alignment");
+  } else {
+    p.aux = nullptr;
+  }
+
+  const int base_tiles = p.tiles_m * p.tiles_n * p.batch;
+  int split = 1;
+  if (epi == EPI_ATOMIC) {
+    if (!g.out_f32) return fail(VMLP_EINVAL, "EPI_ATOMIC needs out_f32");
+    split = g.split_k > 0 ? g.split_k : (dv.sms / base_tiles);
+    if (split < 1) split = 1;
+    if (split > p.k_blocks) split = p.k_blocks;
+    const int per = (p.k_blocks + split - 1) / split;
+    split = (p.k_blocks + per - 1) / per;     // no empty split
+  } else {
+    if (!g.D) return fail(VMLP_EINVAL, "null output");
+    rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 64, GEMM_BM);
+    if (rc) return rc;
+    if (epi == EPI_GELU) {
+      if (!g.D2) return fail(VMLP_EINVAL, "EPI_GELU needs D2");
+      rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 64, GEMM_BM);
+      if (rc) return rc;
+    }
+  }
+  p.split_k = split;
+  const long long total = (long long)base_tiles * split;
+  const int grid = (int)(total < dv.sms ? total : dv.sms);
+  if (bn == 256) return launch_gemm_bn<256>(epi, ta, tb, td, td2, p, grid, st);
+  return launch_gemm_bn<128>(epi, ta, tb, td, td2, p, grid, st);
+}
+
+int rw_grid(long long rows) {
+  const DeviceInfo& dv = device_info();
+  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
+  const long long cap = (long long)(dv.sms > 0 ? dv.sms : 148) * 8;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+int vpl_for(int C) { return (C / 8 + 31) / 32; }
+
+#define DISPATCH_VPL(C, ...)                                                     \
+  do {                                                                           \
+    const int vpl__ = vpl_for(C);                                                \
+    if (vpl__ <= 1) { constexpr int VPL = 1; __VA_ARGS__; }                      \
+    else if (vpl__ <= 2) { constexpr int VPL = 2; __VA_ARGS__; }                 \
+    else if (vpl__ <= 3) { constexpr int VPL = 3; __VA_ARGS__; }                 \
+    else if (vpl__ <= 4) { constexpr int VPL = 4; __VA_ARGS__; }                 \
+    else if (vpl__ <= 6) { constexpr int VPL = 6; __VA_ARGS__; }                 \
+    else if (vpl__ <= 8) { constexpr int VPL = 8; __VA_ARGS__; }                 \
+    else if (vpl__ <= 16) { constexpr int VPL = 16; __VA_ARGS__; }               \
+    else return fail(VMLP_EINVAL, "row length %d too large (max 4096)", C);      \
+  } while (0)
+
+typedef const __nv_bfloat16* cbf;
+typedef __nv_bfloat16* bf;
+
+// ------------------------------------------------------------------------------------------- GEMM arg helpers
+vmlp_operand opnd(const void* p, int64_t rows, int64_t cols, int64_t ld, int64_t bs, int major) {
+  vmlp_operand o;
+  o.ptr = p; o.rows = rows; o.cols = cols; o.ld = ld; o.batch_stride = bs; o.major = major;
+  return o;
+}
+vmlp_gemm_args gemm_args(int M, int N, int K, int batch, vmlp_operand A, vmlp_operand B, int epi) {
+  vmlp_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.batch = batch; g.A = A; g.B = B; g.epilogue = epi;
+  return g;
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+extern "C" {
+
+int vmlp_abi_version(void) { return 1; }
+const char* vmlp_last_error(void) { return g_err; }
+int vmlp_device_check(void) {
+  const DeviceInfo& dv = device_info();
+  if (!dv.ok) return fail(VMLP_ELAUNCH, "no CUDA device");
+  if (dv.cc_major != 10) return fail(VMLP_EARCH, "compute capability %d.%d is not sm_100", dv.cc_major, dv.cc_minor);
+  return VMLP_OK;
+}
+int vmlp_sm_count(void) { return device_info().sms; }
+
+int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream) {
+  if (!args) return fail(VMLP_EINVAL, "null args");
+  return gemm_impl(*args, static_cast<cudaStream_t>(stream));
+}
+
+int vmlp_layernorm_fwd(const void* x, int64_t x_ld, const void* gamma, const void* beta, void* y, int64_t y_ld,
+                       float* mean, float* rstd, int64_t rows, int32_t C, float eps, vmlp_stream_t stream) {
+  if (!x || !y || !gamma || !beta || rows <= 0 || C <= 0 || (C % 8)) return fail(VMLP_EINVAL, "layernorm_fwd args");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (x_ld % 8) || (y_ld % 8))
+    return fail(VMLP_EALIGN, "layernorm_fwd alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DISPATCH_VPL(C, (layernorm_fwd_kernel<VPL><<<rw_grid(rows), RW_THREADS, 0, st>>>(
+                      (cbf)x, x_ld, (cbf)gamma, (cbf)beta, (bf)y, y_ld, mean, rstd, rows, C, eps)));
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_layernorm_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const float* mean,
+                       const float* rstd, const void* gamma, const void* add, int64_t add_ld, void* dx,
+                       int64_t dx_ld, float* dgamma, float* dbeta, int64_t rows, int32_t C, vmlp_stream_t stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || rows <= 0 || (C % 8))
+    return fail(VMLP_EINVAL, "layernorm_bwd args");
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(gamma) || (add && !aligned16(add)) ||
+      (dy_ld % 8) || (x_ld % 8) || (dx_ld % 8) || (add_ld % 8))
+    return fail(VMLP_EALIGN, "layernorm_bwd alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo& dv = device_info();
+  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
+  const int grid = (int)(blocks < dv.sms * 4 ? blocks : dv.sms * 4);
+  DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>(
+                      (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
+                      dbeta, rows, C)));
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_affine_fwd(const void* x, const void* alpha, const void* beta, void* y, int64_t rows, int32_t C,
+                    vmlp_stream_t stream) {
+  if (!x || !y || !alpha || !beta || rows <= 0 || (C % 8)) return fail(VMLP_EINVAL, "affine_fwd args");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(alpha) || !aligned16(beta)) return fail(VMLP_EALIGN, "affine_fwd alignment");
+  const long long nvec = rows * (C / 8);
+  long long blocks = (nvec + RW_THREADS - 1) / RW_THREADS;
+  const long long cap = (long long)device_info().sms * 16;
+  affine_fwd_kernel<<<(int)(blocks < cap ? blocks : cap), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)x, (cbf)alpha, (cbf)beta, (bf)y, nvec, C / 8);
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_affine_bwd(const void* dy, const void* x, const void* alpha, const void* add, void* dx, float* dalpha,
+                    float* dbeta, int64_t rows, int32_t C, vmlp_stream_t stream) {
+  if (!dy || !x || !alpha || !dx || !dalpha || !dbeta || rows <= 0 || (C % 8)) return fail(VMLP_EINVAL, "affine_bwd args");
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(alpha) || (add && !aligned16(add)))
+    return fail(VMLP_EALIGN, "affine_bwd alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo& dv = device_info();
+  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
+  const int grid = (int)(blocks < dv.sms * 4 ? blocks : dv.sms * 4);
+  DISPATCH_VPL(C, (affine_bwd_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>(
+                      (cbf)dy, (cbf)x, (cbf)alpha, (cbf)add, (bf)dx, dalpha, dbeta, rows, C)));
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t rows, int32_t C,
+                vmlp_stream_t stream) {
+  if (!a || !out || rows <= 0 || (C % 8)) return fail(VMLP_EINVAL, "colsum args");
+  if (!aligned16(a) || (a_ld % 8) || (b && (!aligned16(b) || (b_ld % 8)))) return fail(VMLP_EALIGN, "colsum alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo& dv = device_info();
+  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
+  const int grid = (int)(blocks < dv.sms * 4 ? blocks : dv.sms * 4);
+  DISPATCH_VPL(C, (colsum_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>((cbf)a, a_ld, (cbf)b, b_ld,
+                                                                                        out, rows, C)));
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_rowsum_batched(const void* a, float* out, int64_t batch, int32_t rows_per_batch, int32_t C,
+                        vmlp_stream_t stream) {
+  if (!a || !out || batch <= 0 || rows_per_batch <= 0 || (C % 8)) return fail(VMLP_EINVAL, "rowsum args");
+  if (!aligned16(a)) return fail(VMLP_EALIGN, "rowsum alignment");
+  const long long rows = batch * rows_per_batch;
+  rowsum_batched_kernel<<<rw_grid(rows), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>((cbf)a, out, rows,
+                                                                                            rows_per_batch, C);
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vmlp_stream_t stream) {
+  if (!src || !dst || n <= 0) return fail(VMLP_EINVAL, "cast args");
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)device_info().sms * 16;
+  cast_f32_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (bf)dst, n);
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+int vmlp_add_bf16(const void* a, const void* b, void* dst, int64_t n, vmlp_stream_t stream) {
+  if (!a || !b || !dst || n <= 0 || (n % 8)) return fail(VMLP_EINVAL, "add args");
+  if (!aligned16(a) || !aligned16(b) || !aligned16(dst)) return fail(VMLP_EALIGN, "add alignment");
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = (long long)device_info().sms * 16;
+  add_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>((cbf)a, (cbf)b, (bf)dst, nvec);
+  CUDA_OK(cudaGetLastError());
+  return VMLP_OK;
+}
+
+// ============================================================================================ MLP-Mixer block
+static int mixer_check(const vmlp_mixer_params* p) {
+  if (!p) return fail(VMLP_EINVAL, "null params");
+  if (p->B <= 0 || p->N <= 0 || p->C <= 0 || p->Ds <= 0 || p->Dc <= 0) return fail(VMLP_EINVAL, "mixer dims");
+  if ((p->C % 8) || (p->Ds % 8) || (p->Dc % 8)) return fail(VMLP_EINVAL, "mixer: C, Ds, Dc must be multiples of 8");
+  return VMLP_OK;
+}
+static inline int pad8(int n) { return (n + 7) & ~7; }
+
+int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, const vmlp_mixer_saved* s,
+                         vmlp_stream_t stream) {
+  int rc = mixer_check(p);
+  if (rc) return rc;
+  if (!x || !y || !s) return fail(VMLP_EINVAL, "mixer fwd null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = p->B, N = p->N, C = p->C, Ds = p->Ds, Dc = p->Dc;
+  const long long R = (long long)B * N;
+  const int Np = pad8(N);
+  float* mean1 = s->stats; float* rstd1 = mean1 + R; float* mean2 = rstd1 + R; float* rstd2 = mean2 + R;
+
+  // ---- token mixing: u = x + W2t * gelu(W1t * LN1(x) + b1t) + b2t  (contraction over tokens, per image)
+  rc = vmlp_layernorm_fwd(x, C, p->ln1_w, p->ln1_b, s->xhat1, C, mean1, rstd1, R, C, p->eps, stream);
+  if (rc) return rc;
+  {
+    const long long n = (long long)Ds * Np;
+    pad_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((cbf)p->w1t, (bf)s->w1t_pad, Ds, N, Np);
+    CUDA_OK(cudaGetLastError());
+  }
+  {  // Z1[b] [Ds, C] = W1t [Ds, N] * Xhat1[b] [N, C] ; H1 = gelu(Z1)
+    vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(s->w1t_pad, Ds, N, Np, 0, 0),
+                                 opnd(s->xhat1, N, C, C, (long long)N * C, 1), VMLP_EPI_GELU);
+    g.D = s->z1; g.d_ld = C; g.d_bs = (long long)Ds * C;
+    g.D2 = s->h1; g.d2_ld = C; g.d2_bs = (long long)Ds * C;
+    g.bias = p->b1t; g.bias_mode = 2;
+    rc = gemm_impl(g, st);
+    if (rc) return rc;
+  }
+  {  // U[b] [N, C] = W2t [N, Ds] * H1[b] [Ds, C] + b2t[n] + X[b]
+    vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(p->w2t, N, Ds, Ds, 0, 0),
+                                 opnd(s->h1, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_RESID);
+    g.D = s->u; g.d_ld = C; g.d_bs = (long long)N * C;
+    g.bias = p->b2t; g.bias_mode = 2;
+    g.aux = x; g.aux_ld = C; g.aux_bs = (long long)N * C;
+    rc = gemm_impl(g, st);
+    if (rc) return rc;
+  }
+  // ---- channel mixing: y = u + gelu(LN2(u) W1c^T + b1c) W2c^T + b2c   (rows = B*N tokens)
+  rc = vmlp_layernorm_fwd(s->u, C, p->ln2_w, p->ln2_b, s->xhat2, C, mean2, rstd2, R, C, p->eps, stream);
+  if (rc) return rc;
+  {
+    vmlp_gemm_args g = gemm_args((int)R, Dc, C, 1, opnd(s->xhat2, R, C, C, 0, 0), opnd(p->w1c, Dc, C, C, 0, 0),
+                                 VMLP_EPI_GELU);
+    g.D = s->z2; g.d_ld = Dc; g.D2 = s->h2; g.d2_ld = Dc;
+    g.bias = p->b1c; g.bias_mode = 1;
+    rc = gemm_impl(g, st);
+    if (rc) return rc;
+  }
+  {
+    vmlp_gemm_args g = gemm_args((int)R, C, Dc, 1, opnd(s->h2, R, Dc, Dc, 0, 0), opnd(p->w2c, C, Dc, Dc, 0, 0),
+                                 VMLP_EPI_RESID);
+    g.D = y; g.d_ld = C;
+    g.bias = p->b2c; g.bias_mode = 1;
+    g.aux = s->u; g.aux_ld = C;
+    rc = gemm_impl(g, st);
+    if (rc) return rc;
+  }
+  return VMLP_OK;
+}
+
+int64_t vmlp_mixer_grad_elems(const vmlp_mixer_params* p) {
+  if (!p) return 0;
+  const int64_t N = p->N, C = p->C, Ds = p->Ds, Dc = p->Dc;
+  return 2 * C + Ds * N + Ds + N * Ds + N + 2 * C + Dc * C + Dc + C * Dc + C;
+}
+int64_t vmlp_mixer_bwd_workspace_elems(const vmlp_mixer_params* p) {
+  if (!p) return 0;
+  const int64_t R = (int64_t)p->B * p->N, C = p->C;
+  const int64_t tok = (int64_t)p->Ds * C, chn = (int64_t)p->N * p->Dc;
+  const int64_t hid = (int64_t)p->B * (tok > chn ? tok : chn);
+  return hid + 2 * R * C;   // dZ (max of both halves) + dXhat + dU
+}
+
+int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* dy, void* dx,
+                         const vmlp_mixer_saved* s, float* grads, void* workspace, int64_t workspace_elems,
+                         vmlp_stream_t stream) {
+  int rc = mixer_check(p);
+  if (rc) return rc;
+  if (!x || !dy || !dx || !s || !grads || !workspace) return fail(VMLP_EINVAL, "mixer bwd null pointer");
+  if (workspace_elems < vmlp_mixer_bwd_workspace_elems(p)) return fail(VMLP_EWORKSPACE, "mixer bwd workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int B = p->B, N = p->N, C = p->C, Ds = p->Ds, Dc = p->Dc;
+  const long long R = (long long)B * N;
+  const int Np = pad8(N);
+  float* mean1 = s->stats; float* rstd1 = mean1 + R; float* mean2 = rstd1 + R; float* rstd2 = mean2 + R;
+  // fp32 gradient accumulators, in vmlp_mixer_params order
+  float* g_ln1w = grads;            float* g_ln1b = g_ln1w + C;
+  float* g_w1t = g_ln1b + C;        float* g_b1t = g_w1t + (long long)Ds * N;
+  float* g_w2t = g_b1t + Ds;        float* g_b2t = g_w2t + (long long)N * Ds;
+  float* g_ln2w = g_b2t + N;        float* g_ln2b = g_ln2w + C;
+  float* g_w1c = g_ln2b + C;        float* g_b1c = g_w1c + (long long)Dc * C;
+  float* g_w2c = g_b1c + Dc;        float* g_b2c = g_w2c + (long long)C * Dc;
+  // bf16 workspace
+  bf ws = (bf)workspace;
+  const long long hid = vmlp_mixer_bwd_workspace_elems(p) - 2 * R * C;
+  bf dZ = ws; bf dXh = ws + hid; bf dU = dXh + R * C;
+
+  // ================= channel half:  y = u + FF(LN2(u))
+  {  // dZ2 = (dY * W2c) .* gelu'(Z2)            [R, Dc];  W2c [C, Dc] is the MN-major B operand
+    vmlp_gemm_args g = gemm_args((int)R, Dc, C, 1, opnd(dy, R, C, C, 0, 0), opnd(p->w2c, C, Dc, Dc, 0, 1), VMLP_EPI_DGELU);
+    g.D = dZ; g.d_ld = Dc; g.aux = s->z2; g.aux_ld = Dc;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  {  // dW2c [C, Dc] += dY^T * H2     (contraction over the R token rows: both operands MN-major)
+    vmlp_gemm_args g = gemm_args(C, Dc, (int)R, 1, opnd(dy, R, C, C, 0, 1), opnd(s->h2, R, Dc, Dc, 0, 1), VMLP_EPI_ATOMIC);
+    g.out_f32 = g_w2c; g.out_ld = Dc;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  if ((rc = vmlp_colsum(dy, C, nullptr, 0, g_b2c, R, C, stream))) return rc;
+  {  // dXhat2 = dZ2 * W1c                        [R, C];  W1c [Dc, C] MN-major B
+    vmlp_gemm_args g = gemm_args((int)R, C, Dc, 1, opnd(dZ, R, Dc, Dc, 0, 0), opnd(p->w1c, Dc, C, C, 0, 1), VMLP_EPI_STORE);
+    g.D = dXh; g.d_ld = C;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  {  // dW1c [Dc, C] += dZ2^T * Xhat2
+    vmlp_gemm_args g = gemm_args(Dc, C, (int)R, 1, opnd(dZ, R, Dc, Dc, 0, 1), opnd(s->xhat2, R, C, C, 0, 1), VMLP_EPI_ATOMIC);
+    g.out_f32 = g_w1c; g.out_ld = C;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  if ((rc = vmlp_colsum(dZ, Dc, nullptr, 0, g_b1c, R, Dc, stream))) return rc;
+  // dU = dY + LN2'(dXhat2)
+  if ((rc = vmlp_layernorm_bwd(dXh, C, s->u, C, mean2, rstd2, p->ln2_w, dy, C, dU, C, g_ln2w, g_ln2b, R, C, stream))) return rc;
+
+  // ================= token half:  u = x + TokenFF(LN1(x))
+  {
+    const long long n = (long long)Ds * Np;
+    pad_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((cbf)p->w1t, (bf)s->w1t_pad, Ds, N, Np);
+    CUDA_OK(cudaGetLastError());
+  }
+  {  // dZ1[b] [Ds, C] = (W2t^T [Ds, N] * dU[b] [N, C]) .* gelu'(Z1[b]);  W2t [N, Ds] is the MN-major A operand
+    vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(p->w2t, N, Ds, Ds, 0, 1), opnd(dU, N, C, C, (long long)N * C, 1), VMLP_EPI_DGELU);
+    g.D = dZ; g.d_ld = C; g.d_bs = (long long)Ds * C;
+    g.aux = s->z1; g.aux_ld = C; g.aux_bs = (long long)Ds * C;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  {  // dW2t [N, Ds] += sum_b dU[b] [N, C] * H1[b]^T [C, Ds]    (contraction over batch and channels)
+    vmlp_gemm_args g = gemm_args(N, Ds, C, B, opnd(dU, N, C, C, (long long)N * C, 0), opnd(s->h1, Ds, C, C, (long long)Ds * C, 0), VMLP_EPI_ATOMIC);
+    g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  if ((rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;
+  {  // dXhat1[b] [N, C] = W1t^T [N, Ds] * dZ1[b] [Ds, C];  padded W1t [Ds, Np] as MN-major A
+    vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(s->w1t_pad, Ds, N, Np, 0, 1), opnd(dZ, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_STORE);
+    g.D = dXh; g.d_ld = C; g.d_bs = (long long)N * C;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  {  // dW1t [Ds, N] += sum_b dZ1[b] [Ds, C] * Xhat1[b]^T [C, N]
+    vmlp_gemm_args g = gemm_args(Ds, N, C, B, opnd(dZ, Ds, C, C, (long long)Ds * C, 0), opnd(s->xhat1, N, C, C, (long long)N * C, 0), VMLP_EPI_ATOMIC);
+    g.contract_batch = 1; g.out_f32 = g_w1t; g.out_ld = N;
+    if ((rc = gemm_impl(g, st))) return rc;
+  }
+  if ((rc = vmlp_rowsum_batched(dZ, g_b1t, B, Ds, C, stream))) return rc;
+  // dX = dU + LN1'(dXhat1)
+  if ((rc = vmlp_layernorm_bwd(dXh, C, x, C, mean1, rstd1, p->ln1_w, dU, C, dx, C, g_ln1w, g_ln1b, R, C, stream))) return rc;
+  return VMLP_OK;
+}
+
+}  // extern "C"

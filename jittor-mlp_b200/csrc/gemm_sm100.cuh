@@ -1,0 +1,354 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (128B-swizzled tiles) -> 4-stage mbarrier ring -> tcgen05.mma (cta_group::1, 128xBNx16)
+//   -> double-buffered TMEM accumulators -> fused epilogue -> TMA store / fp32 red.add.
+//
+//   D[b][m, n] = epilogue( sum_k A[b][m, k] * B[b][n, k] )
+//
+// Both operands may be K-major (rows = M or N, contiguous K) or MN-major (rows = K, contiguous
+// M or N) -- the token-mixing GEMMs of the vision-MLP blocks consume [B, N, C] activations
+// directly as MN-major operands, so no permute/transposed copy is ever materialised
+// (reference: the Conv1d(k=1)-over-tokens trick, models_pytorch/mlp_mixer.py:34,37).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#pragma once
+#include "ptx.cuh"
+
+namespace vmlp {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_STAGE_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+constexpr int GEMM_STAGING_BYTES = GEMM_BM * 64 * 2;        // 128 rows x 64 bf16 cols = 16 KB
+
+enum GemmEpilogue : int {
+  EPI_STORE = 0,    // D = acc (+bias)                                       -> bf16 via TMA store
+  EPI_GELU = 1,     // D = acc + bias (pre-activation), D2 = gelu(D)         -> two bf16 TMA stores
+  EPI_RESID = 2,    // D = (acc + bias) * colscale + aux                     -> bf16 (aux = residual)
+  EPI_DGELU = 3,    // D = acc * gelu'(aux)                                  -> bf16 (aux = saved pre-activation)
+  EPI_ATOMIC = 4,   // out_f32[m, n] += acc                                  (split-K weight gradients)
+  EPI_MUL = 5,      // D = (acc + bias) * aux                                -> bf16 (gMLP spatial gate)
+  EPI_GELU_ONLY = 6 // D = gelu(acc + bias)                                  -> bf16 (no pre-activation saved)
+};
+
+struct GemmParams {
+  int M, N;              // logical rows / cols of one output matrix (bounds for aux loads / atomics)
+  int tiles_m, tiles_n;  // ceil(M/128), ceil(N/BN)
+  int batch;             // output batches (1 when K spans the batch)
+  int split_k;           // >= 1
+  int k_blocks;          // total 64-wide K blocks (summed over the batch when kbatch != 0)
+  int kpb;               // K blocks per batch element (== k_blocks unless kbatch != 0)
+  int last_ksteps;       // valid 16-wide k-steps in the last block of each kpb group (1..4)
+  int a_mn, b_mn;        // operand major-ness (0 = K-major, 1 = MN-major)
+  int a_batched, b_batched;
+  int kbatch;            // 1: contraction runs over (batch, k) -- token-mixing weight gradients
+  int bias_mode;         // 0 none, 1 per output column (n), 2 per output row (m)
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* colscale;  // optional per-column scale (ResMLP layer-scale), EPI_RESID only
+  const __nv_bfloat16* aux;       // residual / pre-activation / gate operand
+  long long aux_ld, aux_bs;       // row stride, batch stride (elements)
+  float* out_f32;                 // EPI_ATOMIC destination
+  long long out_ld;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int STAGE_B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
+  static constexpr int PIPE_BYTES = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFF = PIPE_BYTES;
+  static constexpr int BAR_OFF = STAGING_OFF + 2 * GEMM_STAGING_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
+                const GemmParams p) {
+  using L = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + L::STAGING_OFF;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tmem_full = empty_bar + GEMM_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
+    if (EPI == EPI_GELU) tma_prefetch_desc(&tmD2);
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BN);   // 2 accumulator stages x BN fp32 columns (power of two: 256 / 512)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_split = p.tiles_m * p.tiles_n * p.batch;
+  const int total_tiles = tiles_per_split * p.split_k;
+  const int kb_per_split = (p.k_blocks + p.split_k - 1) / p.split_k;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int n_idx = t % p.tiles_n; t /= p.tiles_n;
+        const int m_idx = t % p.tiles_m; t /= p.tiles_m;
+        const int b_idx = t % p.batch;
+        const int s_idx = t / p.batch;
+        const int kb0 = s_idx * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
+        const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const int kc = (kb % p.kpb) * GEMM_BK;
+          const int kbatch = p.kbatch ? (kb / p.kpb) : b_idx;
+          const int ba = p.a_batched ? kbatch : 0;
+          const int bb = p.b_batched ? kbatch : 0;
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
+          if (!p.a_mn) {
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc, m0, ba);   // box (64 k, 128 m)
+          } else {
+#pragma unroll
+            for (int a = 0; a < GEMM_BM / 64; ++a)                 // box (64 m, 64 k) per MN atom
+              tma_load_3d(sa + a * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + a * 64, kc, ba);
+          }
+          if (!p.b_mn) {
+            tma_load_3d(sb, &tmB, &full_bar[stage], kc, n0, bb);   // box (64 k, BN n)
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a)
+              tma_load_3d(sb + a * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + a * 64, kc, bb);
+          }
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p.a_mn, p.b_mn);
+      // K-major : 8-row groups 1024 B apart (SBO); one 128B swizzle atom along K (LBO unused).
+      // MN-major: 8-k groups 1024 B apart (SBO); 64-wide MN atoms BK*128 B apart (LBO).
+      const uint32_t a_lbo = p.a_mn ? GEMM_BK * 128 : 0, b_lbo = p.b_mn ? GEMM_BK * 128 : 0;
+      const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
+      uint32_t stage = 0, phase = 0;
+      int tc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+        const int s_idx = tile / tiles_per_split;
+        const int kb0 = s_idx * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
+        const int as = tc & 1;
+        mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + GEMM_STAGE_A_BYTES;
+          const int ksteps = ((kb % p.kpb) == p.kpb - 1) ? p.last_ksteps : (GEMM_BK / 16);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = umma_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;          // accumulator row owned by this thread
+    const bool leader = (threadIdx.x == 64);
+    int tc = 0;
+    uint32_t nstore = 0;                    // chunks stored so far (selects the staging buffer)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      int t = tile;
+      const int n_idx = t % p.tiles_n; t /= p.tiles_n;
+      const int m_idx = t % p.tiles_m; t /= p.tiles_m;
+      const int b_idx = t % p.batch;
+      const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
+      const int grow = m0 + row;
+      const bool row_ok = grow < p.M;
+      const int as = tc & 1;
+      mbar_wait(&tmem_full[as], (tc >> 1) & 1);
+      tc_fence_after();
+      float rbias = 0.f;
+      if (p.bias_mode == 2 && row_ok) rbias = __bfloat162float(p.bias[grow]);
+      const __nv_bfloat16* aux_row =
+          (p.aux != nullptr) ? p.aux + (long long)b_idx * p.aux_bs + (long long)grow * p.aux_ld : nullptr;
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col0 = n0 + c * 64;
+        if (col0 >= p.N) {
+          // fully out-of-range column chunk (ragged N): nothing to compute or store
+          if (c == BN / 64 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          continue;
+        }
+        uint8_t* st0 = staging + ((EPI == EPI_GELU) ? 0 : (nstore & 1) * GEMM_STAGING_BYTES);
+        ++nstore;
+        uint8_t* st1 = staging + GEMM_STAGING_BYTES;
+        if (EPI != EPI_ATOMIC) {
+          // the staging buffer about to be overwritten must have been drained by its TMA store
+          if (leader) {
+            if (EPI == EPI_GELU) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+          }
+          named_bar_sync(1, 128);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + as * BN + c * 64 + h * 32 + (uint32_t(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (c == BN / 64 - 1 && h == 1) {
+            // last TMEM read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          const int colh = col0 + h * 32;
+          if (EPI == EPI_ATOMIC) {
+            if (row_ok) {
+              float* orow = p.out_f32 + (long long)grow * p.out_ld;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (colh + j < p.N) red_add_f32(orow + colh + j, __uint_as_float(v[j]));
+            }
+            continue;
+          }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + rbias;
+          if (p.bias_mode == 1) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (colh + g * 8 < p.N) {
+                const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + colh + g * 8);
+                const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[g * 8 + 2 * e] += bf16lo(w[e]);
+                  f[g * 8 + 2 * e + 1] += bf16hi(w[e]);
+                }
+              }
+            }
+          }
+          if (EPI == EPI_RESID && p.colscale != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (colh + g * 8 < p.N) {
+                const uint4 sv = *reinterpret_cast<const uint4*>(p.colscale + colh + g * 8);
+                const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  f[g * 8 + 2 * e] *= bf16lo(w[e]);
+                  f[g * 8 + 2 * e + 1] *= bf16hi(w[e]);
+                }
+              }
+            }
+          }
+          uint32_t o[16], o2[16];
+          if (EPI == EPI_RESID || EPI == EPI_DGELU || EPI == EPI_MUL) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 av = make_uint4(0, 0, 0, 0);
+              if (row_ok && colh + g * 8 < p.N) av = ldg_nc_v4(aux_row + colh + g * 8);
+              const uint32_t w[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
+                const float a0 = bf16lo(w[e]), a1 = bf16hi(w[e]);
+                if (EPI == EPI_RESID) { x0 += a0; x1 += a1; }
+                if (EPI == EPI_MUL) { x0 *= a0; x1 *= a1; }
+                if (EPI == EPI_DGELU) {
+                  float d0, d1;
+                  gelu_erf(a0, &d0);
+                  gelu_erf(a1, &d1);
+                  x0 *= d0; x1 *= d1;
+                }
+                o[g * 4 + e] = pack_bf16x2(x0, x1);
+              }
+            }
+          } else if (EPI == EPI_GELU) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+              // gelu is applied to the bf16-rounded pre-activation that backward will re-read
+              o2[e] = pack_bf16x2(gelu_erf(bf16lo(o[e]), nullptr), gelu_erf(bf16hi(o[e]), nullptr));
+            }
+          } else if (EPI == EPI_GELU_ONLY) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              o[e] = pack_bf16x2(gelu_erf(f[2 * e], nullptr), gelu_erf(f[2 * e + 1], nullptr));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+          }
+          // staging tile = [128 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7) (matches SWIZZLE_128B)
+          const uint32_t srow = smem_u32(st0) + row * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = (h * 4 + g) ^ (row & 7);
+            st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
+            if (EPI == EPI_GELU)
+              st_shared_v4(smem_u32(st1) + row * 128 + chunk * 16,
+                           make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
+          }
+        }
+        if (EPI != EPI_ATOMIC) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_3d(&tmD, st0, col0, m0, b_idx);
+            if (EPI == EPI_GELU) tma_store_3d(&tmD2, st1, col0, m0, b_idx);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (EPI != EPI_ATOMIC && leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+}  // namespace vmlp

@@ -1,0 +1,316 @@
+// HBM-bound row-wise kernels around the GEMMs: LayerNorm fwd/bwd, per-channel affine,
+// column / batched-row reductions (bias gradients), pad / cast helpers.
+// One warp owns one row at a time; every global access is a 16-byte vector; column
+// partials stay in registers across the grid-stride loop and are flushed once per block.
+#pragma once
+#include "ptx.cuh"
+
+namespace vmlp {
+
+constexpr int RW_THREADS = 256;
+constexpr int RW_WARPS = RW_THREADS / 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                    pack_bf16x2(f[6], f[7]));
+}
+
+// Flush per-lane column partials (VPL vectors x 8 columns, lane-strided) of all warps of the block
+// into global fp32 with one red.add per column per block.
+template <int VPL>
+__device__ __forceinline__ void flush_col_partials(float (&acc)[VPL][8], float* out, int nvec, float* sh) {
+  // sh: [RW_WARPS][VPL*32*8] floats is too large for VPL=8 (64 KB); reduce warp by warp instead.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int w = 0; w < RW_WARPS; ++w) {
+    __syncthreads();
+    if (warp == w) {
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int idx = (v * 32 + lane) * 8 + e;
+          sh[idx] = (w == 0 ? 0.f : sh[idx]) + acc[v][e];
+        }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nvec * 8; i += RW_THREADS) red_add_f32(out + i, sh[i]);
+}
+
+// --------------------------------------------------------------------------- LayerNorm forward
+// y = (x - mean) * rstd * gamma + beta over the last axis (biased variance, eps inside sqrt):
+// torch.nn.LayerNorm semantics used by PreNormResidual (models_pytorch/mlp_mixer.py:6-13).
+template <int VPL>
+__global__ void __launch_bounds__(RW_THREADS)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, const __nv_bfloat16* __restrict__ gamma,
+                     const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long y_ld,
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int C,
+                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * RW_WARPS;
+  for (long long r = gw; r < rows; r += nw) {
+    float v[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        unpack8(ldg_nc_v4(x + r * x_ld + vi * 8), v[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[i][e];
+      }
+    }
+    const float mean = warp_sum(s) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (i * 32 + lane < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; ss += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float g[8], b[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), g);
+        unpack8(*reinterpret_cast<const uint4*>(beta + vi * 8), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * g[e] + b[e];
+        *reinterpret_cast<uint4*>(y + r * y_ld + vi * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- LayerNorm backward
+// dx = add + rstd * (g - mean_C(g) - xhat * mean_C(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 accumulators, red.add once per block)
+template <int VPL>
+__global__ void __launch_bounds__(RW_THREADS)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, const __nv_bfloat16* __restrict__ x,
+                     long long x_ld, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ add,
+                     long long add_ld, __nv_bfloat16* __restrict__ dx, long long dx_ld,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
+  extern __shared__ float sh[];
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * RW_WARPS;
+  float ag[VPL][8], ab[VPL][8], gm[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = i * 32 + lane;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; gm[i][e] = 0.f; }
+    if (vi < nvec) unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), gm[i]);
+  }
+  for (long long r = gw; r < rows; r += nw) {
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float g[VPL][8], xh[VPL][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float d[8], xv[8];
+        unpack8(ldg_nc_v4(dy + r * dy_ld + vi * 8), d);
+        unpack8(ldg_nc_v4(x + r * x_ld + vi * 8), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[i][e] = (xv[e] - mean) * rstd;
+          g[i][e] = d[e] * gm[i][e];
+          s1 += g[i][e];
+          s2 += g[i][e] * xh[i][e];
+          ag[i][e] += d[e] * xh[i][e];
+          ab[i][e] += d[e];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float o[8], a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = 0.f;
+        if (add) unpack8(ldg_nc_v4(add + r * add_ld + vi * 8), a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = a[e] + rstd * (g[i][e] - s1 - xh[i][e] * s2);
+        *reinterpret_cast<uint4*>(dx + r * dx_ld + vi * 8) = pack8(o);
+      }
+    }
+  }
+  flush_col_partials<VPL>(ag, dgamma, nvec, sh);
+  flush_col_partials<VPL>(ab, dbeta, nvec, sh);
+}
+
+// --------------------------------------------------------------------------- per-channel affine (ResMLP Aff)
+// y = x * alpha + beta (models_pytorch/res_mlp.py:11-19)
+__global__ void __launch_bounds__(RW_THREADS)
+affine_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ alpha,
+                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long nvec_total,
+                  int nvec_row) {
+  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < nvec_total;
+       i += (long long)gridDim.x * RW_THREADS) {
+    const int c = static_cast<int>(i % nvec_row) * 8;
+    float xv[8], a[8], b[8], o[8];
+    unpack8(ldg_nc_v4(x + i * 8), xv);
+    unpack8(*reinterpret_cast<const uint4*>(alpha + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(beta + c), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = xv[e] * a[e] + b[e];
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(o);
+  }
+}
+// dx = dy * alpha (+ add); dalpha += sum dy * x ; dbeta += sum dy
+template <int VPL>
+__global__ void __launch_bounds__(RW_THREADS)
+affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                  const __nv_bfloat16* __restrict__ alpha, const __nv_bfloat16* __restrict__ add,
+                  __nv_bfloat16* __restrict__ dx, float* __restrict__ dalpha, float* __restrict__ dbeta,
+                  long long rows, int C) {
+  extern __shared__ float sh[];
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * RW_WARPS;
+  float aa[VPL][8], ab[VPL][8], al[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = i * 32 + lane;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { aa[i][e] = 0.f; ab[i][e] = 0.f; al[i][e] = 0.f; }
+    if (vi < nvec) unpack8(*reinterpret_cast<const uint4*>(alpha + vi * 8), al[i]);
+  }
+  for (long long r = gw; r < rows; r += nw) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float d[8], xv[8], a[8], o[8];
+        unpack8(ldg_nc_v4(dy + r * C + vi * 8), d);
+        unpack8(ldg_nc_v4(x + r * C + vi * 8), xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = 0.f;
+        if (add) unpack8(ldg_nc_v4(add + r * C + vi * 8), a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          aa[i][e] += d[e] * xv[e];
+          ab[i][e] += d[e];
+          o[e] = d[e] * al[i][e] + a[e];
+        }
+        *reinterpret_cast<uint4*>(dx + r * C + vi * 8) = pack8(o);
+      }
+    }
+  }
+  flush_col_partials<VPL>(aa, dalpha, nvec, sh);
+  flush_col_partials<VPL>(ab, dbeta, nvec, sh);
+}
+
+// --------------------------------------------------------------------------- column sums  out[c] += sum_r (a[r,c] (* b[r,c]))
+template <int VPL>
+__global__ void __launch_bounds__(RW_THREADS)
+colsum_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bfloat16* __restrict__ b,
+              long long b_ld, float* __restrict__ out, long long rows, int C) {
+  extern __shared__ float sh[];
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * RW_WARPS;
+  float acc[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+  for (long long r = gw; r < rows; r += nw) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float d[8];
+        unpack8(ldg_nc_v4(a + r * a_ld + vi * 8), d);
+        if (b) {
+          float m[8];
+          unpack8(ldg_nc_v4(b + r * b_ld + vi * 8), m);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] *= m[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] += d[e];
+      }
+    }
+  }
+  flush_col_partials<VPL>(acc, out, nvec, sh);
+}
+
+// --------------------------------------------------------------------------- batched row sums
+// out[m] += sum_{b, c} a[b, m, c]   (token-mixing bias gradients: reductions over B*C)
+__global__ void __launch_bounds__(RW_THREADS)
+rowsum_batched_kernel(const __nv_bfloat16* __restrict__ a, float* __restrict__ out, long long rows_total,
+                      int rows_per_batch, int C) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * RW_WARPS;
+  for (long long r = gw; r < rows_total; r += nw) {
+    float s = 0.f;
+    for (int vi = lane; vi < nvec; vi += 32) {
+      float d[8];
+      unpack8(ldg_nc_v4(a + r * C + vi * 8), d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += d[e];
+    }
+    s = warp_sum(s);
+    if (lane == 0) red_add_f32(out + (r % rows_per_batch), s);
+  }
+}
+
+// --------------------------------------------------------------------------- small helpers
+// dst[r, 0:cols] = src[r, 0:cols], dst[r, cols:ld_dst] = 0  (makes the row pitch a multiple of 16 B for TMA)
+__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
+                                int cols, int ld_dst) {
+  const long long n = (long long)rows * ld_dst;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = static_cast<int>(i / ld_dst), c = static_cast<int>(i % ld_dst);
+    dst[i] = (c < cols) ? src[(long long)r * cols + c] : __float2bfloat16(0.f);
+  }
+}
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16(src[i]);
+}
+// dst[i] = a[i] + b[i]
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ dst, long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(ldg_nc_v4(a + i * 8), x);
+    unpack8(ldg_nc_v4(b + i * 8), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    *reinterpret_cast<uint4*>(dst + i * 8) = pack8(x);
+  }
+}
+
+}  // namespace vmlp

@@ -1,0 +1,53 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference modules (authoring container only).
+
+TEST INFRASTRUCTURE.  Usage: python -m oracle.gen_golden   (needs /root/reference; see oracle/ref_loader.py)
+Each fixture holds: ctor kwargs, a randomised fp32 state_dict (every parameter perturbed),
+a seeded input, the reference forward output (train() mode, fp32, CPU) and the autograd gradients of
+loss = out.square().mean() w.r.t. the input and every parameter.
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader as R  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+CASES = {
+    # name: (module, class, kwargs, input shape)
+    "mixer_tiny": ("mlp_mixer", "MLPMixerForImageClassification",
+                   dict(d_model=64, depth=2, image_size=32, patch_size=8, num_classes=10), (2, 3, 32, 32)),
+    "mixer_ragged": ("mlp_mixer", "MLPMixerForImageClassification",
+                     dict(d_model=72, depth=1, image_size=(48, 40), patch_size=8, num_classes=7, expansion_factor=4),
+                     (3, 3, 48, 40)),
+    "resmlp_tiny": ("res_mlp", "ResMLPForImageClassification",
+                    dict(d_model=64, depth=2, image_size=32, patch_size=8, num_classes=10), (2, 3, 32, 32)),
+    "gmlp_tiny": ("g_mlp", "gMLPForImageClassification",
+                  dict(image_size=32, patch_size=8, num_classes=10, d_model=64, d_ffn=128, depth=2), (2, 3, 32, 32)),
+}
+
+
+def make(name):
+    mod, cls, kwargs, xshape = CASES[name]
+    torch.manual_seed(0)
+    model = getattr(R.load(mod), cls)(**kwargs)
+    R.randomize_(model, 0.1, seed=1)
+    model.train()
+    x = torch.randn(*xshape, generator=torch.Generator().manual_seed(2)).requires_grad_(True)
+    out = model(x)
+    loss = out.square().mean()
+    loss.backward()
+    fx = dict(module=mod, cls=cls, kwargs=kwargs,
+              state_dict={k: v.detach().clone() for k, v in model.state_dict().items()},
+              x=x.detach().clone(), out=out.detach().clone(), dx=x.grad.clone(),
+              grads={k: (p.grad.clone() if p.grad is not None else None) for k, p in model.named_parameters()})
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(name, tuple(out.shape), f"{os.path.getsize(os.path.join(OUT, name + '.pt')) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    for n in (sys.argv[1:] or CASES):
+        make(n)
