@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- images/s, forward+backward, of the fused vision-MLP path on N B200s of one node.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W            (N == 1)
+                    python -m torch.distributed.run ... bench.py --gpus N ... (N  > 1, one rank per GPU, NCCL)
+                    python bench.py --impl reference ...                      (the reference algorithm on host cores)
+Prints ONE JSON line on rank 0.  Workload = BASELINE.json configs[1]: MLP-Mixer-B/16 (reference kwargs
+d_model=768, depth=12 -> N 196, Ds 784, C 768, Dc 3072), 224x224, bf16, batch 256 per GPU,
+synthetic images, random-init weights.  A "step" = model forward + backward (+ one NCCL gradient average for N > 1);
+the reference has no optimizer (model zoo only), so none is timed.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PRESETS = {
+    # name: (class, kwargs, oracle forward fn name, fwd GFLOP/img, stem GFLOP/img)
+    "mixer_b16": ("MLPMixerForImageClassification", dict(d_model=768, depth=12), "mixer_forward", 28.094, 0.2312),
+    "mixer_l16": ("MLPMixerForImageClassification", dict(d_model=1024, depth=24), "mixer_forward", 94.336, 0.3083),
+    "mixer_s16": ("MLPMixerForImageClassification", dict(d_model=512, depth=8), "mixer_forward", 9.249, 0.1541),
+}
+METRIC = "images/sec fwd+bwd MLP-Mixer-B/16 224px"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    m = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    m = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if m & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def build_model(name, device):
+    import jittor_mlp_b200 as J
+    cls, kw, _, _, _ = PRESETS[name]
+    torch.manual_seed(0)
+    return getattr(J, cls)(**kw).to(device).bfloat16().train()
+
+
+def loss_fn(out):
+    return out.float().square().mean()
+
+
+def timed_steps(step, steps, warmup, barrier):
+    for _ in range(warmup):
+        step()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    return e0.elapsed_time(e1) / 1e3   # seconds on the device
+
+
+def time_kernel(fn, iters=12, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3 / iters
+
+
+def kernel_rooflines(B, N, C, Ds, Dc, pk):
+    """Time every GEMM of one MixerBlock stand-alone (operands >> L2, CUDA events on the launching stream) and
+    return per-kernel achieved TFLOP/s; algorithmic FLOPs = 2*M*N*K at the true (unpadded) dims."""
+    from jittor_mlp_b200 import _lib as L, ops
+    dev = "cuda"
+    bf = lambda *s: torch.randn(*s, device=dev, dtype=torch.bfloat16) * 0.05
+    R = B * N
+    X, Hc, Zc = bf(R, C), bf(R, Dc), bf(R, Dc)
+    W1c, W2c, b1c, b2c = bf(Dc, C), bf(C, Dc), bf(Dc), bf(C)
+    out = torch.empty(R, C, device=dev, dtype=torch.bfloat16)
+    gW = torch.zeros(Dc, C, device=dev, dtype=torch.float32)
+    Xt, Ht, Zt = bf(B, N, C), bf(B, Ds, C), bf(B, Ds, C)
+    Np = (N + 7) // 8 * 8
+    W1p, W2t, b1t, b2t = bf(Ds, Np), bf(N, Ds), bf(Ds), bf(N)
+    outt = torch.empty(B, N, C, device=dev, dtype=torch.bfloat16)
+    gWt = torch.zeros(N, Ds, device=dev, dtype=torch.float32)
+    w1p_k = L.Operand(W1p.data_ptr(), Ds, N, Np, 0, 0)
+    w1p_mn = L.Operand(W1p.data_ptr(), Ds, N, Np, 0, 1)
+    cases = {
+        # name: (callable, algorithmic flops, launches of this kind per block fwd+bwd)
+        "chan_fc1_gelu<256,GELU>": (lambda: ops.gemm(R, Dc, C, ops.operand(X, 0), ops.operand(W1c, 0), L.EPI_GELU, D=Zc, D2=Hc, bias=b1c, bias_mode=1), 2.0 * R * Dc * C),
+        "chan_fc2_resid<256,RESID>": (lambda: ops.gemm(R, C, Dc, ops.operand(Hc, 0), ops.operand(W2c, 0), L.EPI_RESID, D=out, bias=b2c, bias_mode=1, aux=X), 2.0 * R * Dc * C),
+        "chan_dgrad2_dgelu<256,DGELU>": (lambda: ops.gemm(R, Dc, C, ops.operand(X, 0), ops.operand(W2c, 1), L.EPI_DGELU, D=Hc, aux=Zc), 2.0 * R * Dc * C),
+        "chan_dgrad1<256,STORE>": (lambda: ops.gemm(R, C, Dc, ops.operand(Hc, 0), ops.operand(W1c, 1), L.EPI_STORE, D=out), 2.0 * R * Dc * C),
+        "chan_wgrad<256,ATOMIC>": (lambda: ops.gemm(Dc, C, R, ops.operand(Hc, 1), ops.operand(X, 1), L.EPI_ATOMIC, out_f32=gW), 2.0 * R * Dc * C),
+        "tok_fc1_gelu<256,GELU>": (lambda: ops.gemm(Ds, C, N, w1p_k, ops.operand(Xt, 1), L.EPI_GELU, batch=B, D=Zt, D2=Ht, bias=b1t, bias_mode=2), 2.0 * B * Ds * C * N),
+        "tok_fc2_resid<256,RESID>": (lambda: ops.gemm(N, C, Ds, ops.operand(W2t, 0), ops.operand(Ht, 1), L.EPI_RESID, batch=B, D=outt, bias=b2t, bias_mode=2, aux=Xt), 2.0 * B * Ds * C * N),
+        "tok_dgrad2_dgelu<256,DGELU>": (lambda: ops.gemm(Ds, C, N, ops.operand(W2t, 1), ops.operand(Xt, 1), L.EPI_DGELU, batch=B, D=Ht, aux=Zt), 2.0 * B * Ds * C * N),
+        "tok_dgrad1<256,STORE>": (lambda: ops.gemm(N, C, Ds, w1p_mn, ops.operand(Ht, 1), L.EPI_STORE, batch=B, D=outt), 2.0 * B * Ds * C * N),
+        "tok_wgrad<256,ATOMIC>": (lambda: ops.gemm(N, Ds, C, ops.operand(Xt, 0), ops.operand(Ht, 0), L.EPI_ATOMIC, batch=B, contract_batch=True, out_f32=gWt), 2.0 * B * Ds * C * N),
+    }
+    res = {}
+    for k, (fn, flops) in cases.items():
+        t = time_kernel(fn)
+        res[k] = {"ms": round(t * 1e3, 4), "tflops": round(flops / t / 1e12, 1),
+                  "frac_of_sustained_peak": round(flops / t / 1e12 / pk["bf16_tflops_sustained"], 3)}
+    return res
+
+
+def cpu_port_images_per_s(name, batch, iters, warm=1):
+    """The oracle restatement (reference algorithm, fp32, autograd) on the host cores: the reported CPU baseline."""
+    from oracle import restate
+    import jittor_mlp_b200 as J
+    cls, kw, fwd, _, _ = PRESETS[name]
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    m = getattr(J, cls)(**kw)                       # parameter container only; nothing of the product runs here
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    restate.USE_ATEN = True     # same ATen primitives as the reference modules (conv1d / layer_norm / gelu)
+    fn = getattr(restate, fwd)
+    ts = []
+    for i in range(warm + iters):
+        t0 = time.perf_counter()
+        out = fn(sd, x, kw["depth"])
+        out.square().mean().backward()
+        for v in sd.values():
+            v.grad = None
+        if i >= warm:
+            ts.append(time.perf_counter() - t0)
+    return batch * len(ts) / sum(ts), sum(ts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    batch = max(1, min(32, int(round(100.0 * 6.0 / max(1, K + W)))))   # ~100 s of host work in total
+    ips, secs = cpu_port_images_per_s(args.model, batch, K, warm=W)
+    cores = os.cpu_count() or 1
+    sample = f"{K} timed fwd+bwd steps of batch {batch} (after {W} warm-up), fp32, torch {torch.__version__}, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": round(secs / K * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} fwd+bwd 224x224 (reference algorithm restated in oracle/restate.py, host CPU)",
+                       "batch_per_step": batch},
+            "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="mixer_b16", choices=sorted(PRESETS))
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+
+    from jittor_mlp_b200 import _lib as L, dp
+    L.check(L.lib().vmlp_device_check())
+    pk, pk_src = peaks()
+    model = build_model(args.model, dev)
+    ddp = dp.DataParallel(model)
+    B = args.batch
+    g = torch.Generator().manual_seed(1 + rank)
+    x_host = torch.randn(B, 3, 224, 224, generator=g).bfloat16().pin_memory()
+    x_dev = x_host.to(dev)
+
+    def step_resident():
+        model.zero_grad(set_to_none=True)
+        return ddp.step_fwd_bwd(x_dev, loss_fn)
+
+    def step_e2e():
+        model.zero_grad(set_to_none=True)
+        xb = x_host.to(dev, non_blocking=True)           # H2D of this step's images from pinned host memory
+        return float(ddp.step_fwd_bwd(xb, loss_fn).item())   # D2H read of the loss
+
+    n0 = L.lib().vmlp_launch_count()
+    step_resident()
+    launches_per_step = L.lib().vmlp_launch_count() - n0
+
+    with ClockSampler(local) as cs:
+        t = timed_steps(step_resident, args.steps, args.warmup, barrier)
+    t_e2e = timed_steps(step_e2e, args.steps, args.warmup, barrier)
+    if world > 1:
+        tt = torch.tensor([t, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t, t_e2e = float(tt[0]), float(tt[1])
+    value = world * B * args.steps / t
+    e2e = world * B * args.steps / t_e2e
+
+    line = None
+    if rank == 0:
+        cls, kw, _, gf_fwd, gf_stem = PRESETS[args.model]
+        flops_img = 3.0 * (gf_fwd - gf_stem) + 2.0 * gf_stem          # fwd+bwd = 3x fwd, stem 2x (no input grad)
+        line = {"metric": METRIC if args.model == "mixer_b16" else f"images/sec fwd+bwd {args.model} 224px",
+                "value": round(value, 1), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 3), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.model} ({cls}{kw}) fwd+bwd, 224x224, batch {B}/GPU, bf16 params+activations, fp32 accumulate",
+                           "global_batch": B * world, "parallelism": f"dp{world}",
+                           "l2": "per-step working set (>= 18 GB of activations) >> 126 MB L2; no flush needed"},
+                "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 2,
+                        "d2h_bytes_per_step": 4, "ms_per_step": round(t_e2e / args.steps * 1e3, 3)},
+                "gpu_launches": int(launches_per_step * args.steps),
+                "gpu_launches_per_step": int(launches_per_step),
+                "clocks": cs.summary(),
+                "model_tflops": round(value / world * flops_img / 1e3, 1),
+                "model_frac_of_sustained_peak": round(value / world * flops_img / 1e3 / pk["bf16_tflops_sustained"], 3)}
+    if rank == 0 and not args.no_kernels:
+        del ddp
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
+        C, depth = kw["d_model"], kw["depth"]
+        ks = kernel_rooflines(B, 196, C, 784, 4 * C, pk)
+        dom = max(ks, key=lambda k: ks[k]["ms"] * (2 if "wgrad" in k else 1))
+        flops = ks[dom]["tflops"] * ks[dom]["ms"] * 1e9
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_sm100 " + dom, "achieved": ks[dom]["tflops"],
+                            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": round(ks[dom]["tflops"] / pk["bf16_tflops_sustained"], 3), "traffic": None,
+                            "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed in a back-to-back loop)",
+                            "algorithmic_flops_per_launch": flops}
+        line["kernels"] = ks
+        blk_ms = sum(v["ms"] * (2 if "wgrad" in k else 1) for k, v in ks.items())
+        line["block_gemm_ms"] = round(blk_ms, 3)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, secs = cpu_port_images_per_s(args.model, 16, 2)
+        line["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"2 timed fwd+bwd steps of batch 16 (1 warm-up), oracle/restate.py fp32, {secs:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

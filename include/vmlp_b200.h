@@ -44,6 +44,7 @@ int vmlp_abi_version(void);
 const char* vmlp_last_error(void);          /* thread-local message for the last failing call */
 int vmlp_device_check(void);                /* VMLP_OK iff current device is compute capability 10.x */
 int vmlp_sm_count(void);
+int64_t vmlp_launch_count(void);             /* kernels launched by this library in this process */
 
 /* --------------------------------------------------------------------------------------------
  * Generic fused GEMM (the building block of every mixing MLP):

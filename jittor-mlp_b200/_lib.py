@@ -85,6 +85,7 @@ SYMBOLS = [
     ("vmlp_last_error", ctypes.c_char_p, []),
     ("vmlp_device_check", c_int32, []),
     ("vmlp_sm_count", c_int32, []),
+    ("vmlp_launch_count", c_int64, []),
     ("vmlp_gemm_bf16", c_int32, [_P(GemmArgs), c_void_p]),
     ("vmlp_layernorm_fwd", c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                      c_int64, c_int32, c_float, c_void_p]),

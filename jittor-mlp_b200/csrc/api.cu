@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 using namespace vmlp;
@@ -14,6 +15,7 @@ using namespace vmlp;
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};   // kernels launched by this library (bench.py reports it)
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -102,6 +104,7 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   }
   kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(ta, tb, td, td2, p);
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -266,6 +269,7 @@ int vmlp_device_check(void) {
   return VMLP_OK;
 }
 int vmlp_sm_count(void) { return device_info().sms; }
+int64_t vmlp_launch_count(void) { return g_launches.load(); }
 
 int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream) {
   if (!args) return fail(VMLP_EINVAL, "null args");
@@ -281,6 +285,7 @@ int vmlp_layernorm_fwd(const void* x, int64_t x_ld, const void* gamma, const voi
   DISPATCH_VPL(C, (layernorm_fwd_kernel<VPL><<<rw_grid(rows), RW_THREADS, 0, st>>>(
                       (cbf)x, x_ld, (cbf)gamma, (cbf)beta, (bf)y, y_ld, mean, rstd, rows, C, eps)));
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -300,6 +305,7 @@ int vmlp_layernorm_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
                       (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
                       dbeta, rows, C)));
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -313,6 +319,7 @@ int vmlp_affine_fwd(const void* x, const void* alpha, const void* beta, void* y,
   affine_fwd_kernel<<<(int)(blocks < cap ? blocks : cap), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)x, (cbf)alpha, (cbf)beta, (bf)y, nvec, C / 8);
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -328,6 +335,7 @@ int vmlp_affine_bwd(const void* dy, const void* x, const void* alpha, const void
   DISPATCH_VPL(C, (affine_bwd_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>(
                       (cbf)dy, (cbf)x, (cbf)alpha, (cbf)add, (bf)dx, dalpha, dbeta, rows, C)));
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -342,6 +350,7 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
   DISPATCH_VPL(C, (colsum_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>((cbf)a, a_ld, (cbf)b, b_ld,
                                                                                         out, rows, C)));
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -353,6 +362,7 @@ int vmlp_rowsum_batched(const void* a, float* out, int64_t batch, int32_t rows_p
   rowsum_batched_kernel<<<rw_grid(rows), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>((cbf)a, out, rows,
                                                                                             rows_per_batch, C);
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -362,6 +372,7 @@ int vmlp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vmlp_stream_t 
   const long long cap = (long long)device_info().sms * 16;
   cast_f32_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, (bf)dst, n);
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -373,6 +384,7 @@ int vmlp_add_bf16(const void* a, const void* b, void* dst, int64_t n, vmlp_strea
   const long long cap = (long long)device_info().sms * 16;
   add_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>((cbf)a, (cbf)b, (bf)dst, nvec);
   CUDA_OK(cudaGetLastError());
+  ++g_launches;
   return VMLP_OK;
 }
 
@@ -403,6 +415,7 @@ int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, con
     const long long n = (long long)Ds * Np;
     pad_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((cbf)p->w1t, (bf)s->w1t_pad, Ds, N, Np);
     CUDA_OK(cudaGetLastError());
+    ++g_launches;
   }
   {  // Z1[b] [Ds, C] = W1t [Ds, N] * Xhat1[b] [N, C] ; H1 = gelu(Z1)
     vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(s->w1t_pad, Ds, N, Np, 0, 0),
@@ -513,6 +526,7 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     const long long n = (long long)Ds * Np;
     pad_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((cbf)p->w1t, (bf)s->w1t_pad, Ds, N, Np);
     CUDA_OK(cudaGetLastError());
+    ++g_launches;
   }
   {  // dZ1[b] [Ds, C] = (W2t^T [Ds, N] * dU[b] [N, C]) .* gelu'(Z1[b]);  W2t [N, Ds] is the MN-major A operand
     vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(p->w2t, N, Ds, Ds, 0, 1), opnd(dU, N, C, C, (long long)N * C, 1), VMLP_EPI_DGELU);

@@ -1,0 +1,82 @@
+"""Data-parallel wrapper: one process per GPU, batch sharded across ranks, ONE gradient all-reduce per step.
+
+The reference has no distributed code; no block mixes samples (ConvMixer's BatchNorm aside),
+so the path shards along the batch axis with a single exchange: the gradient average.  The
+fused block backward hands back all parameter gradients of a block as views of one flat bf16 buffer; with an
+active DataParallel context that buffer is all-reduced in place on NCCL's stream as soon as the block's
+backward has been enqueued, so the exchange of block i overlaps the backward of blocks i-1 .. 0.
+Parameters outside the fused blocks (stem / head) go in one more flat bucket at the end.
+"""
+import torch
+import torch.distributed as dist
+
+_active = None
+
+
+def active():
+    return _active
+
+
+class DataParallel(torch.nn.Module):
+    def __init__(self, module, process_group=None):
+        super().__init__()
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self._pending = []      # (work handle, flat bucket tensor)
+        self._bucketed = set()  # data_ptrs already covered by an in-flight bucket
+        if self.world > 1:
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=0, group=process_group)   # identical replicas
+
+    def forward(self, *a, **kw):
+        return self.module(*a, **kw)
+
+    # called by the fused block backward (ops.py) with the block's flat bf16 gradient buffer
+    def reduce_bucket_async(self, flat):
+        if self.world == 1:
+            return
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        self._pending.append((work, flat))
+
+    def __enter__(self):
+        global _active
+        _active = self
+        self._pending.clear()
+        return self
+
+    def __exit__(self, *exc):
+        global _active
+        _active = None
+        return False
+
+    def finish(self):
+        """Reduce what the block buckets did not cover, then join the communication stream."""
+        if self.world == 1:
+            return
+        covered = []
+        for _, flat in self._pending:
+            covered.append((flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()))
+        rest = []
+        for p in self.module.parameters():
+            if p.grad is None:
+                continue   # never-used parameters have no gradient on any rank
+            a = p.grad.data_ptr()
+            if not any(lo <= a < hi for lo, hi in covered):
+                rest.append(p)
+        if rest:
+            flat = torch._utils._flatten_dense_tensors([p.grad for p in rest])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            for p, g in zip(rest, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in rest])):
+                p.grad.copy_(g)
+        for work, _ in self._pending:
+            work.wait()          # makes the current stream wait for the NCCL stream
+        self._pending.clear()
+
+    def step_fwd_bwd(self, x, loss_fn):
+        """One data-parallel fwd+bwd on this rank's shard; gradients are averaged over ranks on return."""
+        with self:
+            loss = loss_fn(self.module(x))
+            loss.backward()
+            self.finish()
+        return loss

@@ -157,6 +157,9 @@ class MixerBlockFn(torch.autograd.Function):
         L.check(lib.vmlp_mixer_block_bwd(ctypes.byref(p), x.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                                          ctypes.byref(s), grads.data_ptr(), ws.data_ptr(), n_ws, L.stream_ptr()))
         gb = cast_f32_to_bf16(grads)
+        from . import dp
+        if dp.active() is not None:       # data parallel: average this block's gradients while backward continues
+            dp.active().reduce_bucket_async(gb)
         outs, off = [], 0
         for t in params:
             outs.append(gb[off:off + t.numel()].view(t.shape))

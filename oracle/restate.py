@@ -12,16 +12,33 @@ import torch
 import torch.nn.functional as F
 
 
+# bench.py's CPU-baseline legs flip this to time the SAME ATen primitives the reference modules dispatch to
+# (conv1d / layer_norm / gelu); the parity tests keep the elementary formulas and check both agree.
+USE_ATEN = False
+
+
 def gelu(z):
     """Exact erf GELU = nn.GELU() default (mlp_mixer.py:21)."""
+    if USE_ATEN:
+        return F.gelu(z)
     return 0.5 * z * (1.0 + torch.erf(z / math.sqrt(2.0)))
 
 
 def layer_norm(x, w, b, eps=1e-5):
     """nn.LayerNorm over the last axis, biased variance (mlp_mixer.py:10)."""
+    if USE_ATEN:
+        return F.layer_norm(x, (x.shape[-1],), w, b, eps)
     mu = x.mean(-1, keepdim=True)
     var = ((x - mu) ** 2).mean(-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def token_mix(w, x, bias):
+    """nn.Conv1d(N_in, N_out, kernel_size=1) applied to [B, N_in, C] (mlp_mixer.py:34,37): contraction over tokens.
+    w is the Conv1d weight [N_out, N_in, 1]."""
+    if USE_ATEN:
+        return F.conv1d(x, w, bias)
+    return torch.einsum("mn,bnc->bmc", w[:, :, 0], x) + bias[None, :, None]
 
 
 # ----------------------------------------------------------------------------------------------- MLP-Mixer
@@ -31,11 +48,9 @@ def mixer_block(sd, pre, x):
     token half  (mlp_mixer.py:12-13,19-25,37): Conv1d(k=1) over the token axis == W[m, n] contraction over n.
     channel half (mlp_mixer.py:38): Linear over channels.
     """
-    w1t = sd[pre + "0.fn.net.0.weight"][:, :, 0]   # [Ds, N]
-    w2t = sd[pre + "0.fn.net.3.weight"][:, :, 0]   # [N, Ds]
     xh = layer_norm(x, sd[pre + "0.norm.weight"], sd[pre + "0.norm.bias"])
-    z1 = torch.einsum("mn,bnc->bmc", w1t, xh) + sd[pre + "0.fn.net.0.bias"][None, :, None]
-    u = x + torch.einsum("nm,bmc->bnc", w2t, gelu(z1)) + sd[pre + "0.fn.net.3.bias"][None, :, None]
+    z1 = token_mix(sd[pre + "0.fn.net.0.weight"], xh, sd[pre + "0.fn.net.0.bias"])      # [B, Ds, C]
+    u = x + token_mix(sd[pre + "0.fn.net.3.weight"], gelu(z1), sd[pre + "0.fn.net.3.bias"])
     uh = layer_norm(u, sd[pre + "1.norm.weight"], sd[pre + "1.norm.bias"])
     z2 = uh @ sd[pre + "1.fn.net.0.weight"].t() + sd[pre + "1.fn.net.0.bias"]
     return u + gelu(z2) @ sd[pre + "1.fn.net.3.weight"].t() + sd[pre + "1.fn.net.3.bias"]
@@ -61,8 +76,7 @@ def mixer_forward(sd, x, depth):
 def resmlp_block(sd, pre, x):
     """MLPblock.forward (res_mlp.py:52-57): the residual is taken AFTER the pre-affine."""
     a = x * sd[pre + "pre_affine.alpha"] + sd[pre + "pre_affine.beta"]
-    wt = sd[pre + "token_mix.weight"][:, :, 0]     # [N, N]
-    t = a + sd[pre + "gamma_1"] * (torch.einsum("mn,bnc->bmc", wt, a) + sd[pre + "token_mix.bias"][None, :, None])
+    t = a + sd[pre + "gamma_1"] * token_mix(sd[pre + "token_mix.weight"], a, sd[pre + "token_mix.bias"])
     u = t * sd[pre + "post_affine.alpha"] + sd[pre + "post_affine.beta"]
     z = u @ sd[pre + "ff.net.0.weight"].t() + sd[pre + "ff.net.0.bias"]
     return u + sd[pre + "gamma_2"] * (gelu(z) @ sd[pre + "ff.net.3.weight"].t() + sd[pre + "ff.net.3.bias"])
@@ -83,8 +97,7 @@ def gmlp_block(sd, pre, x):
              + sd[pre + "channel_proj1.bias"])
     u, v = z.chunk(2, dim=-1)
     v = layer_norm(v, sd[pre + "sgu.norm.weight"], sd[pre + "sgu.norm.bias"])
-    ws = sd[pre + "sgu.spatial_proj.weight"][:, :, 0]   # [N, N]
-    v = torch.einsum("mn,bnf->bmf", ws, v) + sd[pre + "sgu.spatial_proj.bias"][None, :, None]
+    v = token_mix(sd[pre + "sgu.spatial_proj.weight"], v, sd[pre + "sgu.spatial_proj.bias"])
     return (u * v) @ sd[pre + "channel_proj2.weight"].t() + sd[pre + "channel_proj2.bias"] + x
 
 

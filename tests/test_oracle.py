@@ -53,3 +53,15 @@ def test_config1_mixer_s16_cpu_plumbing():
     x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         assert restate.rel_l2(restate.mixer_forward(model.state_dict(), x, 8), model(x)) < 1e-4
+
+
+def test_aten_fast_path_of_the_port_equals_the_elementary_restatement(golden):
+    """bench.py times the port with USE_ATEN=True; it must be the same function."""
+    fx = golden("mixer_tiny")
+    a = restate.mixer_forward(fx["state_dict"], fx["x"], fx["kwargs"]["depth"])
+    restate.USE_ATEN = True
+    try:
+        b = restate.mixer_forward(fx["state_dict"], fx["x"], fx["kwargs"]["depth"])
+    finally:
+        restate.USE_ATEN = False
+    assert restate.rel_l2(b, a) < 1e-5
