@@ -99,10 +99,10 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::TOTAL));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, EPI>::TOTAL));
     attr_set[dev & 63] = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::TOTAL, st>>>(ta, tb, td, td2, p);
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN, EPI>::TOTAL, st>>>(ta, tb, td, td2, p);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -203,11 +203,11 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
     split = (p.k_blocks + per - 1) / per;     // no empty split
   } else {
     if (!g.D) return fail(VMLP_EINVAL, "null output");
-    rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 64, GEMM_BM);
+    rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 64, 32);   // per-warp store box: 64 cols x 32 rows
     if (rc) return rc;
     if (epi == EPI_GELU) {
       if (!g.D2) return fail(VMLP_EINVAL, "EPI_GELU needs D2");
-      rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 64, GEMM_BM);
+      rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 64, 32);
       if (rc) return rc;
     }
   }
@@ -300,8 +300,8 @@ int vmlp_layernorm_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo& dv = device_info();
   long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
-  const int grid = (int)(blocks < dv.sms * 4 ? blocks : dv.sms * 4);
-  DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>(
+  const int grid = (int)(blocks < dv.sms * 6 ? blocks : dv.sms * 6);
+  DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL><<<grid, RW_THREADS, 16 * VPL * 32 * sizeof(float), st>>>(
                       (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
                       dbeta, rows, C)));
   CUDA_OK(cudaGetLastError());
@@ -345,10 +345,12 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
   if (!aligned16(a) || (a_ld % 8) || (b && (!aligned16(b) || (b_ld % 8)))) return fail(VMLP_EALIGN, "colsum alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo& dv = device_info();
-  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
-  const int grid = (int)(blocks < dv.sms * 4 ? blocks : dv.sms * 4);
-  DISPATCH_VPL(C, (colsum_kernel<VPL><<<grid, RW_THREADS, VPL * 256 * sizeof(float), st>>>((cbf)a, a_ld, (cbf)b, b_ld,
-                                                                                        out, rows, C)));
+  const int slabs = (C + 255) / 256;
+  long long gx = (rows + RW_WARPS - 1) / RW_WARPS;
+  const long long cap = (long long)(dv.sms * 8 + slabs - 1) / slabs;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  colsum_kernel<<<dim3((unsigned)gx, (unsigned)slabs), RW_THREADS, 0, st>>>((cbf)a, a_ld, (cbf)b, b_ld, out, rows, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

@@ -1,6 +1,6 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:
-//   TMA (128B-swizzled tiles) -> 4-stage mbarrier ring -> tcgen05.mma (cta_group::1, 128xBNx16)
-//   -> double-buffered TMEM accumulators -> fused epilogue -> TMA store / fp32 red.add.
+//   TMA (128B-swizzled tiles) -> mbarrier ring -> tcgen05.mma (cta_group::1, 128xBNx16)
+//   -> double-buffered TMEM accumulators -> fused epilogue -> per-warp TMA store / fp32 red.add.
 //
 //   D[b][m, n] = epilogue( sum_k A[b][m, k] * B[b][n, k] )
 //
@@ -9,8 +9,13 @@
 // directly as MN-major operands, so no permute/transposed copy is ever materialised
 // (reference: the Conv1d(k=1)-over-tokens trick, models_pytorch/mlp_mixer.py:34,37).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
-// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
+// (one lane), warps 2..9 = epilogue.  A warp may only read the TMEM lane quarter (warp_idx % 4),
+// so two warps share each 32-row quarter and split the 64-column chunks between them
+// (even / odd chunks).  Every epilogue warp is an independent pipeline: it owns two 4 KB staging
+// buffers, issues its own TMA stores (box 64 cols x 32 rows) and prefetches the auxiliary
+// operand (residual / saved pre-activation / gate) of its NEXT work item into registers before
+// doing the math of the current one -- no block-level barrier anywhere in the steady state.
 #pragma once
 #include "ptx.cuh"
 
@@ -18,10 +23,10 @@ namespace vmlp {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGE_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
-constexpr int GEMM_STAGING_BYTES = GEMM_BM * 64 * 2;        // 128 rows x 64 bf16 cols = 16 KB
+constexpr int GEMM_WARP_STAGING = 32 * 64 * 2;              // 32 rows x 64 bf16 cols = 4 KB
 
 enum GemmEpilogue : int {
   EPI_STORE = 0,    // D = acc (+bias)                                       -> bf16 via TMA store
@@ -53,28 +58,47 @@ struct GemmParams {
   long long out_ld;
 };
 
-template <int BN>
+template <int BN, int EPI>
 struct GemmSmem {
+  static constexpr int STAGES = (EPI == EPI_ATOMIC) ? 4 : 3;
   static constexpr int STAGE_B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
-  static constexpr int PIPE_BYTES = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_OFF = PIPE_BYTES;
-  static constexpr int BAR_OFF = STAGING_OFF + 2 * GEMM_STAGING_BYTES;
+  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * 2 * GEMM_WARP_STAGING;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
 };
+
+struct TileCoord {
+  int m0, n0, b_idx, s_idx;
+};
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord c;
+  int t = tile;
+  c.n0 = (t % p.tiles_n) * BN; t /= p.tiles_n;
+  c.m0 = (t % p.tiles_m) * GEMM_BM; t /= p.tiles_m;
+  c.b_idx = t % p.batch;
+  c.s_idx = t / p.batch;
+  return c;
+}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                 const GemmParams p) {
-  using L = GemmSmem<BN>;
+  using L = GemmSmem<BN, EPI>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int NCHUNK = BN / 64;
+  constexpr bool HAS_AUX = (EPI == EPI_RESID || EPI == EPI_DGELU || EPI == EPI_MUL);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + L::STAGING_OFF;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* tmem_full = empty_bar + GEMM_STAGES;
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -86,13 +110,13 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
     if (EPI == EPI_GELU) tma_prefetch_desc(&tmD2);
-    for (int s = 0; s < GEMM_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -114,38 +138,33 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int n_idx = t % p.tiles_n; t /= p.tiles_n;
-        const int m_idx = t % p.tiles_m; t /= p.tiles_m;
-        const int b_idx = t % p.batch;
-        const int s_idx = t / p.batch;
-        const int kb0 = s_idx * kb_per_split;
+        const TileCoord tc = decode_tile<BN>(p, tile);
+        const int kb0 = tc.s_idx * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
-        const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           const int kc = (kb % p.kpb) * GEMM_BK;
-          const int kbatch = p.kbatch ? (kb / p.kpb) : b_idx;
+          const int kbatch = p.kbatch ? (kb / p.kpb) : tc.b_idx;
           const int ba = p.a_batched ? kbatch : 0;
           const int bb = p.b_batched ? kbatch : 0;
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
           if (!p.a_mn) {
-            tma_load_3d(sa, &tmA, &full_bar[stage], kc, m0, ba);   // box (64 k, 128 m)
+            tma_load_3d(sa, &tmA, &full_bar[stage], kc, tc.m0, ba);   // box (64 k, 128 m)
           } else {
 #pragma unroll
-            for (int a = 0; a < GEMM_BM / 64; ++a)                 // box (64 m, 64 k) per MN atom
-              tma_load_3d(sa + a * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + a * 64, kc, ba);
+            for (int a = 0; a < GEMM_BM / 64; ++a)                    // box (64 m, 64 k) per MN atom
+              tma_load_3d(sa + a * (GEMM_BK * 128), &tmA, &full_bar[stage], tc.m0 + a * 64, kc, ba);
           }
           if (!p.b_mn) {
-            tma_load_3d(sb, &tmB, &full_bar[stage], kc, n0, bb);   // box (64 k, BN n)
+            tma_load_3d(sb, &tmB, &full_bar[stage], kc, tc.n0, bb);   // box (64 k, BN n)
           } else {
 #pragma unroll
             for (int a = 0; a < BN / 64; ++a)
-              tma_load_3d(sb + a * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + a * 64, kc, bb);
+              tma_load_3d(sb + a * (GEMM_BK * 128), &tmB, &full_bar[stage], tc.n0 + a * 64, kc, bb);
           }
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -178,68 +197,89 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
             umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);               // frees the smem slot when these MMAs retire
+          umma_commit(&empty_bar[stage]);                   // frees the smem slot when these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
+    const int ew = warp - 2;                // 0..7
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int par = ew >> 2;                // this warp handles 64-col chunks with (chunk & 1) == par
     const int row = q * 32 + lane;          // accumulator row owned by this thread
-    const bool leader = (threadIdx.x == 64);
-    int tc = 0;
-    uint32_t nstore = 0;                    // chunks stored so far (selects the staging buffer)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
-      int t = tile;
-      const int n_idx = t % p.tiles_n; t /= p.tiles_n;
-      const int m_idx = t % p.tiles_m; t /= p.tiles_m;
-      const int b_idx = t % p.batch;
-      const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
-      const int grow = m0 + row;
+    uint8_t* my_staging = staging + ew * 2 * GEMM_WARP_STAGING;
+    constexpr int MY_CHUNKS = (NCHUNK + 1) / 2;   // chunks per tile for this warp (BN=128: 1, BN=256: 2)
+    uint32_t nstore = 0;
+
+    // ---- auxiliary-operand prefetch (registers): 32 columns of this thread's row = 4 x 16 B
+    uint4 aux_nxt[4];
+    auto load_aux = [&](int tile, int c, int h, uint4 (&dst)[4]) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) dst[g] = make_uint4(0, 0, 0, 0);
+      if (!HAS_AUX || tile >= total_tiles) return;
+      const TileCoord t = decode_tile<BN>(p, tile);
+      const int grow = t.m0 + row;
+      const int col = t.n0 + c * 64 + h * 32;
+      if (grow >= p.M) return;
+      const __nv_bfloat16* src = p.aux + (long long)t.b_idx * p.aux_bs + (long long)grow * p.aux_ld + col;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (col + g * 8 < p.N) dst[g] = ldg_v4(src + g * 8);
+    };
+    if (HAS_AUX) load_aux(blockIdx.x, par, 0, aux_nxt);
+
+    int tcnt = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcnt) {
+      const TileCoord tc = decode_tile<BN>(p, tile);
+      const int grow = tc.m0 + row;
       const bool row_ok = grow < p.M;
-      const int as = tc & 1;
-      mbar_wait(&tmem_full[as], (tc >> 1) & 1);
+      const int as = tcnt & 1;
+      mbar_wait(&tmem_full[as], (tcnt >> 1) & 1);
       tc_fence_after();
       float rbias = 0.f;
       if (p.bias_mode == 2 && row_ok) rbias = __bfloat162float(p.bias[grow]);
-      const __nv_bfloat16* aux_row =
-          (p.aux != nullptr) ? p.aux + (long long)b_idx * p.aux_bs + (long long)grow * p.aux_ld : nullptr;
 
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int col0 = n0 + c * 64;
-        if (col0 >= p.N) {
-          // fully out-of-range column chunk (ragged N): nothing to compute or store
-          if (c == BN / 64 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
-          }
-          continue;
-        }
-        uint8_t* st0 = staging + ((EPI == EPI_GELU) ? 0 : (nstore & 1) * GEMM_STAGING_BYTES);
-        ++nstore;
-        uint8_t* st1 = staging + GEMM_STAGING_BYTES;
-        if (EPI != EPI_ATOMIC) {
+      for (int ci = 0; ci < MY_CHUNKS; ++ci) {
+        const int c = ci * 2 + par;
+        const bool last_chunk = (ci == MY_CHUNKS - 1);
+        const int col0 = tc.n0 + c * 64;
+        const bool chunk_live = (c < NCHUNK) && (col0 < p.N);   // ragged N: dead chunks are skipped entirely
+        uint8_t* st0 = my_staging + ((EPI == EPI_GELU) ? 0 : (nstore & 1) * GEMM_WARP_STAGING);
+        uint8_t* st1 = my_staging + GEMM_WARP_STAGING;
+        if (chunk_live && EPI != EPI_ATOMIC) {
           // the staging buffer about to be overwritten must have been drained by its TMA store
-          if (leader) {
+          if (lane == 0) {
             if (EPI == EPI_GELU) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
-          named_bar_sync(1, 128);
+          __syncwarp();
+          ++nstore;
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          uint4 aux_cur[4];
+          if (HAS_AUX) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) aux_cur[g] = aux_nxt[g];
+            // prefetch the aux operand of this warp's NEXT work item (next half / chunk / tile)
+            if (h == 0) load_aux(tile, c, 1, aux_nxt);
+            else if (!last_chunk) load_aux(tile, c + 2, 0, aux_nxt);
+            else load_aux(tile + gridDim.x, par, 0, aux_nxt);
+          }
           uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + as * BN + c * 64 + h * 32 + (uint32_t(q * 32) << 16), v);
-          tmem_ld_wait();
-          if (c == BN / 64 - 1 && h == 1) {
-            // last TMEM read of this accumulator stage: hand it back to the MMA warp
+          if (chunk_live) {
+            tmem_ld_32x32b_x32(tmem_base + as * BN + c * 64 + h * 32 + (uint32_t(q * 32) << 16), v);
+            tmem_ld_wait();
+          }
+          if (last_chunk && h == 1) {
+            // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
           }
+          if (!chunk_live) continue;
           const int colh = col0 + h * 32;
           if (EPI == EPI_ATOMIC) {
             if (row_ok) {
@@ -282,24 +322,17 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
           }
           uint32_t o[16], o2[16];
-          if (EPI == EPI_RESID || EPI == EPI_DGELU || EPI == EPI_MUL) {
+          if (HAS_AUX) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              uint4 av = make_uint4(0, 0, 0, 0);
-              if (row_ok && colh + g * 8 < p.N) av = ldg_nc_v4(aux_row + colh + g * 8);
-              const uint32_t w[4] = {av.x, av.y, av.z, av.w};
+              const uint32_t w[4] = {aux_cur[g].x, aux_cur[g].y, aux_cur[g].z, aux_cur[g].w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
                 const float a0 = bf16lo(w[e]), a1 = bf16hi(w[e]);
                 if (EPI == EPI_RESID) { x0 += a0; x1 += a1; }
                 if (EPI == EPI_MUL) { x0 *= a0; x1 *= a1; }
-                if (EPI == EPI_DGELU) {
-                  float d0, d1;
-                  gelu_erf(a0, &d0);
-                  gelu_erf(a1, &d1);
-                  x0 *= d0; x1 *= d1;
-                }
+                if (EPI == EPI_DGELU) { x0 *= dgelu_erf(a0); x1 *= dgelu_erf(a1); }
                 o[g * 4 + e] = pack_bf16x2(x0, x1);
               }
             }
@@ -308,39 +341,38 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int e = 0; e < 16; ++e) {
               o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
               // gelu is applied to the bf16-rounded pre-activation that backward will re-read
-              o2[e] = pack_bf16x2(gelu_erf(bf16lo(o[e]), nullptr), gelu_erf(bf16hi(o[e]), nullptr));
+              o2[e] = pack_bf16x2(gelu_erf(bf16lo(o[e])), gelu_erf(bf16hi(o[e])));
             }
           } else if (EPI == EPI_GELU_ONLY) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              o[e] = pack_bf16x2(gelu_erf(f[2 * e], nullptr), gelu_erf(f[2 * e + 1], nullptr));
+            for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(gelu_erf(f[2 * e]), gelu_erf(f[2 * e + 1]));
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
           }
-          // staging tile = [128 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7) (matches SWIZZLE_128B)
-          const uint32_t srow = smem_u32(st0) + row * 128;
+          // staging tile = [32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7) (matches SWIZZLE_128B)
+          const uint32_t srow = smem_u32(st0) + lane * 128;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int chunk = (h * 4 + g) ^ (row & 7);
+            const int chunk = (h * 4 + g) ^ (lane & 7);
             st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
             if (EPI == EPI_GELU)
-              st_shared_v4(smem_u32(st1) + row * 128 + chunk * 16,
+              st_shared_v4(smem_u32(st1) + lane * 128 + chunk * 16,
                            make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
           }
         }
-        if (EPI != EPI_ATOMIC) {
+        if (chunk_live && EPI != EPI_ATOMIC) {
           fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          if (leader) {
-            tma_store_3d(&tmD, st0, col0, m0, b_idx);
-            if (EPI == EPI_GELU) tma_store_3d(&tmD2, st1, col0, m0, b_idx);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
+            if (EPI == EPI_GELU) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
             tma_store_commit();
           }
         }
       }
     }
-    if (EPI != EPI_ATOMIC && leader) tma_store_wait_all<0>();
+    if (EPI != EPI_ATOMIC && lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

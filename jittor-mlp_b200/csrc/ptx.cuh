@@ -182,6 +182,13 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
+__device__ __forceinline__ uint4 ldg_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -196,23 +203,44 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// erf-GELU, exact-form semantics (torch nn.GELU() default), evaluated with the
-// Abramowitz-Stegun 7.1.26 rational-exponential erf (|err| <= 1.5e-7, far below
-// the bf16 quantum of the stored result).  Returns gelu(z); *dgelu = d/dz.
-__device__ __forceinline__ float gelu_erf(float z, float* dgelu) {
-  const float x = fabsf(z) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, x, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = exp2f(-x * x * 1.4426950408889634f);   // exp(-z^2/2)
-  const float erf_abs = fmaf(-p, e, 1.0f);               // erf(|z|/sqrt2)
-  const float erf_s = copysignf(erf_abs, z);
-  const float cdf = fmaf(0.5f, erf_s, 0.5f);
-  if (dgelu) *dgelu = fmaf(z * 0.3989422804014327f, e, cdf);   // Phi(z) + z*phi(z)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// erf-GELU with the exact-form semantics of torch nn.GELU() (mlp_mixer.py:21): gelu(z) = z * Phi(z),
+// Phi via the Abramowitz-Stegun 7.1.26 erfc form (|err| <= 1.5e-7 plus MUFU rcp/ex2 rounding ~1e-7; both far
+// below the bf16 quantum of the stored result).  2 MUFU + ~12 FMA-pipe ops per element.
+//   Phi(z) = h            (z <  0)      h = 0.5 * poly(t) * exp(-z^2/2),  t = 1 / (1 + p |z| / sqrt2)
+//          = 1 - h        (z >= 0)
+template <bool WITH_GRAD>
+__device__ __forceinline__ float gelu_erf_t(float z, float& dgelu) {
+  const float az = fabsf(z);
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, az, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float e = ex2_approx(az * az * (-0.5f * 1.4426950408889634f));   // exp(-z^2/2)
+  const float h = p * t * e;
+  const float cdf = (z < 0.f) ? h : 1.0f - h;
+  if (WITH_GRAD) dgelu = fmaf(z * 0.3989422804014327f, e, cdf);           // Phi(z) + z * phi(z)
   return z * cdf;
+}
+__device__ __forceinline__ float gelu_erf(float z) {
+  float unused;
+  return gelu_erf_t<false>(z, unused);
+}
+__device__ __forceinline__ float dgelu_erf(float z) {
+  float d;
+  gelu_erf_t<true>(z, d);
+  return d;
 }
 
 }  // namespace vmlp

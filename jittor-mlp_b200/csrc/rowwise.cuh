@@ -102,46 +102,55 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, const 
 
 // --------------------------------------------------------------------------- LayerNorm backward
 // dx = add + rstd * (g - mean_C(g) - xhat * mean_C(g * xhat)),  g = dy * gamma,  xhat = (x - mean) * rstd
-// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 accumulators, red.add once per block)
+// dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (fp32 accumulators)
+// HBM-bound (3 reads + 1 write per element): rows stay packed (bf16) in registers so that 3-4 blocks fit per
+// SM and enough loads are in flight; the per-column partials of a block live in shared memory
+// ([e][vector] layout => conflict-free red.shared) and are flushed with one global red.add per column.
 template <int VPL>
-__global__ void __launch_bounds__(RW_THREADS)
+__global__ void __launch_bounds__(RW_THREADS, (VPL <= 4) ? 3 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, const __nv_bfloat16* __restrict__ x,
                      long long x_ld, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ add,
                      long long add_ld, __nv_bfloat16* __restrict__ dx, long long dx_ld,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
-  extern __shared__ float sh[];
+  extern __shared__ float sh[];           // [2][8][NV]  (NV = VPL * 32 vectors)
+  constexpr int NV = VPL * 32;
+  float* sh_g = sh;
+  float* sh_b = sh + 8 * NV;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
+  for (int i = threadIdx.x; i < 16 * NV; i += RW_THREADS) sh[i] = 0.f;
+  __syncthreads();
   const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * RW_WARPS;
-  float ag[VPL][8], ab[VPL][8], gm[VPL][8];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int vi = i * 32 + lane;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; gm[i][e] = 0.f; }
-    if (vi < nvec) unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), gm[i]);
-  }
   for (long long r = gw; r < rows; r += nw) {
     const float mean = mean_in[r], rstd = rstd_in[r];
-    float g[VPL][8], xh[VPL][8];
+    uint4 rd[VPL], rx[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        rd[i] = ldg_nc_v4(dy + r * dy_ld + vi * 8);
+        rx[i] = ldg_nc_v4(x + r * x_ld + vi * 8);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = i * 32 + lane;
       if (vi < nvec) {
-        float d[8], xv[8];
-        unpack8(ldg_nc_v4(dy + r * dy_ld + vi * 8), d);
-        unpack8(ldg_nc_v4(x + r * x_ld + vi * 8), xv);
+        float d[8], xv[8], gm[8];
+        unpack8(rd[i], d);
+        unpack8(rx[i], xv);
+        unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), gm);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          xh[i][e] = (xv[e] - mean) * rstd;
-          g[i][e] = d[e] * gm[i][e];
-          s1 += g[i][e];
-          s2 += g[i][e] * xh[i][e];
-          ag[i][e] += d[e] * xh[i][e];
-          ab[i][e] += d[e];
+          const float xh = (xv[e] - mean) * rstd;
+          const float g = d[e] * gm[e];
+          s1 += g;
+          s2 += g * xh;
+          atomicAdd(&sh_g[e * NV + vi], d[e] * xh);
+          atomicAdd(&sh_b[e * NV + vi], d[e]);
         }
       }
     }
@@ -151,18 +160,28 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
     for (int i = 0; i < VPL; ++i) {
       const int vi = i * 32 + lane;
       if (vi < nvec) {
-        float o[8], a[8];
+        float d[8], xv[8], gm[8], o[8], a[8];
+        unpack8(rd[i], d);
+        unpack8(rx[i], xv);
+        unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), gm);
 #pragma unroll
         for (int e = 0; e < 8; ++e) a[e] = 0.f;
         if (add) unpack8(ldg_nc_v4(add + r * add_ld + vi * 8), a);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = a[e] + rstd * (g[i][e] - s1 - xh[i][e] * s2);
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] - mean) * rstd;
+          o[e] = a[e] + rstd * (d[e] * gm[e] - s1 - xh * s2);
+        }
         *reinterpret_cast<uint4*>(dx + r * dx_ld + vi * 8) = pack8(o);
       }
     }
   }
-  flush_col_partials<VPL>(ag, dgamma, nvec, sh);
-  flush_col_partials<VPL>(ab, dbeta, nvec, sh);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nvec * 8; i += RW_THREADS) {
+    const int vi = i >> 3, e = i & 7;
+    red_add_f32(dgamma + i, sh_g[e * NV + vi]);
+    red_add_f32(dbeta + i, sh_b[e * NV + vi]);
+  }
 }
 
 // --------------------------------------------------------------------------- per-channel affine (ResMLP Aff)
@@ -229,39 +248,41 @@ affine_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __r
 }
 
 // --------------------------------------------------------------------------- column sums  out[c] += sum_r (a[r,c] (* b[r,c]))
-template <int VPL>
+// grid = (row groups, 256-column slabs): a warp reads 512 contiguous bytes per row of its slab and keeps
+// 8 fp32 partials per lane; one smem reduction + one global red.add per column per block.
 __global__ void __launch_bounds__(RW_THREADS)
 colsum_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bfloat16* __restrict__ b,
               long long b_ld, float* __restrict__ out, long long rows, int C) {
-  extern __shared__ float sh[];
-  const int lane = threadIdx.x & 31;
-  const int nvec = C >> 3;
-  const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
-  const long long nw = (long long)gridDim.x * RW_WARPS;
-  float acc[VPL][8];
+  __shared__ float sh[RW_WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.y * 256 + lane * 8;
+  float acc[8];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (col < C) {
+    for (long long r = (long long)blockIdx.x * RW_WARPS + warp; r < rows; r += (long long)gridDim.x * RW_WARPS) {
+      float d[8];
+      unpack8(ldg_nc_v4(a + r * a_ld + col), d);
+      if (b) {
+        float m[8];
+        unpack8(ldg_nc_v4(b + r * b_ld + col), m);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-  for (long long r = gw; r < rows; r += nw) {
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
-        float d[8];
-        unpack8(ldg_nc_v4(a + r * a_ld + vi * 8), d);
-        if (b) {
-          float m[8];
-          unpack8(ldg_nc_v4(b + r * b_ld + vi * 8), m);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d[e] *= m[e];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] += d[e];
+        for (int e = 0; e < 8; ++e) d[e] *= m[e];
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += d[e];
     }
   }
-  flush_col_partials<VPL>(acc, out, nvec, sh);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sh[warp][lane * 8 + e] = acc[e];
+  __syncthreads();
+  const int c = threadIdx.x;     // 256 threads <-> 256 columns of the slab
+  if (blockIdx.y * 256 + c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < RW_WARPS; ++w) s += sh[w][c];
+    red_add_f32(out + blockIdx.y * 256 + c, s);
+  }
 }
 
 // --------------------------------------------------------------------------- batched row sums
