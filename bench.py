@@ -27,6 +27,8 @@ PRESETS = {
     "mixer_b16": ("MLPMixerForImageClassification", dict(d_model=768, depth=12), "mixer_forward", 28.094, 0.2312),
     "mixer_l16": ("MLPMixerForImageClassification", dict(d_model=1024, depth=24), "mixer_forward", 94.336, 0.3083),
     "mixer_s16": ("MLPMixerForImageClassification", dict(d_model=512, depth=8), "mixer_forward", 9.249, 0.1541),
+    "resmlp_24": ("ResMLPForImageClassification", dict(d_model=384, depth=24), "resmlp_forward", 11.923, 0.1156),
+    "gmlp_s": ("gMLPForImageClassification", dict(image_size=224, d_model=256, d_ffn=1536, depth=30), "gmlp_forward", 17.491, 0.0771),
 }
 METRIC = "images/sec fwd+bwd MLP-Mixer-B/16 224px"
 
@@ -286,7 +288,7 @@ def main():
                 "clocks": cs.summary(),
                 "model_tflops": round(value / world * flops_img / 1e3, 1),
                 "model_frac_of_sustained_peak": round(value / world * flops_img / 1e3 / pk["bf16_tflops_sustained"], 3)}
-    if rank == 0 and not args.no_kernels:
+    if rank == 0 and not args.no_kernels and args.model.startswith("mixer"):
         del ddp
         model.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()

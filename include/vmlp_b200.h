@@ -70,7 +70,9 @@ enum {
   VMLP_EPI_DGELU = 3,     /* D = acc * gelu_erf'(aux)                         */
   VMLP_EPI_ATOMIC = 4,    /* out_f32 += acc   (split-K, weight gradients)     */
   VMLP_EPI_MUL = 5,       /* D = (acc + bias) * aux                           */
-  VMLP_EPI_GELU_ONLY = 6  /* D = gelu_erf(acc + bias)                         */
+  VMLP_EPI_GELU_ONLY = 6, /* D = gelu_erf(acc + bias)                         */
+  VMLP_EPI_RESID_DUAL = 7,/* VMLP_EPI_RESID and D2 = acc + bias               */
+  VMLP_EPI_MUL_DUAL = 8   /* VMLP_EPI_MUL and D2 = acc + bias                 */
 };
 
 typedef struct {
@@ -113,7 +115,20 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
 int vmlp_rowsum_batched(const void* a, float* out, int64_t batch, int32_t rows_per_batch, int32_t C,
                         vmlp_stream_t stream);
 int vmlp_cast_f32_to_bf16(const float* src, void* dst, int64_t n, vmlp_stream_t stream);
+/* dst[r, 0:cols] = src[r, 0:cols], zero elsewhere: gives a [rows, cols] weight a 16-byte row pitch (ld_dst % 8 == 0) */
+int vmlp_pad_rows(const void* src, void* dst, int32_t rows, int32_t cols, int32_t ld_dst, vmlp_stream_t stream);
 int vmlp_add_bf16(const void* a, const void* b, void* dst, int64_t n, vmlp_stream_t stream);
+/* Strided elementwise helpers over [rows, C] views (row strides in elements, C % 8 == 0):
+ *   vmlp_mul_colvec : out = a * v[c]                   (ResMLP layer-scale backward, res_mlp.py:54,56)
+ *   vmlp_dgelu_mul  : out = a * gelu_erf'(z)
+ *   vmlp_gate_bwd   : out = dg * vt * gelu_erf'(zp_u) ; out2 = dg * u     (gMLP SGU gate, g_mlp.py:21) */
+int vmlp_mul_colvec(const void* a, int64_t a_ld, const void* v, void* out, int64_t out_ld, int64_t rows, int32_t C,
+                    vmlp_stream_t stream);
+int vmlp_dgelu_mul(const void* a, int64_t a_ld, const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows,
+                   int32_t C, vmlp_stream_t stream);
+int vmlp_gate_bwd(const void* dg, int64_t dg_ld, const void* vt, int64_t vt_ld, const void* zp_u, int64_t zp_ld,
+                  const void* u, int64_t u_ld, void* out, int64_t out_ld, void* out2, int64_t out2_ld, int64_t rows,
+                  int32_t C, vmlp_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
  * MLP-Mixer block: models_pytorch/mlp_mixer.py:35-40

@@ -2,3 +2,5 @@
 liuruiyang98/Jittor-MLP.  Import as ``jittor_mlp_b200`` (see jittor_mlp_b200.py at the repo root)."""
 from . import _lib, ops  # noqa: F401
 from .mlp_mixer import MLPMixer, MLPMixerForImageClassification  # noqa: F401
+from .res_mlp import MLPblock, ResMLP, ResMLPForImageClassification  # noqa: F401
+from .g_mlp import gMLP, gMLPBlock, gMLPForImageClassification  # noqa: F401

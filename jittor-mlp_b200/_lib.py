@@ -76,7 +76,7 @@ class MixerSaved(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("xhat1", "z1", "h1", "u", "xhat2", "z2", "h2", "stats", "w1t_pad")]
 
 
-EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ATOMIC, EPI_MUL, EPI_GELU_ONLY = range(7)
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ATOMIC, EPI_MUL, EPI_GELU_ONLY, EPI_RESID_DUAL, EPI_MUL_DUAL = range(9)
 
 # Every symbol include/vmlp_b200.h declares: (name, restype, argtypes).
 _P = ctypes.POINTER
@@ -97,7 +97,12 @@ SYMBOLS = [
     ("vmlp_colsum", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]),
     ("vmlp_rowsum_batched", c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     ("vmlp_cast_f32_to_bf16", c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    ("vmlp_pad_rows", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_add_bf16", c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    ("vmlp_mul_colvec", c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
+    ("vmlp_dgelu_mul", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
+    ("vmlp_gate_bwd", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     ("vmlp_mixer_block_fwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, _P(MixerSaved), c_void_p]),
     ("vmlp_mixer_grad_elems", c_int64, [_P(MixerParams)]),
     ("vmlp_mixer_bwd_workspace_elems", c_int64, [_P(MixerParams)]),

@@ -119,6 +119,8 @@ int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const 
     case EPI_ATOMIC: return launch_gemm_t<BN, EPI_ATOMIC>(ta, tb, td, td2, p, grid, st);
     case EPI_MUL: return launch_gemm_t<BN, EPI_MUL>(ta, tb, td, td2, p, grid, st);
     case EPI_GELU_ONLY: return launch_gemm_t<BN, EPI_GELU_ONLY>(ta, tb, td, td2, p, grid, st);
+    case EPI_RESID_DUAL: return launch_gemm_t<BN, EPI_RESID_DUAL>(ta, tb, td, td2, p, grid, st);
+    case EPI_MUL_DUAL: return launch_gemm_t<BN, EPI_MUL_DUAL>(ta, tb, td, td2, p, grid, st);
   }
   return fail(VMLP_EINVAL, "unknown epilogue %d", epi);
 }
@@ -184,7 +186,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   p.out_ld = g.out_ld;
   if (p.bias_mode == 1 && !aligned16(g.bias)) return fail(VMLP_EALIGN, "bias must be 16-byte aligned");
   if (p.colscale && !aligned16(p.colscale)) return fail(VMLP_EALIGN, "colscale must be 16-byte aligned");
-  const bool needs_aux = (epi == EPI_RESID || epi == EPI_DGELU || epi == EPI_MUL);
+  const bool needs_aux = (epi_is_resid(epi) || epi == EPI_DGELU || epi_is_mul(epi));
   if (needs_aux) {
     if (!g.aux) return fail(VMLP_EINVAL, "epilogue %d needs aux", epi);
     if (!aligned16(g.aux) || (g.aux_ld % 8) || (g.aux_bs % 8)) return fail(VMLP_EALIGN, "aux alignment");
@@ -205,8 +207,8 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
     if (!g.D) return fail(VMLP_EINVAL, "null output");
     rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 64, 32);   // per-warp store box: 64 cols x 32 rows
     if (rc) return rc;
-    if (epi == EPI_GELU) {
-      if (!g.D2) return fail(VMLP_EINVAL, "EPI_GELU needs D2");
+    if (epi_is_dual(epi)) {
+      if (!g.D2) return fail(VMLP_EINVAL, "dual-output epilogue needs D2");
       rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 64, 32);
       if (rc) return rc;
     }
@@ -385,6 +387,53 @@ int vmlp_add_bf16(const void* a, const void* b, void* dst, int64_t n, vmlp_strea
   long long blocks = (nvec + 255) / 256;
   const long long cap = (long long)device_info().sms * 16;
   add_bf16_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>((cbf)a, (cbf)b, (bf)dst, nvec);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+int vmlp_pad_rows(const void* src, void* dst, int32_t rows, int32_t cols, int32_t ld_dst, vmlp_stream_t stream) {
+  if (!src || !dst || rows <= 0 || cols <= 0 || ld_dst < cols || (ld_dst % 8)) return fail(VMLP_EINVAL, "pad_rows args");
+  const long long n = (long long)rows * ld_dst;
+  pad_rows_kernel<<<(int)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>((cbf)src, (bf)dst, rows, cols, ld_dst);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+static int ew_grid(long long total_vec) {
+  long long blocks = (total_vec + RW_THREADS - 1) / RW_THREADS;
+  const long long cap = (long long)device_info().sms * 16;
+  return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+int vmlp_mul_colvec(const void* a, int64_t a_ld, const void* v, void* out, int64_t out_ld, int64_t rows, int32_t C,
+                    vmlp_stream_t stream) {
+  if (!a || !v || !out || rows <= 0 || (C % 8)) return fail(VMLP_EINVAL, "mul_colvec args");
+  if (!aligned16(a) || !aligned16(v) || !aligned16(out) || (a_ld % 8) || (out_ld % 8)) return fail(VMLP_EALIGN, "mul_colvec alignment");
+  ew_kernel<0><<<ew_grid(rows * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)a, a_ld, (cbf)v, 0, nullptr, 0, nullptr, 0, (bf)out, out_ld, nullptr, 0, rows, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_dgelu_mul(const void* a, int64_t a_ld, const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows,
+                   int32_t C, vmlp_stream_t stream) {
+  if (!a || !z || !out || rows <= 0 || (C % 8)) return fail(VMLP_EINVAL, "dgelu_mul args");
+  if (!aligned16(a) || !aligned16(z) || !aligned16(out) || (a_ld % 8) || (z_ld % 8) || (out_ld % 8)) return fail(VMLP_EALIGN, "dgelu_mul alignment");
+  ew_kernel<1><<<ew_grid(rows * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)a, a_ld, (cbf)z, z_ld, nullptr, 0, nullptr, 0, (bf)out, out_ld, nullptr, 0, rows, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_gate_bwd(const void* dg, int64_t dg_ld, const void* vt, int64_t vt_ld, const void* zp_u, int64_t zp_ld,
+                  const void* u, int64_t u_ld, void* out, int64_t out_ld, void* out2, int64_t out2_ld, int64_t rows,
+                  int32_t C, vmlp_stream_t stream) {
+  if (!dg || !vt || !zp_u || !u || !out || !out2 || rows <= 0 || (C % 8)) return fail(VMLP_EINVAL, "gate_bwd args");
+  if (!aligned16(dg) || !aligned16(vt) || !aligned16(zp_u) || !aligned16(u) || !aligned16(out) || !aligned16(out2) ||
+      (dg_ld % 8) || (vt_ld % 8) || (zp_ld % 8) || (u_ld % 8) || (out_ld % 8) || (out2_ld % 8))
+    return fail(VMLP_EALIGN, "gate_bwd alignment");
+  ew_kernel<2><<<ew_grid(rows * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)dg, dg_ld, (cbf)vt, vt_ld, (cbf)zp_u, zp_ld, (cbf)u, u_ld, (bf)out, out_ld, (bf)out2, out2_ld, rows, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

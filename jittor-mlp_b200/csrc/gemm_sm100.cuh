@@ -35,8 +35,13 @@ enum GemmEpilogue : int {
   EPI_DGELU = 3,    // D = acc * gelu'(aux)                                  -> bf16 (aux = saved pre-activation)
   EPI_ATOMIC = 4,   // out_f32[m, n] += acc                                  (split-K weight gradients)
   EPI_MUL = 5,      // D = (acc + bias) * aux                                -> bf16 (gMLP spatial gate)
-  EPI_GELU_ONLY = 6 // D = gelu(acc + bias)                                  -> bf16 (no pre-activation saved)
+  EPI_GELU_ONLY = 6,  // D = gelu(acc + bias)                                -> bf16 (no pre-activation saved)
+  EPI_RESID_DUAL = 7, // EPI_RESID plus D2 = acc + bias (the un-scaled branch output, needed for d(layer-scale))
+  EPI_MUL_DUAL = 8    // EPI_MUL plus D2 = acc + bias (the gate value, needed for d(gated operand))
 };
+__host__ __device__ constexpr bool epi_is_resid(int e) { return e == EPI_RESID || e == EPI_RESID_DUAL; }
+__host__ __device__ constexpr bool epi_is_mul(int e) { return e == EPI_MUL || e == EPI_MUL_DUAL; }
+__host__ __device__ constexpr bool epi_is_dual(int e) { return e == EPI_GELU || e == EPI_RESID_DUAL || e == EPI_MUL_DUAL; }
 
 struct GemmParams {
   int M, N;              // logical rows / cols of one output matrix (bounds for aux loads / atomics)
@@ -92,7 +97,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using L = GemmSmem<BN, EPI>;
   constexpr int STAGES = L::STAGES;
   constexpr int NCHUNK = BN / 64;
-  constexpr bool HAS_AUX = (EPI == EPI_RESID || EPI == EPI_DGELU || EPI == EPI_MUL);
+  constexpr bool HAS_AUX = (epi_is_resid(EPI) || EPI == EPI_DGELU || epi_is_mul(EPI));
+  constexpr bool DUAL = epi_is_dual(EPI);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + L::STAGING_OFF;
@@ -109,7 +115,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
-    if (EPI == EPI_GELU) tma_prefetch_desc(&tmD2);
+    if (DUAL) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -247,12 +253,12 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const bool last_chunk = (ci == MY_CHUNKS - 1);
         const int col0 = tc.n0 + c * 64;
         const bool chunk_live = (c < NCHUNK) && (col0 < p.N);   // ragged N: dead chunks are skipped entirely
-        uint8_t* st0 = my_staging + ((EPI == EPI_GELU) ? 0 : (nstore & 1) * GEMM_WARP_STAGING);
+        uint8_t* st0 = my_staging + (DUAL ? 0 : (nstore & 1) * GEMM_WARP_STAGING);
         uint8_t* st1 = my_staging + GEMM_WARP_STAGING;
         if (chunk_live && EPI != EPI_ATOMIC) {
           // the staging buffer about to be overwritten must have been drained by its TMA store
           if (lane == 0) {
-            if (EPI == EPI_GELU) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            if (DUAL) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
           __syncwarp();
           ++nstore;
@@ -291,6 +297,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             continue;
           }
           float f[32];
+          uint32_t o2[16];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + rbias;
           if (p.bias_mode == 1) {
@@ -307,7 +314,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          if (EPI == EPI_RESID && p.colscale != nullptr) {
+          if (epi_is_resid(EPI) && DUAL) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);   // un-scaled branch output
+          }
+          if (epi_is_resid(EPI) && p.colscale != nullptr) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (colh + g * 8 < p.N) {
@@ -321,7 +332,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          uint32_t o[16], o2[16];
+          uint32_t o[16];
+          if (epi_is_mul(EPI) && DUAL) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);   // gate value before the product
+          }
           if (HAS_AUX) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -330,8 +345,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               for (int e = 0; e < 4; ++e) {
                 float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
                 const float a0 = bf16lo(w[e]), a1 = bf16hi(w[e]);
-                if (EPI == EPI_RESID) { x0 += a0; x1 += a1; }
-                if (EPI == EPI_MUL) { x0 *= a0; x1 *= a1; }
+                if (epi_is_resid(EPI)) { x0 += a0; x1 += a1; }
+                if (epi_is_mul(EPI)) { x0 *= a0; x1 *= a1; }
                 if (EPI == EPI_DGELU) { x0 *= dgelu_erf(a0); x1 *= dgelu_erf(a1); }
                 o[g * 4 + e] = pack_bf16x2(x0, x1);
               }
@@ -356,7 +371,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int g = 0; g < 4; ++g) {
             const int chunk = (h * 4 + g) ^ (lane & 7);
             st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
-            if (EPI == EPI_GELU)
+            if (DUAL)
               st_shared_v4(smem_u32(st1) + lane * 128 + chunk * 16,
                            make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
           }
@@ -366,7 +381,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) {
             tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
-            if (EPI == EPI_GELU) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
+            if (DUAL) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
             tma_store_commit();
           }
         }

@@ -23,6 +23,8 @@ class DataParallel(torch.nn.Module):
         self.module = module
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # NCCL averages in the collective; gloo (CPU tests of this host logic) has no AVG: sum, then scale
+        self._nccl = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         self._pending = []      # (work handle, flat bucket tensor)
         self._bucketed = set()  # data_ptrs already covered by an in-flight bucket
         if self.world > 1:
@@ -36,7 +38,8 @@ class DataParallel(torch.nn.Module):
     def reduce_bucket_async(self, flat):
         if self.world == 1:
             return
-        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM, group=self.group,
+                               async_op=True)
         self._pending.append((work, flat))
 
     def __enter__(self):
@@ -66,11 +69,15 @@ class DataParallel(torch.nn.Module):
                 rest.append(p)
         if rest:
             flat = torch._utils._flatten_dense_tensors([p.grad for p in rest])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM, group=self.group)
+            if not self._nccl:
+                flat.div_(self.world)
             for p, g in zip(rest, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in rest])):
                 p.grad.copy_(g)
-        for work, _ in self._pending:
+        for work, flat in self._pending:
             work.wait()          # makes the current stream wait for the NCCL stream
+            if not self._nccl:
+                flat.div_(self.world)
         self._pending.clear()
 
     def step_fwd_bwd(self, x, loss_fn):

@@ -1,0 +1,70 @@
+"""Data-parallel host logic (jittor-mlp_b200/dp.py) on CPU: world_size 2, gloo.  The fused blocks cannot run
+without a GPU, so a plain torch module stands in for the stem/head path ("rest" bucket) and hand-made flat buffers
+stand in for the per-block gradient buckets the fused backward registers."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import jittor_mlp_b200 as J
+    from jittor_mlp_b200 import dp
+    torch.manual_seed(100 + rank)                      # different init per rank: the wrapper must broadcast rank 0's
+    model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+    unused = torch.nn.Parameter(torch.ones(3))         # never receives a gradient (SURVEY.md F6 situation)
+    model.register_parameter("unused", unused)
+    ddp = dp.DataParallel(model)
+    w0 = model[0].weight.detach().clone()
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(7))      # global batch 4 -> 2 per rank
+    x = xs[rank * 2:(rank + 1) * 2]
+    with ddp:
+        loss = model(x).square().mean()
+        loss.backward()
+        # emulate one fused-block bucket: a flat buffer whose views are parameter grads
+        bucket = torch.full((5,), float(rank + 1))
+        ddp.reduce_bucket_async(bucket)
+        ddp.finish()
+    q.put((rank, w0, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+           bucket.clone(), unused.grad is None))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_matches_single_process_big_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, w0a, ga, ba, ua), (_, w0b, gb, bb, ub) = res
+    assert torch.equal(w0a, w0b)                       # replicas identical after the initial broadcast
+    for k in ga:
+        assert torch.allclose(ga[k], gb[k])            # every rank holds the same averaged gradient
+    assert torch.allclose(ba, torch.full((5,), 1.5)) and torch.allclose(bb, ba)   # bucket averaged in place
+    assert ua and ub                                   # unused parameter: grad stays None on every rank
+    # reference: one process, the concatenated batch, mean-of-shard-means == mean over the batch for equal shards
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(7))
+    ref(xs).square().mean().backward()
+    for k, p in ref.named_parameters():
+        assert torch.allclose(ga[k], p.grad, atol=1e-6), k
