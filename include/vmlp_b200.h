@@ -131,6 +131,50 @@ int vmlp_gate_bwd(const void* dg, int64_t dg_ld, const void* vt, int64_t vt_ld, 
                   int32_t C, vmlp_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Spatial operators of the shift family.  Tensors are channels-last [B, H, W, C] bf16, C % 8 == 0.
+ * ------------------------------------------------------------------------------------------ */
+/* Channel-group token shift: group g = channels [start[g], start[g+1]) reads (h + dh[g], w + dw[g]).
+ *   mode 0 zero padding   -- AS-MLP Shift forward; its backward is the same call with negated offsets
+ *                            (models_pytorch/utils/shift_cuda.py:44-103)
+ *   mode 1 clamp-to-edge  -- S2-MLP spatial_shift, intended semantics (s2_mlp_v1.py:19-25, s2_mlp_v2.py:15-29)
+ *   mode 2 adjoint of mode 1 (|offset| <= 1)
+ * start has ngroups + 1 entries; ngroups <= 8. */
+int vmlp_shift_nhwc(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode,
+                    int32_t ngroups, const int32_t* start, const int32_t* dh, const int32_t* dw, vmlp_stream_t stream);
+/* GroupNorm(1, C) (as_mlp.py:343-344): statistics over each sample's P*C elements.
+ * acc: fp32 [B][2] (sum, sum of squares), zero-filled by the caller before vmlp_gn_stats. */
+int vmlp_gn_stats(const void* x, float* acc, int32_t B, int64_t P, int32_t C, vmlp_stream_t stream);
+int vmlp_gn_apply(const void* x, const float* acc, const void* gamma, const void* beta, void* y, int32_t B, int64_t P,
+                  int32_t C, float eps, int32_t gelu, vmlp_stream_t stream);
+/* dx of y = [gelu](gn(x)); dn: bf16 scratch [B*P*C]; acc2: fp32 [B][2] zero-filled; dgamma/dbeta fp32 += */
+int vmlp_gn_bwd(const void* dy, const void* x, const float* acc, const void* gamma, const void* beta, void* dn,
+                float* acc2, float* dgamma, float* dbeta, void* dx, int32_t B, int64_t P, int32_t C, float eps,
+                int32_t gelu, vmlp_stream_t stream);
+/* out = (A[c]*p + Bq[c]*q + Cc[c]) * (z ? gelu_erf'(z) : 1); q, Bq, z optional; A/Bq/Cc fp32 [C] */
+int vmlp_chan_lin(const void* p, const void* q, const void* z, const float* A, const float* Bq, const float* Cc,
+                  void* out, int64_t rows, int32_t C, vmlp_stream_t stream);
+/* BatchNorm2d training-mode coefficients (conv_mixer.py:20,27,31): s1 = sum(a), s2 = sum(a*a) over R rows */
+int vmlp_bn_fwd_coef(const float* s1, const float* s2, const void* gamma, const void* beta, float* A, float* Cc,
+                     float* mean, float* rstd, float* running_mean, float* running_var, int64_t R, float eps,
+                     float momentum, int32_t C, vmlp_stream_t stream);
+int vmlp_bn_bwd_coef(const float* sdy, const float* sdya, const void* gamma, const float* mean, const float* rstd,
+                     float* A, float* Bq, float* Cc, float* dgamma, float* dbeta, int64_t R, int32_t C,
+                     vmlp_stream_t stream);
+
+/* S2-MLPv2 split attention (s2_mlp_v2.py:31-69).  t: [B,H,W,3C] (mlp1 output); branch k = t[..., kC:(k+1)C] read through
+ * spatial_shift1 (k=0), spatial_shift2 (k=1) or unshifted (k=2) as load-time clamp offsets.
+ *   sum      : a_f32[b,c] += sum_pos (x_0 + x_1 + x_2)                        (caller zero-fills a_f32)
+ *   combine  : out[b,pos,c] = sum_k softmax_k(hat[b,:,c]) * x_k[b,pos,c]      (hat: bf16 [B,3C])
+ *   combine_bwd : dt (bf16 [B,H,W,3C]) and dhat (bf16 [B,3C]) from dout; dbar_f32 is a zero-filled fp32 [B,3C] scratch
+ *   sum_bwd  : dt from da (bf16 [B,C]) */
+int vmlp_s2v2_sum(const void* t, float* a_f32, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
+int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                      vmlp_stream_t stream);
+int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, float* dbar_f32, void* dhat, void* dt,
+                          int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
+int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * MLP-Mixer block: models_pytorch/mlp_mixer.py:35-40
  *     u = x + TokenFF(LN1(x))   (FeedForward with Conv1d(k=1) over tokens, :16-27,:37)
  *     y = u + ChanFF(LN2(u))    (FeedForward with Linear over channels,    :38)

@@ -4,3 +4,5 @@ from . import _lib, ops  # noqa: F401
 from .mlp_mixer import MLPMixer, MLPMixerForImageClassification  # noqa: F401
 from .res_mlp import MLPblock, ResMLP, ResMLPForImageClassification  # noqa: F401
 from .g_mlp import gMLP, gMLPBlock, gMLPForImageClassification  # noqa: F401
+from .s2_mlp import S2MLPv1, S2MLPv1_deep, S2MLPv1_wide, S2MLPv2  # noqa: F401
+from .as_mlp import AS_MLP  # noqa: F401

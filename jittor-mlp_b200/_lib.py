@@ -103,6 +103,24 @@ SYMBOLS = [
     ("vmlp_dgelu_mul", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
     ("vmlp_gate_bwd", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                 c_int64, c_void_p, c_int64, c_int64, c_int32, c_void_p]),
+    ("vmlp_shift_nhwc", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                  _P(c_int32), _P(c_int32), _P(c_int32), c_void_p]),
+    ("vmlp_gn_stats", c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p]),
+    ("vmlp_gn_apply", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_float,
+                                c_int32, c_void_p]),
+    ("vmlp_gn_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_int32, c_int64, c_int32, c_float, c_int32, c_void_p]),
+    ("vmlp_chan_lin", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                c_void_p]),
+    ("vmlp_bn_fwd_coef", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int64, c_float, c_float, c_int32, c_void_p]),
+    ("vmlp_bn_bwd_coef", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    ("vmlp_s2v2_sum", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_combine", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_combine_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                        c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_sum_bwd", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_mixer_block_fwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, _P(MixerSaved), c_void_p]),
     ("vmlp_mixer_grad_elems", c_int64, [_P(MixerParams)]),
     ("vmlp_mixer_bwd_workspace_elems", c_int64, [_P(MixerParams)]),

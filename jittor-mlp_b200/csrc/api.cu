@@ -3,6 +3,7 @@
 #include "../../include/vmlp_b200.h"
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
+#include "spatial.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -434,6 +435,174 @@ int vmlp_gate_bwd(const void* dg, int64_t dg_ld, const void* vt, int64_t vt_ld, 
     return fail(VMLP_EALIGN, "gate_bwd alignment");
   ew_kernel<2><<<ew_grid(rows * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)dg, dg_ld, (cbf)vt, vt_ld, (cbf)zp_u, zp_ld, (cbf)u, u_ld, (bf)out, out_ld, (bf)out2, out2_ld, rows, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+// ============================================================================================ spatial operators
+int vmlp_shift_nhwc(const void* in, void* out, int32_t B, int32_t H, int32_t W, int32_t C, int32_t mode,
+                    int32_t ngroups, const int32_t* start, const int32_t* dh, const int32_t* dw, vmlp_stream_t stream) {
+  if (!in || !out || !start || !dh || !dw || B <= 0 || H <= 0 || W <= 0 || (C % 8) || ngroups < 1 || ngroups > 8 ||
+      mode < 0 || mode > 2)
+    return fail(VMLP_EINVAL, "shift_nhwc args");
+  if (!aligned16(in) || !aligned16(out)) return fail(VMLP_EALIGN, "shift_nhwc alignment");
+  ShiftTable t;
+  memset(&t, 0, sizeof(t));
+  t.ngroups = ngroups;
+  for (int g = 0; g < ngroups; ++g) { t.start[g] = start[g]; t.dh[g] = dh[g]; t.dw[g] = dw[g]; }
+  t.start[ngroups] = start[ngroups];
+  const long long total = (long long)B * H * W * (C / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mode == 0) shift_nhwc_kernel<0><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
+  else if (mode == 1) shift_nhwc_kernel<1><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
+  else shift_nhwc_kernel<2><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+static dim3 gn_grid(int B, long long per_sample_vec) {
+  long long gx = (per_sample_vec + RW_THREADS * 4 - 1) / (RW_THREADS * 4);
+  const long long cap = ((long long)device_info().sms * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)B);
+}
+int vmlp_gn_stats(const void* x, float* acc, int32_t B, int64_t P, int32_t C, vmlp_stream_t stream) {
+  if (!x || !acc || B <= 0 || P <= 0 || (C % 8)) return fail(VMLP_EINVAL, "gn_stats args");
+  if (!aligned16(x)) return fail(VMLP_EALIGN, "gn_stats alignment");
+  const long long psv = P * (C / 8);
+  gn_stats_kernel<<<gn_grid(B, psv), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>((cbf)x, acc, psv);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_gn_apply(const void* x, const float* acc, const void* gamma, const void* beta, void* y, int32_t B, int64_t P,
+                  int32_t C, float eps, int32_t gelu, vmlp_stream_t stream) {
+  if (!x || !acc || !gamma || !beta || !y || B <= 0 || P <= 0 || (C % 8)) return fail(VMLP_EINVAL, "gn_apply args");
+  if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta)) return fail(VMLP_EALIGN, "gn_apply alignment");
+  const long long psv = P * (C / 8), total = psv * B;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (gelu) gn_apply_kernel<1><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)y, psv, C, eps, total);
+  else gn_apply_kernel<0><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)y, psv, C, eps, total);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_gn_bwd(const void* dy, const void* x, const float* acc, const void* gamma, const void* beta, void* dn,
+                float* acc2, float* dgamma, float* dbeta, void* dx, int32_t B, int64_t P, int32_t C, float eps,
+                int32_t gelu, vmlp_stream_t stream) {
+  if (!dy || !x || !acc || !gamma || !beta || !dn || !acc2 || !dgamma || !dbeta || !dx || B <= 0 || P <= 0 || (C % 8))
+    return fail(VMLP_EINVAL, "gn_bwd args");
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dn) || !aligned16(dx) || !aligned16(gamma) || !aligned16(beta))
+    return fail(VMLP_EALIGN, "gn_bwd alignment");
+  const long long psv = P * (C / 8), total = psv * B;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sh = 2 * (size_t)C * sizeof(float);
+  if (gelu) gn_bwd_reduce_kernel<1><<<gn_grid(B, psv), RW_THREADS, sh, st>>>((cbf)dy, (cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)dn, acc2, dgamma, dbeta, psv, C, eps);
+  else gn_bwd_reduce_kernel<0><<<gn_grid(B, psv), RW_THREADS, sh, st>>>((cbf)dy, (cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)dn, acc2, dgamma, dbeta, psv, C, eps);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  gn_bwd_apply_kernel<<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)dn, (cbf)x, acc, acc2, (cbf)gamma, (bf)dx, psv, C, eps, total);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_chan_lin(const void* p, const void* q, const void* z, const float* A, const float* Bq, const float* Cc,
+                  void* out, int64_t rows, int32_t C, vmlp_stream_t stream) {
+  if (!p || !A || !Cc || !out || rows <= 0 || (C % 8) || (q && !Bq)) return fail(VMLP_EINVAL, "chan_lin args");
+  if (!aligned16(p) || !aligned16(out) || (q && !aligned16(q)) || (z && !aligned16(z))) return fail(VMLP_EALIGN, "chan_lin alignment");
+  const long long total = rows * (C / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = ew_grid(total);
+  if (q && z) chan_lin_kernel<1, 1><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);
+  else if (q) chan_lin_kernel<1, 0><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);
+  else if (z) chan_lin_kernel<0, 1><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);
+  else chan_lin_kernel<0, 0><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_bn_fwd_coef(const float* s1, const float* s2, const void* gamma, const void* beta, float* A, float* Cc,
+                     float* mean, float* rstd, float* running_mean, float* running_var, int64_t R, float eps,
+                     float momentum, int32_t C, vmlp_stream_t stream) {
+  if (!s1 || !s2 || !gamma || !beta || !A || !Cc || !mean || !rstd || R <= 0 || C <= 0) return fail(VMLP_EINVAL, "bn_fwd_coef args");
+  bn_fwd_coef_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      s1, s2, (cbf)gamma, (cbf)beta, A, Cc, mean, rstd, running_mean, running_var, (float)R, eps, momentum, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_bn_bwd_coef(const float* sdy, const float* sdya, const void* gamma, const float* mean, const float* rstd,
+                     float* A, float* Bq, float* Cc, float* dgamma, float* dbeta, int64_t R, int32_t C,
+                     vmlp_stream_t stream) {
+  if (!sdy || !sdya || !gamma || !mean || !rstd || !A || !Bq || !Cc || !dgamma || !dbeta || R <= 0 || C <= 0)
+    return fail(VMLP_EINVAL, "bn_bwd_coef args");
+  bn_bwd_coef_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sdy, sdya, (cbf)gamma, mean, rstd, A, Bq, Cc, dgamma, dbeta, (float)R, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+static int s2v2_check(const void* a, const void* b, int B, int H, int W, int C) {
+  if (!a || !b || B <= 0 || H <= 0 || W <= 0 || (C % 8) || C > 2048) return fail(VMLP_EINVAL, "s2v2 args");
+  if (!aligned16(a) || !aligned16(b)) return fail(VMLP_EALIGN, "s2v2 alignment");
+  return VMLP_OK;
+}
+static dim3 s2v2_reduce_grid(int B, int H, int W, int C) {
+  const int plane = RW_THREADS / (C / 8);
+  long long gx = ((long long)H * W + plane - 1) / plane;
+  const long long cap = ((long long)device_info().sms * 4 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)B);
+}
+int vmlp_s2v2_sum(const void* t, float* a_f32, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
+  int rc = s2v2_check(t, a_f32, B, H, W, C);
+  if (rc) return rc;
+  s2v2_reduce_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, RW_THREADS * 8 * sizeof(float),
+                          static_cast<cudaStream_t>(stream)>>>((cbf)t, nullptr, a_f32, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
+                      vmlp_stream_t stream) {
+  int rc = s2v2_check(t, out, B, H, W, C);
+  if (rc) return rc;
+  if (!hat || !aligned16(hat)) return fail(VMLP_EALIGN, "s2v2 hat");
+  s2v2_combine_kernel<<<ew_grid((long long)B * H * W * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)t, (cbf)hat, (bf)out, B, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, float* dbar_f32, void* dhat, void* dt,
+                          int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
+  int rc = s2v2_check(t, dt, B, H, W, C);
+  if (rc) return rc;
+  if (!hat || !dout || !dbar_f32 || !dhat || !aligned16(hat) || !aligned16(dout) || !aligned16(dhat)) return fail(VMLP_EALIGN, "s2v2 bwd");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  s2v2_reduce_kernel<1><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, RW_THREADS * 24 * sizeof(float), st>>>(
+      (cbf)t, (cbf)dout, dbar_f32, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  const long long nv = (long long)B * (C / 8);
+  s2v2_softmax_bwd_kernel<<<(int)((nv + 127) / 128), 128, 0, st>>>((cbf)hat, dbar_f32, (bf)dhat, B, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  s2v2_dt_kernel<0><<<ew_grid((long long)B * H * W * (C / 8)), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, (bf)dt, B, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
+  int rc = s2v2_check(da, dt, B, H, W, C);
+  if (rc) return rc;
+  s2v2_dt_kernel<1><<<ew_grid((long long)B * H * W * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)da, nullptr, (bf)dt, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

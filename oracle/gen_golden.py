@@ -24,6 +24,12 @@ CASES = {
                      (3, 3, 48, 40)),
     "resmlp_tiny": ("res_mlp", "ResMLPForImageClassification",
                     dict(d_model=64, depth=2, image_size=32, patch_size=8, num_classes=10), (2, 3, 32, 32)),
+    "s2v1_tiny": ("s2_mlp_v1", "S2MLPv1", dict(image_size=32, patch_size=[4, 2], d_model=[32, 64], depth=[1, 2],
+                                               expansion_factor=[2, 3], num_classes=10), (2, 3, 32, 32)),
+    "s2v2_tiny": ("s2_mlp_v2", "S2MLPv2", dict(image_size=(32, 24), patch_size=[4, 2], d_model=[24, 64], depth=[1, 2],
+                                               expansion_factor=[2, 3], num_classes=10), (2, 3, 32, 24)),
+    "asmlp_tiny": ("as_mlp", "AS_MLP", dict(img_size=32, patch_size=4, embed_dim=24, depths=[1, 2], shift_size=5,
+                                            num_classes=10, drop_path_rate=0.), (2, 3, 32, 32)),
     "gmlp_tiny": ("g_mlp", "gMLPForImageClassification",
                   dict(image_size=32, patch_size=8, num_classes=10, d_model=64, d_ffn=128, depth=2), (2, 3, 32, 32)),
 }

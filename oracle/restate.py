@@ -120,3 +120,125 @@ def compare_py_metric(a, b):
     """The reference's own parity metric, mean(|(x+1)-(y+1)| / |y+1|) (compare.py:179-186)."""
     a, b = a.detach().double(), b.detach().double()
     return float(((a + 1) - (b + 1)).abs().div((b + 1).abs()).mean())
+
+
+# ----------------------------------------------------------------------------------------------- shift family helpers
+def linear(x, w, b=None):
+    """x [..., Cin] @ W^T (+ b); W may be a Linear weight [out, in] or a 1x1 Conv2d weight [out, in, 1, 1]."""
+    y = x @ w.reshape(w.shape[0], -1).t()
+    return y if b is None else y + b
+
+
+def shift_tokens(x, groups, clamp):
+    """x [B, H, W, C]; groups = [(c_lo, c_hi, dh, dw)]: out[h, w] = x[h + dh, w + dw] per channel group, zero outside
+    (AS-MLP Shift kernel, shift_cuda.py:44-72) or clamped to the edge (S2-MLP intended semantics).
+    Written with explicit index tensors (no roll / no in-place slice copies)."""
+    B, H, W, C = x.shape
+    out = torch.zeros_like(x)
+    hh = torch.arange(H)
+    ww = torch.arange(W)
+    for lo, hi, dh, dw in groups:
+        hs, ws = hh + dh, ww + dw
+        if clamp:
+            g = x[:, hs.clamp(0, H - 1)][:, :, ws.clamp(0, W - 1)][..., lo:hi]
+        else:
+            g = x[:, hs.clamp(0, H - 1)][:, :, ws.clamp(0, W - 1)][..., lo:hi]
+            ok = ((hs >= 0) & (hs < H))[:, None] & ((ws >= 0) & (ws < W))[None, :]
+            g = g * ok[None, :, :, None].to(x.dtype)
+        out = torch.cat([out[..., :lo], g, out[..., hi:]], -1)
+    return out
+
+
+def s2_groups(C, plan):
+    """Channel quarters and offsets of spatial_shift1 / spatial_shift2 (s2_mlp_v2.py:15-29):
+    `x[:,1:] = x[:,:-1]` is out[i] = in[i-1]."""
+    q = [0, C // 4, C // 2, C * 3 // 4, C]
+    offs = [(-1, 0), (1, 0), (0, -1), (0, 1)] if plan == 1 else [(0, -1), (0, 1), (-1, 0), (1, 0)]
+    return [(q[i], q[i + 1], offs[i][0], offs[i][1]) for i in range(4)]
+
+
+def as_groups(C, S, dim):
+    """Shift(kernel_size=S, dim): group g = c // ceil(C/S) reads position + (S//2 - g) (shift_cuda.py:44-72)."""
+    cs = -(-C // S)
+    out = []
+    for g in range(S):
+        if g * cs >= C:
+            break
+        s = S // 2 - g
+        out.append((g * cs, min((g + 1) * cs, C), s, 0) if dim == 2 else (g * cs, min((g + 1) * cs, C), 0, s))
+    return out
+
+
+def group_norm1(x, w, b, eps=1e-5):
+    """nn.GroupNorm(1, C) on channels-last x [B, H, W, C]: statistics over the whole sample (as_mlp.py:343-344)."""
+    mu = x.mean((1, 2, 3), keepdim=True)
+    var = ((x - mu) ** 2).mean((1, 2, 3), keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+# ----------------------------------------------------------------------------------------------- S2-MLP v1 / v2
+def s2v1_forward(sd, x, depths, patch_sizes):
+    """S2MLPv1.forward (s2_mlp_v1.py:88-93, block :32-46), clamp-shift semantics."""
+    t = x
+    for s, (depth, ps) in enumerate(zip(depths, patch_sizes)):
+        t = F.conv2d(t, sd[f"stages.{s}.0.weight"], sd[f"stages.{s}.0.bias"], stride=ps).permute(0, 2, 3, 1)
+        C = t.shape[-1]
+        for i in range(depth):
+            p = f"stages.{s}.1.model.{i}."
+            h = gelu(linear(layer_norm(t, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"]), sd[p + "0.fn.0.weight"], sd[p + "0.fn.0.bias"]))
+            t = t + linear(shift_tokens(h, s2_groups(C, 1), True), sd[p + "0.fn.3.weight"], sd[p + "0.fn.3.bias"])
+            h = gelu(linear(layer_norm(t, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"]), sd[p + "1.fn.0.weight"], sd[p + "1.fn.0.bias"]))
+            t = t + linear(h, sd[p + "1.fn.3.weight"], sd[p + "1.fn.3.bias"])
+        t = t.permute(0, 3, 1, 2)
+    return linear(t.mean((2, 3)), sd["mlp_head.1.weight"], sd["mlp_head.1.bias"])
+
+
+def s2v2_forward(sd, x, depths, patch_sizes):
+    """S2MLPv2.forward (s2_mlp_v2.py:129-132; S2Attention :60-69; SplitAttention :41-51)."""
+    t = x
+    for s, (depth, ps) in enumerate(zip(depths, patch_sizes)):
+        t = F.conv2d(t, sd[f"stages.{s}.0.weight"], sd[f"stages.{s}.0.bias"], stride=ps).permute(0, 2, 3, 1)
+        C = t.shape[-1]
+        for i in range(depth):
+            p = f"stages.{s}.1.model.{i}."
+            u = linear(layer_norm(t, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"]), sd[p + "0.fn.mlp1.weight"], sd[p + "0.fn.mlp1.bias"])
+            xs = [shift_tokens(u[..., :C], s2_groups(C, 1), True), shift_tokens(u[..., C:2 * C], s2_groups(C, 2), True), u[..., 2 * C:]]
+            a = (xs[0] + xs[1] + xs[2]).sum((1, 2))                                   # [B, C]
+            hat = linear(gelu(linear(a, sd[p + "0.fn.split_attention.mlp1.weight"])), sd[p + "0.fn.split_attention.mlp2.weight"])
+            bar = torch.softmax(hat.reshape(-1, 3, C), 1)                             # [B, 3, C]
+            o = sum(bar[:, k, None, None, :] * xs[k] for k in range(3))
+            t = t + linear(o, sd[p + "0.fn.mlp2.weight"], sd[p + "0.fn.mlp2.bias"])
+            h = gelu(linear(layer_norm(t, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"]), sd[p + "1.fn.0.weight"], sd[p + "1.fn.0.bias"]))
+            t = t + linear(h, sd[p + "1.fn.3.weight"], sd[p + "1.fn.3.bias"])
+        t = t.permute(0, 3, 1, 2)
+    return linear(t.mean((2, 3)), sd["mlp_head.1.weight"], sd["mlp_head.1.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- AS-MLP
+def asmlp_block(sd, p, t, S):
+    """AxialShiftedBlock.forward (as_mlp.py:149-162) with AxialShift (as_mlp.py:55-95) on channels-last t; DropPath = identity."""
+    C = t.shape[-1]
+    n = group_norm1(t, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+    a = p + "axial_shift."
+    v = gelu(group_norm1(linear(n, sd[a + "conv1.weight"], sd.get(a + "conv1.bias")), sd[a + "norm1.weight"], sd[a + "norm1.bias"]))
+    lr = gelu(linear(shift_tokens(v, as_groups(C, S, 3), False), sd[a + "conv2_1.weight"], sd.get(a + "conv2_1.bias")))
+    td = gelu(linear(shift_tokens(v, as_groups(C, S, 2), False), sd[a + "conv2_2.weight"], sd.get(a + "conv2_2.bias")))
+    t = t + linear(group_norm1(lr + td, sd[a + "norm2.weight"], sd[a + "norm2.bias"]), sd[a + "conv3.weight"], sd.get(a + "conv3.bias"))
+    n = group_norm1(t, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    return t + linear(gelu(linear(n, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])), sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+
+
+def asmlp_forward(sd, x, depths, patch_size=4, shift_size=5):
+    """AS_MLP.forward (as_mlp.py:428-443) with drop_path = 0 / eval."""
+    t = F.conv2d(x, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=patch_size).permute(0, 2, 3, 1)
+    if "patch_embed.norm.weight" in sd:
+        t = group_norm1(t, sd["patch_embed.norm.weight"], sd["patch_embed.norm.bias"])
+    for li, depth in enumerate(depths):
+        for i in range(depth):
+            t = asmlp_block(sd, f"layers.{li}.blocks.{i}.", t, shift_size)
+        if li < len(depths) - 1:                                    # PatchMerging (as_mlp.py:197-216)
+            t = torch.cat([t[:, 0::2, 0::2], t[:, 1::2, 0::2], t[:, 0::2, 1::2], t[:, 1::2, 1::2]], -1)
+            d = f"layers.{li}.downsample."
+            t = linear(group_norm1(t, sd[d + "norm.weight"], sd[d + "norm.bias"]), sd[d + "reduction.weight"])
+    t = group_norm1(t, sd["norm.weight"], sd["norm.bias"])
+    return linear(t.mean((1, 2)), sd["head.weight"], sd["head.bias"])

@@ -8,7 +8,8 @@ import torch
 import jittor_mlp_b200 as J
 from oracle import ref_loader
 
-CASES = {"mixer_tiny": 1, "mixer_ragged": 1, "resmlp_tiny": 1, "gmlp_tiny": 1}
+CASES = {"mixer_tiny": 1, "mixer_ragged": 1, "resmlp_tiny": 1, "gmlp_tiny": 1, "s2v1_tiny": 1, "s2v2_tiny": 1,
+         "asmlp_tiny": 1}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -25,7 +26,12 @@ def test_state_dict_roundtrip_strict(golden, name):
 @pytest.mark.parametrize("mod,cls", [("mlp_mixer", "MLPMixerForImageClassification"), ("mlp_mixer", "MLPMixer"),
                                      ("res_mlp", "ResMLPForImageClassification"), ("res_mlp", "ResMLP"),
                                      ("res_mlp", "MLPblock"), ("g_mlp", "gMLPForImageClassification"),
-                                     ("g_mlp", "gMLP"), ("g_mlp", "gMLPBlock")])
+                                     ("g_mlp", "gMLP"), ("g_mlp", "gMLPBlock"),
+                                     ("s2_mlp_v1", "S2MLPv1"), ("s2_mlp_v1", "S2MLPv1_deep"), ("s2_mlp_v2", "S2MLPv2"),
+                                     ("as_mlp", "AS_MLP")])
 def test_constructor_signature_matches_reference(mod, cls):
     ref = getattr(ref_loader.load(mod), cls)
-    assert str(inspect.signature(getattr(J, cls).__init__)) == str(inspect.signature(ref.__init__))
+
+    def sig(f):   # parameter names + defaults (function-object defaults compared by name)
+        return [(n, getattr(p.default, "__name__", p.default)) for n, p in inspect.signature(f).parameters.items()]
+    assert sig(getattr(J, cls).__init__ if inspect.isclass(ref) else getattr(J, cls)) == sig(ref.__init__ if inspect.isclass(ref) else ref)

@@ -3,18 +3,17 @@ reference modules and (b), when /root/reference is present, the live reference m
 import pytest
 import torch
 
-from oracle import ref_loader, restate
+from oracle import models, ref_loader, restate
 
-FWD = {"mixer_tiny": restate.mixer_forward, "mixer_ragged": restate.mixer_forward,
-       "resmlp_tiny": restate.resmlp_forward, "gmlp_tiny": restate.gmlp_forward}
+GOLDEN = ["mixer_tiny", "mixer_ragged", "resmlp_tiny", "gmlp_tiny", "s2v1_tiny", "s2v2_tiny", "asmlp_tiny"]
 
 
-@pytest.mark.parametrize("name", sorted(FWD))
+@pytest.mark.parametrize("name", GOLDEN)
 def test_restatement_matches_golden(golden, name):
     fx = golden(name)
     sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in fx["state_dict"].items()}
     x = fx["x"].clone().requires_grad_(True)
-    out = FWD[name](sd, x, fx["kwargs"]["depth"])
+    out = models.forward(fx["cls"], fx["kwargs"], sd, x)
     assert restate.rel_l2(out, fx["out"]) < 1e-5            # fp32 tolerance (north_star: 1e-4)
     assert restate.compare_py_metric(out, fx["out"]) < 1e-4  # the reference's own metric (compare.py:179-186)
     out.square().mean().backward()

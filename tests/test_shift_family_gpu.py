@@ -1,0 +1,137 @@
+"""Shift family on the GPU: S2-MLP v1/v2, AS-MLP (and later Hire-MLP, ConvMixer) against the reference golden vectors,
+plus operator-level checks of the spatial kernels against the oracle restatement."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import jittor_mlp_b200 as J  # noqa: E402
+from jittor_mlp_b200 import fn, fn_s2  # noqa: E402
+from oracle import models, restate  # noqa: E402
+
+DEV = "cuda"
+TOL = 1e-2
+
+
+def bf(t):
+    return t.to(DEV).bfloat16()
+
+
+def run_model(model, x):
+    model = model.to(DEV).bfloat16().train()
+    xg = bf(x).requires_grad_(True)
+    out = model(xg)
+    out.float().square().mean().backward()
+    return out, xg.grad, {k: p.grad for k, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("name", ["s2v1_tiny", "s2v2_tiny", "asmlp_tiny"])
+def test_against_reference_golden(golden, name):
+    fx = golden(name)
+    m = getattr(J, fx["cls"])(**fx["kwargs"])
+    m.load_state_dict(fx["state_dict"], strict=True)
+    out, dx, grads = run_model(m, fx["x"])
+    assert restate.rel_l2(out.cpu(), fx["out"]) < TOL
+    assert restate.rel_l2(dx.cpu(), fx["dx"]) < 3 * TOL
+    scale = float(fx["dx"].abs().max() + 1)
+    for k, g in fx["grads"].items():
+        if g is None:
+            assert grads[k] is None, k
+            continue
+        err = restate.rel_l2(grads[k].cpu(), g)
+        assert err < 4 * TOL or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * scale, (k, err)
+
+
+@pytest.mark.parametrize("C,H,W", [(96, 14, 14), (24, 5, 7), (64, 8, 8)])
+@pytest.mark.parametrize("kind", ["as2", "as3", "s2p1", "s2p2"])
+def test_shift_forward_and_adjoint(C, H, W, kind):
+    """The gather and its adjoint: bit-exact against the index-arithmetic restatement (pure data movement)."""
+    x = torch.randn(3, H, W, C, generator=torch.Generator().manual_seed(0)).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    if kind.startswith("as"):
+        dim = int(kind[-1])
+        ref = restate.shift_tokens(xr, restate.as_groups(C, 5, dim), False)
+        xg = bf(x).requires_grad_(True)
+        out = fn.axial_shift(xg, 5, dim)
+    else:
+        plan = int(kind[-1])
+        ref = restate.shift_tokens(xr, restate.s2_groups(C, plan), True)
+        xg = bf(x).requires_grad_(True)
+        out = fn.s2_shift(xg, plan)
+    assert torch.equal(out.float().cpu(), ref.detach())
+    dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    ref.backward(dy)
+    out.backward(bf(dy))
+    # the adjoint sums at most two bf16 values per element: compare with one bf16 rounding of slack
+    assert restate.rel_l2(xg.grad.cpu(), xr.grad) < 4e-3
+
+
+def test_group_norm1_fwd_bwd():
+    B, H, W, C = 4, 14, 14, 96
+    x = (torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(0)) * 2 + 0.3).bfloat16().float()
+    w = (torch.randn(C, generator=torch.Generator().manual_seed(1)) * 0.2 + 1).bfloat16().float()
+    b = (torch.randn(C, generator=torch.Generator().manual_seed(2)) * 0.2).bfloat16().float()
+    for gelu in (False, True):
+        xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        ref = restate.group_norm1(xr, wr, br)
+        if gelu:
+            ref = restate.gelu(ref)
+        dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3)).bfloat16().float()
+        ref.backward(dy)
+        xg, wg, bg = bf(x).requires_grad_(True), bf(w).requires_grad_(True), bf(b).requires_grad_(True)
+        out = fn.group_norm1(xg, wg, bg, 1e-5, gelu)
+        out.backward(bf(dy))
+        assert restate.rel_l2(out.cpu(), ref) < 5e-3
+        assert restate.rel_l2(xg.grad.cpu(), xr.grad) < TOL
+        assert restate.rel_l2(wg.grad.cpu(), wr.grad) < TOL
+        assert restate.rel_l2(bg.grad.cpu(), br.grad) < TOL
+
+
+def test_s2v2_split_attention_ops():
+    B, H, W, C = 3, 8, 6, 48
+    t = torch.randn(B, H, W, 3 * C, generator=torch.Generator().manual_seed(0)).bfloat16().float()
+    hat = torch.randn(B, 3 * C, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    tr, hr = t.clone().requires_grad_(True), hat.clone().requires_grad_(True)
+    xs = [restate.shift_tokens(tr[..., :C], restate.s2_groups(C, 1), True),
+          restate.shift_tokens(tr[..., C:2 * C], restate.s2_groups(C, 2), True), tr[..., 2 * C:]]
+    a_ref = (xs[0] + xs[1] + xs[2]).sum((1, 2))
+    bar = torch.softmax(hr.reshape(B, 3, C), 1)
+    o_ref = sum(bar[:, k, None, None, :] * xs[k] for k in range(3))
+    da = torch.randn(a_ref.shape, generator=torch.Generator().manual_seed(2)).bfloat16().float()
+    do = torch.randn(o_ref.shape, generator=torch.Generator().manual_seed(3)).bfloat16().float()
+    (a_ref * da).sum().backward(retain_graph=True)
+    dt_a = tr.grad.clone(); tr.grad = None
+    (o_ref * do).sum().backward()
+    tg, hg = bf(t).requires_grad_(True), bf(hat).requires_grad_(True)
+    a = fn_s2.S2v2SumFn.apply(tg)
+    a.backward(bf(da))
+    assert restate.rel_l2(a.cpu(), a_ref) < 5e-3
+    assert restate.rel_l2(tg.grad.cpu(), dt_a) < 5e-3
+    tg.grad = None
+    o = fn_s2.S2v2CombineFn.apply(tg, hg)
+    o.backward(bf(do))
+    assert restate.rel_l2(o.cpu(), o_ref) < 5e-3
+    assert restate.rel_l2(tg.grad.cpu(), tr.grad) < TOL
+    assert restate.rel_l2(hg.grad.cpu(), hr.grad) < TOL
+
+
+@pytest.mark.parametrize("cls,kw,xshape", [
+    ("S2MLPv2", dict(image_size=56, patch_size=[7, 2], d_model=[192, 384], depth=[1, 1], expansion_factor=[3, 3], num_classes=16), (4, 3, 56, 56)),
+    ("AS_MLP", dict(img_size=64, patch_size=4, embed_dim=96, depths=[1, 1], shift_size=5, num_classes=16, drop_path_rate=0.), (4, 3, 64, 64)),
+    ("S2MLPv1", dict(image_size=64, patch_size=[16], d_model=[384], depth=[2], expansion_factor=[4], num_classes=16), (4, 3, 64, 64)),
+])
+def test_config4_channel_widths_against_oracle(cls, kw, xshape):
+    """Real channel widths of BASELINE config 4 (C 96/192/384) at small spatial size, forward + input gradient."""
+    torch.manual_seed(0)
+    m = getattr(J, cls)(**kw)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.03 * torch.randn_like(p))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x = torch.randn(*xshape, generator=torch.Generator().manual_seed(1))
+    xr = x.clone().requires_grad_(True)
+    ref = models.forward(cls, kw, sd, xr)
+    ref.square().mean().backward()
+    out, dx, _ = run_model(m, x)
+    assert restate.rel_l2(out.cpu(), ref) < TOL
+    assert restate.rel_l2(dx.cpu(), xr.grad) < 3 * TOL
