@@ -174,6 +174,33 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
                           int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
 int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
 
+/* Hire-MLP region rearrangement (hire_mlp.py:44-152) as load-time index arithmetic on channels-last tensors.
+ * Padding is circular with Hp = H + (h - H % h), Wp = W + (w - W % w); step = cross_region_step or 0.
+ *   build       : zh [B, Hp/h, W, h*C], zw [B, H, Wp/w, w*C]  (feature axis ordered [region index][channel])
+ *   build_adj   : dx = adjoint of both gathers (sums the circular-padding duplicates)
+ *   combine     : out = base + restore_H(oh) + restore_W(ow), cropped to H x W
+ *   restore_adj : dzh, dzw from dout (entries that land in the cropped padding get 0) */
+typedef struct {
+  int32_t B, H, W, C;
+  int32_t h, w;              /* region sizes */
+  int32_t step_h, step_w;    /* roll amounts (0 when this block does not cross regions) */
+} vmlp_hire_dims;
+int vmlp_hire_build(const void* x, void* zh, void* zw, const vmlp_hire_dims* d, vmlp_stream_t stream);
+int vmlp_hire_build_adj(const void* dzh, const void* dzw, void* dx, const vmlp_hire_dims* d, vmlp_stream_t stream);
+int vmlp_hire_combine(const void* base, const void* oh, const void* ow, void* out, const vmlp_hire_dims* d,
+                      vmlp_stream_t stream);
+int vmlp_hire_restore_adj(const void* dout, void* dzh, void* dzw, const vmlp_hire_dims* d, vmlp_stream_t stream);
+
+/* ConvMixer depthwise k x k convolution, padding "same", channels-last (conv_mixer.py:24); K in {3, 5, 7, 9}.
+ * weight: bf16 [C, 1, K, K].  fwd writes z = conv + bias and a = gelu_erf(z); dgrad is the 180-degree-rotated stencil;
+ * wgrad accumulates fp32 dW [C, K, K] (caller zero-fills). */
+int vmlp_dwconv_fwd(const void* x, const void* weight, const void* bias, void* z, void* a, int32_t B, int32_t H,
+                    int32_t W, int32_t C, int32_t K, vmlp_stream_t stream);
+int vmlp_dwconv_dgrad(const void* dz, const void* weight, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
+                      int32_t K, vmlp_stream_t stream);
+int vmlp_dwconv_wgrad(const void* x, const void* dz, float* dw, int32_t B, int32_t H, int32_t W, int32_t C, int32_t K,
+                      vmlp_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------
  * MLP-Mixer block: models_pytorch/mlp_mixer.py:35-40
  *     u = x + TokenFF(LN1(x))   (FeedForward with Conv1d(k=1) over tokens, :16-27,:37)

@@ -6,3 +6,5 @@ from .res_mlp import MLPblock, ResMLP, ResMLPForImageClassification  # noqa: F40
 from .g_mlp import gMLP, gMLPBlock, gMLPForImageClassification  # noqa: F401
 from .s2_mlp import S2MLPv1, S2MLPv1_deep, S2MLPv1_wide, S2MLPv2  # noqa: F401
 from .as_mlp import AS_MLP  # noqa: F401
+from .hire_mlp import HireMLP  # noqa: F401
+from .conv_mixer import ConvMixer  # noqa: F401

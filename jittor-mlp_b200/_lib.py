@@ -72,6 +72,10 @@ class MixerParams(ctypes.Structure):
                     "ln1_w", "ln1_b", "w1t", "b1t", "w2t", "b2t", "ln2_w", "ln2_b", "w1c", "b1c", "w2c", "b2c")]
 
 
+class HireDims(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("B", "H", "W", "C", "h", "w", "step_h", "step_w")]
+
+
 class MixerSaved(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("xhat1", "z1", "h1", "u", "xhat2", "z2", "h2", "stats", "w1t_pad")]
 
@@ -121,6 +125,14 @@ SYMBOLS = [
     ("vmlp_s2v2_combine_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                         c_int32, c_int32, c_void_p]),
     ("vmlp_s2v2_sum_bwd", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_hire_build", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
+    ("vmlp_hire_build_adj", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
+    ("vmlp_hire_combine", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
+    ("vmlp_hire_restore_adj", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
+    ("vmlp_dwconv_fwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                  c_int32, c_void_p]),
+    ("vmlp_dwconv_dgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_dwconv_wgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_mixer_block_fwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, _P(MixerSaved), c_void_p]),
     ("vmlp_mixer_grad_elems", c_int64, [_P(MixerParams)]),
     ("vmlp_mixer_bwd_workspace_elems", c_int64, [_P(MixerParams)]),

@@ -4,6 +4,7 @@
 #include "gemm_sm100.cuh"
 #include "rowwise.cuh"
 #include "spatial.cuh"
+#include "spatial2.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -606,6 +607,135 @@ int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W,
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
+}
+
+static int hire_dims(const vmlp_hire_dims* d, HireDims& o) {
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0 || (d->C % 8) || d->h <= 0 || d->w <= 0) return fail(VMLP_EINVAL, "hire dims");
+  o.B = d->B; o.H = d->H; o.W = d->W; o.C = d->C;
+  o.nh = d->h; o.Hp = d->H + (d->h - d->H % d->h); o.Gh = o.Hp / d->h; o.step_h = d->step_h;
+  o.nw = d->w; o.Wp = d->W + (d->w - d->W % d->w); o.Gw = o.Wp / d->w; o.step_w = d->step_w;
+  return VMLP_OK;
+}
+int vmlp_hire_build(const void* x, void* zh, void* zw, const vmlp_hire_dims* d, vmlp_stream_t stream) {
+  HireDims hd;
+  int rc = hire_dims(d, hd);
+  if (rc) return rc;
+  if (!x || !zh || !zw || !aligned16(x) || !aligned16(zh) || !aligned16(zw)) return fail(VMLP_EALIGN, "hire_build pointers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nv = hd.C / 8;
+  hire_build_kernel<0><<<ew_grid((long long)hd.B * hd.Gh * hd.W * hd.nh * nv), RW_THREADS, 0, st>>>((cbf)x, (bf)zh, hd);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  hire_build_kernel<1><<<ew_grid((long long)hd.B * hd.H * hd.Gw * hd.nw * nv), RW_THREADS, 0, st>>>((cbf)x, (bf)zw, hd);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_hire_build_adj(const void* dzh, const void* dzw, void* dx, const vmlp_hire_dims* d, vmlp_stream_t stream) {
+  HireDims hd;
+  int rc = hire_dims(d, hd);
+  if (rc) return rc;
+  if (!dzh || !dzw || !dx || !aligned16(dzh) || !aligned16(dzw) || !aligned16(dx)) return fail(VMLP_EALIGN, "hire_build_adj pointers");
+  hire_build_adj_kernel<<<ew_grid((long long)hd.B * hd.H * hd.W * (hd.C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)dzh, (cbf)dzw, (bf)dx, hd);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_hire_combine(const void* base, const void* oh, const void* ow, void* out, const vmlp_hire_dims* d,
+                      vmlp_stream_t stream) {
+  HireDims hd;
+  int rc = hire_dims(d, hd);
+  if (rc) return rc;
+  if (!base || !oh || !ow || !out || !aligned16(base) || !aligned16(oh) || !aligned16(ow) || !aligned16(out))
+    return fail(VMLP_EALIGN, "hire_combine pointers");
+  hire_combine_kernel<<<ew_grid((long long)hd.B * hd.H * hd.W * (hd.C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)base, (cbf)oh, (cbf)ow, (bf)out, hd);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_hire_restore_adj(const void* dout, void* dzh, void* dzw, const vmlp_hire_dims* d, vmlp_stream_t stream) {
+  HireDims hd;
+  int rc = hire_dims(d, hd);
+  if (rc) return rc;
+  if (!dout || !dzh || !dzw || !aligned16(dout) || !aligned16(dzh) || !aligned16(dzw)) return fail(VMLP_EALIGN, "hire_restore_adj pointers");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long nv = hd.C / 8;
+  hire_restore_adj_kernel<0><<<ew_grid((long long)hd.B * hd.Gh * hd.W * hd.nh * nv), RW_THREADS, 0, st>>>((cbf)dout, (bf)dzh, hd);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  hire_restore_adj_kernel<1><<<ew_grid((long long)hd.B * hd.H * hd.Gw * hd.nw * nv), RW_THREADS, 0, st>>>((cbf)dout, (bf)dzw, hd);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+}  // extern "C" (templates need C++ linkage)
+template <int K, int FLIP, int EPI>
+static int dwconv_launch(const void* x, const void* w, const void* bias, void* o1, void* o2, int B, int H, int W, int C,
+                         cudaStream_t st) {
+  auto kern = dwconv_kernel<K, FLIP, EPI>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+  const long long tiles = (long long)B * ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
+  const int cb = (C + DW_CH - 1) / DW_CH;
+  long long gx = ((long long)device_info().sms * 3 + cb - 1) / cb;
+  if (gx > tiles) gx = tiles;
+  kern<<<dim3((unsigned)gx, (unsigned)cb), 256, DwSmem<K>::BYTES, st>>>((cbf)x, (cbf)w, (cbf)bias, (bf)o1, (bf)o2, B, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+template <int K>
+static int dwconv_wgrad_launch(const void* x, const void* dz, float* dw, int B, int H, int W, int C, cudaStream_t st) {
+  auto kern = dwconv_wgrad_kernel<K>;
+  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+  const long long tiles = (long long)B * ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
+  const int cb = (C + DW_CH - 1) / DW_CH;
+  long long gx = ((long long)device_info().sms * 3 + cb - 1) / cb;
+  if (gx > tiles) gx = tiles;
+  kern<<<dim3((unsigned)gx, (unsigned)cb), 256, DwSmem<K>::BYTES, st>>>((cbf)x, (cbf)dz, dw, B, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+extern "C" {
+static int dwconv_check(const void* a, const void* b, const void* c, int B, int H, int W, int C, int K) {
+  if (!a || !b || !c || B <= 0 || H <= 0 || W <= 0 || (C % 8)) return fail(VMLP_EINVAL, "dwconv args");
+  if (K != 3 && K != 5 && K != 7 && K != 9) return fail(VMLP_EINVAL, "dwconv kernel_size %d not in {3,5,7,9}", K);
+  if (!aligned16(a) || !aligned16(c)) return fail(VMLP_EALIGN, "dwconv alignment");
+  return VMLP_OK;
+}
+#define DW_DISPATCH(K, CALL3, CALL5, CALL7, CALL9) ((K) == 3 ? (CALL3) : (K) == 5 ? (CALL5) : (K) == 7 ? (CALL7) : (CALL9))
+int vmlp_dwconv_fwd(const void* x, const void* weight, const void* bias, void* z, void* a, int32_t B, int32_t H,
+                    int32_t W, int32_t C, int32_t K, vmlp_stream_t stream) {
+  int rc = dwconv_check(x, weight, z, B, H, W, C, K);
+  if (rc) return rc;
+  if (!bias || !a) return fail(VMLP_EINVAL, "dwconv_fwd needs bias and both outputs");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return DW_DISPATCH(K, (dwconv_launch<3, 0, 1>(x, weight, bias, z, a, B, H, W, C, st)),
+                     (dwconv_launch<5, 0, 1>(x, weight, bias, z, a, B, H, W, C, st)),
+                     (dwconv_launch<7, 0, 1>(x, weight, bias, z, a, B, H, W, C, st)),
+                     (dwconv_launch<9, 0, 1>(x, weight, bias, z, a, B, H, W, C, st)));
+}
+int vmlp_dwconv_dgrad(const void* dz, const void* weight, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
+                      int32_t K, vmlp_stream_t stream) {
+  int rc = dwconv_check(dz, weight, dx, B, H, W, C, K);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return DW_DISPATCH(K, (dwconv_launch<3, 1, 0>(dz, weight, nullptr, dx, nullptr, B, H, W, C, st)),
+                     (dwconv_launch<5, 1, 0>(dz, weight, nullptr, dx, nullptr, B, H, W, C, st)),
+                     (dwconv_launch<7, 1, 0>(dz, weight, nullptr, dx, nullptr, B, H, W, C, st)),
+                     (dwconv_launch<9, 1, 0>(dz, weight, nullptr, dx, nullptr, B, H, W, C, st)));
+}
+int vmlp_dwconv_wgrad(const void* x, const void* dz, float* dw, int32_t B, int32_t H, int32_t W, int32_t C, int32_t K,
+                      vmlp_stream_t stream) {
+  int rc = dwconv_check(x, dz, dz, B, H, W, C, K);
+  if (rc) return rc;
+  if (!dw) return fail(VMLP_EINVAL, "dwconv_wgrad null dw");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return DW_DISPATCH(K, (dwconv_wgrad_launch<3>(x, dz, dw, B, H, W, C, st)), (dwconv_wgrad_launch<5>(x, dz, dw, B, H, W, C, st)),
+                     (dwconv_wgrad_launch<7>(x, dz, dw, B, H, W, C, st)), (dwconv_wgrad_launch<9>(x, dz, dw, B, H, W, C, st)));
 }
 
 // ============================================================================================ MLP-Mixer block

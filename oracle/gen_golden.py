@@ -30,6 +30,10 @@ CASES = {
                                                expansion_factor=[2, 3], num_classes=10), (2, 3, 32, 24)),
     "asmlp_tiny": ("as_mlp", "AS_MLP", dict(img_size=32, patch_size=4, embed_dim=24, depths=[1, 2], shift_size=5,
                                             num_classes=10, drop_path_rate=0.), (2, 3, 32, 32)),
+    "hire_tiny": ("hire_mlp", "HireMLP", dict(patch_size=4, d_model=[16, 32], h=[4, 3], w=[4, 3], cross_region_step=[2, 1],
+                                             depth=[2, 2], num_classes=10), (2, 3, 40, 32)),
+    "convmixer_tiny": ("conv_mixer", "ConvMixer", dict(dim=32, depth=2, kernel_size=5, patch_size=4, n_classes=10),
+                       (4, 3, 32, 32)),
     "gmlp_tiny": ("g_mlp", "gMLPForImageClassification",
                   dict(image_size=32, patch_size=8, num_classes=10, d_model=64, d_ffn=128, depth=2), (2, 3, 32, 32)),
 }

@@ -242,3 +242,80 @@ def asmlp_forward(sd, x, depths, patch_size=4, shift_size=5):
             t = linear(group_norm1(t, sd[d + "norm.weight"], sd[d + "norm.bias"]), sd[d + "reduction.weight"])
     t = group_norm1(t, sd["norm.weight"], sd["norm.bias"])
     return linear(t.mean((1, 2)), sd["head.weight"], sd["head.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- Hire-MLP
+def hire_block(sd, p, t, h, w, step):
+    """HireMLPBlock.forward (hire_mlp.py:130-152) on channels-last t = LN(x) [B, H, W, C], index formulation of
+    SURVEY.md Appendix A6: circular pad (a full extra region when divisible), roll, strided region gather, bottleneck
+    1x1-conv MLP, inverse gather, roll back, crop."""
+    B, H, W, C = t.shape
+    Hp, Wp = H + (h - H % h), W + (w - W % w)
+    xp = t[:, torch.arange(Hp) % H][:, :, torch.arange(Wp) % W]                 # circular pad right / bottom
+
+    def branch(xp, n, L, axis, key):
+        G = L // n
+        src = (torch.arange(L) - step) % L                                       # roll(+step): rolled[r] = x[r - step]
+        xr = xp.index_select(axis, src)
+        # region gather: position r = i*G + g -> feature index (c, i) at spatial g
+        shape = list(xr.shape)
+        xr = xr.reshape(shape[:axis] + [n, G] + shape[axis + 1:])               # [.., i, g, ..]
+        xr = xr.movedim(axis, -1)                                                # [..., g, .., C, i]
+        z = xr.reshape(list(xr.shape[:-2]) + [C * n])                            # feature index c*n + i
+        hdn = gelu(linear(z, sd[key + "net.0.weight"], sd[key + "net.0.bias"]))
+        o = linear(hdn, sd[key + "net.2.weight"], sd[key + "net.2.bias"])
+        o = o.reshape(list(o.shape[:-1]) + [C, n]).movedim(-1, axis)             # back to [.., i, g, .., C]
+        shape2 = list(o.shape)
+        o = o.reshape(shape2[:axis] + [L] + shape2[axis + 2:])
+        return o.index_select(axis, (torch.arange(L) + step) % L)                # roll(-step)
+
+    xh = branch(xp, h, Hp, 1, p + "proj_h.")
+    xw = branch(xp, w, Wp, 2, p + "proj_w.")
+    xc = linear(xp, sd[p + "proj_c.weight"], sd[p + "proj_c.bias"])
+    return (xc + xh + xw)[:, :H, :W]
+
+
+def hire_forward(sd, x, kw):
+    """HireMLP.forward (hire_mlp.py:223-229); kw = constructor kwargs."""
+    d_model = kw.get("d_model", [64, 128, 320, 512]); hs = kw.get("h", [4, 3, 3, 2]); ws = kw.get("w", [4, 3, 3, 2])
+    steps = kw.get("cross_region_step", [2, 2, 1, 1]); interval = kw.get("cross_region_interval", 2)
+    depth = kw.get("depth", [4, 6, 24, 3]); ps = kw.get("patch_size", 4)
+    t = F.conv2d(x, sd["patcher.reduction.0.weight"], sd["patcher.reduction.0.bias"], stride=ps, padding=3)
+    t = t.permute(0, 2, 3, 1)
+    if "patcher.reduction.1.1.weight" in sd:
+        t = layer_norm(t, sd["patcher.reduction.1.1.weight"], sd["patcher.reduction.1.1.bias"])
+    for s in range(len(depth)):
+        for i in range(depth[s]):
+            p = f"layers.{s}.model.{i}."
+            step = steps[s] if ((i + 1) % interval == 0) else 0
+            n = layer_norm(t, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"])
+            t = t + hire_block(sd, p + "0.fn.0.", n, hs[s], ws[s], step)
+            n = layer_norm(t, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"])
+            t = t + linear(gelu(linear(n, sd[p + "1.fn.0.weight"], sd[p + "1.fn.0.bias"])), sd[p + "1.fn.3.weight"], sd[p + "1.fn.3.bias"])
+        if s + 1 < len(depth):
+            m = f"layers.{s}.patch_merge.1.reduction.0."
+            t = F.conv2d(t.permute(0, 3, 1, 2), sd[m + "weight"], sd[m + "bias"], stride=2, padding=1).permute(0, 2, 3, 1)
+    t = layer_norm(t, sd["mlp_head.0.weight"], sd["mlp_head.0.bias"])
+    return linear(t.mean((1, 2)), sd["mlp_head.2.weight"], sd["mlp_head.2.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- ConvMixer
+def batch_norm_train(x, w, b, eps=1e-5):
+    """nn.BatchNorm2d in train(): biased batch variance over (B, H, W) per channel (conv_mixer.py:20)."""
+    mu = x.mean((0, 2, 3), keepdim=True)
+    var = ((x - mu) ** 2).mean((0, 2, 3), keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w[None, :, None, None] + b[None, :, None, None]
+
+
+def convmixer_forward(sd, x, kw):
+    """ConvMixer.forward in train() (conv_mixer.py:41-45); NCHW, batch statistics."""
+    depth, k, ps = kw["depth"], kw.get("kernel_size", 9), kw.get("patch_size", 7)
+    t = F.conv2d(x, sd["embedding.0.weight"], sd["embedding.0.bias"], stride=ps, padding=ps // 2)
+    t = batch_norm_train(gelu(t), sd["embedding.2.weight"], sd["embedding.2.bias"])
+    for i in range(depth):
+        p = f"blocks.{i}."
+        dw = F.conv2d(t, sd[p + "0.fn.0.weight"], sd[p + "0.fn.0.bias"], padding=k // 2, groups=t.shape[1])
+        t = batch_norm_train(gelu(dw), sd[p + "0.fn.2.weight"], sd[p + "0.fn.2.bias"]) + t
+        pw = F.conv2d(t, sd[p + "1.weight"], sd[p + "1.bias"])
+        t = batch_norm_train(gelu(pw), sd[p + "3.weight"], sd[p + "3.bias"])
+    return linear(t.mean((2, 3)), sd["classifier.2.weight"], sd["classifier.2.bias"])

@@ -5,7 +5,8 @@ import torch
 
 from oracle import models, ref_loader, restate
 
-GOLDEN = ["mixer_tiny", "mixer_ragged", "resmlp_tiny", "gmlp_tiny", "s2v1_tiny", "s2v2_tiny", "asmlp_tiny"]
+GOLDEN = ["mixer_tiny", "mixer_ragged", "resmlp_tiny", "gmlp_tiny", "s2v1_tiny", "s2v2_tiny", "asmlp_tiny", "hire_tiny",
+          "convmixer_tiny"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)

@@ -6,7 +6,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import jittor_mlp_b200 as J  # noqa: E402
-from jittor_mlp_b200 import fn, fn_s2  # noqa: E402
+from jittor_mlp_b200 import fn, fn_s2, fn_spatial  # noqa: E402
 from oracle import models, restate  # noqa: E402
 
 DEV = "cuda"
@@ -25,7 +25,7 @@ def run_model(model, x):
     return out, xg.grad, {k: p.grad for k, p in model.named_parameters()}
 
 
-@pytest.mark.parametrize("name", ["s2v1_tiny", "s2v2_tiny", "asmlp_tiny"])
+@pytest.mark.parametrize("name", ["s2v1_tiny", "s2v2_tiny", "asmlp_tiny", "hire_tiny", "convmixer_tiny"])
 def test_against_reference_golden(golden, name):
     fx = golden(name)
     m = getattr(J, fx["cls"])(**fx["kwargs"])
@@ -34,12 +34,17 @@ def test_against_reference_golden(golden, name):
     assert restate.rel_l2(out.cpu(), fx["out"]) < TOL
     assert restate.rel_l2(dx.cpu(), fx["dx"]) < 3 * TOL
     scale = float(fx["dx"].abs().max() + 1)
+    ours, refs = [], []
     for k, g in fx["grads"].items():
         if g is None:
             assert grads[k] is None, k
             continue
         err = restate.rel_l2(grads[k].cpu(), g)
-        assert err < 4 * TOL or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * scale, (k, err)
+        # 1-D parameters of these tiny fixtures are sums over < 100 rows: a larger bf16 noise floor per tensor
+        lim = (8 if g.dim() == 1 else 4) * TOL
+        assert err < lim or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * scale, (k, err)
+        ours.append(grads[k].cpu().float().flatten()); refs.append(g.flatten())
+    assert restate.rel_l2(torch.cat(ours), torch.cat(refs)) < 2 * TOL      # all parameter gradients together
 
 
 @pytest.mark.parametrize("C,H,W", [(96, 14, 14), (24, 5, 7), (64, 8, 8)])
@@ -115,10 +120,79 @@ def test_s2v2_split_attention_ops():
     assert restate.rel_l2(hg.grad.cpu(), hr.grad) < TOL
 
 
+@pytest.mark.parametrize("K,C,H,W", [(3, 64, 9, 12), (5, 32, 8, 8), (7, 96, 16, 16), (9, 72, 10, 7)])
+def test_depthwise_conv_gelu_fwd_bwd(K, C, H, W):
+    import torch.nn.functional as F
+    B = 3
+    x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(0)).bfloat16().float()
+    w = (torch.randn(C, 1, K, K, generator=torch.Generator().manual_seed(1)) * 0.2).bfloat16().float()
+    b = (torch.randn(C, generator=torch.Generator().manual_seed(2)) * 0.2).bfloat16().float()
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = restate.gelu(F.conv2d(xr, wr, br, padding=K // 2, groups=C))
+    dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3)).bfloat16().float()
+    ref.backward(dy)
+    xg = bf(x.permute(0, 2, 3, 1).contiguous()).requires_grad_(True)
+    wg, bg = bf(w).requires_grad_(True), bf(b).requires_grad_(True)
+    out = fn_spatial.DwConvGeluFn.apply(xg, wg, bg)
+    out.backward(bf(dy.permute(0, 2, 3, 1).contiguous()))
+    assert restate.rel_l2(out.cpu().permute(0, 3, 1, 2), ref) < 6e-3
+    assert restate.rel_l2(xg.grad.cpu().permute(0, 3, 1, 2), xr.grad) < TOL
+    assert restate.rel_l2(wg.grad.cpu(), wr.grad) < TOL
+    assert restate.rel_l2(bg.grad.cpu(), br.grad) < TOL
+
+
+def test_batch_norm_train_fwd_bwd_and_running_stats():
+    B, H, W, C = 4, 8, 8, 64
+    a = (torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(0)) * 1.5 + 0.4).bfloat16().float()
+    res = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_((torch.rand(C) + 0.5).bfloat16().float()); bn.bias.copy_((torch.randn(C) * 0.1).bfloat16().float())
+    ar = a.clone().requires_grad_(True)
+    ref = bn(ar.permute(0, 3, 1, 2)).permute(0, 2, 3, 1) + res
+    dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2)).bfloat16().float()
+    ref.backward(dy)
+    ag = bf(a).requires_grad_(True)
+    g, bt = bf(bn.weight.detach()).requires_grad_(True), bf(bn.bias.detach()).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    out = fn_spatial.BatchNormFn.apply(ag, g, bt, rm, rv, 0.1, 1e-5, bf(res))
+    out.backward(bf(dy))
+    assert restate.rel_l2(out.cpu(), ref) < 6e-3
+    assert restate.rel_l2(ag.grad.cpu(), ar.grad) < TOL
+    assert restate.rel_l2(g.grad.cpu(), bn.weight.grad) < TOL
+    assert restate.rel_l2(bt.grad.cpu(), bn.bias.grad) < TOL
+    assert restate.rel_l2(rm.cpu(), bn.running_mean) < 1e-3      # momentum update with the batch mean
+    assert restate.rel_l2(rv.cpu(), bn.running_var) < 1e-3       # ... and the UNBIASED batch variance
+
+
+@pytest.mark.parametrize("H,W,h,w,step", [(10, 8, 4, 4, 2), (7, 7, 2, 2, 1), (14, 14, 3, 3, 0), (5, 4, 3, 3, 1)])
+def test_hire_region_ops_are_exact_data_movement(H, W, h, w, step):
+    """build: gathered rows equal the reference pad/roll/rearrange pipeline; combine: inverse; adjoints via autograd."""
+    import torch.nn.functional as F
+    from einops import rearrange
+    B, C = 2, 16
+    x = torch.randn(B, H, W, C, generator=torch.Generator().manual_seed(0)).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    xn = xr.permute(0, 3, 1, 2)
+    xp = F.pad(xn, (0, w - W % w, 0, h - H % h), "circular")
+    zh_ref = rearrange(torch.roll(xp, step, 2), "b c (h g) w -> b g w (h c)", h=h)[:, :, :W]     # [i][c] feature order
+    zw_ref = rearrange(torch.roll(xp, step, 3), "b c h (w g) -> b h g (w c)", w=w)[:, :H]
+    xg = bf(x).requires_grad_(True)
+    zh, zw = fn_spatial.HireBuildFn.apply(xg, h, w, step, step)
+    assert torch.equal(zh.float().cpu(), zh_ref.detach()) and torch.equal(zw.float().cpu(), zw_ref.detach())
+    d1 = torch.randn(zh_ref.shape, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    d2 = torch.randn(zw_ref.shape, generator=torch.Generator().manual_seed(2)).bfloat16().float()
+    ((zh_ref * d1).sum() + (zw_ref * d2).sum()).backward()
+    torch.autograd.backward([zh, zw], [bf(d1), bf(d2)])
+    assert restate.rel_l2(xg.grad.cpu(), xr.grad) < 5e-3
+
+
 @pytest.mark.parametrize("cls,kw,xshape", [
     ("S2MLPv2", dict(image_size=56, patch_size=[7, 2], d_model=[192, 384], depth=[1, 1], expansion_factor=[3, 3], num_classes=16), (4, 3, 56, 56)),
     ("AS_MLP", dict(img_size=64, patch_size=4, embed_dim=96, depths=[1, 1], shift_size=5, num_classes=16, drop_path_rate=0.), (4, 3, 64, 64)),
     ("S2MLPv1", dict(image_size=64, patch_size=[16], d_model=[384], depth=[2], expansion_factor=[4], num_classes=16), (4, 3, 64, 64)),
+    ("HireMLP", dict(d_model=[64, 128], h=[4, 3], w=[4, 3], cross_region_step=[2, 2], depth=[2, 2], num_classes=16), (4, 3, 64, 64)),
+    ("ConvMixer", dict(dim=256, depth=2, kernel_size=7, patch_size=7, n_classes=16), (8, 3, 56, 56)),
 ])
 def test_config4_channel_widths_against_oracle(cls, kw, xshape):
     """Real channel widths of BASELINE config 4 (C 96/192/384) at small spatial size, forward + input gradient."""
