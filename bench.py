@@ -29,6 +29,12 @@ PRESETS = {
     "mixer_s16": ("MLPMixerForImageClassification", dict(d_model=512, depth=8), "mixer_forward", 9.249, 0.1541),
     "resmlp_24": ("ResMLPForImageClassification", dict(d_model=384, depth=24), "resmlp_forward", 11.923, 0.1156),
     "gmlp_s": ("gMLPForImageClassification", dict(image_size=224, d_model=256, d_ffn=1536, depth=30), "gmlp_forward", 17.491, 0.0771),
+    # BASELINE config 4 (+ the two north_star models without a config): fwd GFLOP/img from SURVEY.md section 8(d)
+    "as_mlp_t": ("AS_MLP", dict(drop_path_rate=0.), None, 8.701, 0.0289),
+    "s2mlpv2": ("S2MLPv2", dict(), None, 13.817, 0.0578),
+    "hire_t": ("HireMLP", dict(depth=[2, 2, 4, 2]), None, 2.832, 0.0590),
+    "s2mlpv1_deep": ("S2MLPv1_deep", dict(), None, 20.93, 0.1156),
+    "convmixer_768_32": ("ConvMixer", dict(dim=768, depth=32, kernel_size=7, patch_size=7), None, 41.24, 0.2312),
 }
 METRIC = "images/sec fwd+bwd MLP-Mixer-B/16 224px"
 
@@ -169,7 +175,7 @@ def kernel_rooflines(B, N, C, Ds, Dc, pk):
 
 def cpu_port_images_per_s(name, batch, iters, warm=1):
     """The oracle restatement (reference algorithm, fp32, autograd) on the host cores: the reported CPU baseline."""
-    from oracle import restate
+    from oracle import models, restate
     import jittor_mlp_b200 as J
     cls, kw, fwd, _, _ = PRESETS[name]
     torch.set_num_threads(os.cpu_count() or 1)
@@ -178,11 +184,15 @@ def cpu_port_images_per_s(name, batch, iters, warm=1):
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in m.state_dict().items()}
     x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(1))
     restate.USE_ATEN = True     # same ATen primitives as the reference modules (conv1d / layer_norm / gelu)
-    fn = getattr(restate, fwd)
+    ocls, okw = ("S2MLPv1", dict(image_size=224, patch_size=[16], d_model=[384], depth=[36], expansion_factor=[4])) \
+        if cls == "S2MLPv1_deep" else (cls, kw)
+
+    def fn(sd_, x_, _depth):
+        return models.forward(ocls, okw, sd_, x_)
     ts = []
     for i in range(warm + iters):
         t0 = time.perf_counter()
-        out = fn(sd, x, kw["depth"])
+        out = fn(sd, x, None)
         out.square().mean().backward()
         for v in sd.values():
             v.grad = None
@@ -200,7 +210,7 @@ def run_reference(args):
     ips, secs = cpu_port_images_per_s(args.model, batch, K, warm=W)
     cores = os.cpu_count() or 1
     sample = f"{K} timed fwd+bwd steps of batch {batch} (after {W} warm-up), fp32, torch {torch.__version__}, {cores} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC if args.model == "mixer_b16" else f"images/sec fwd+bwd {args.model} 224px", "value": round(ips, 3), "unit": "images/s", "n_gpus": args.gpus,
             "steps": K, "warmup": W, "ms_per_step": round(secs / K * 1e3, 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.model} fwd+bwd 224x224 (reference algorithm restated in oracle/restate.py, host CPU)",
