@@ -89,6 +89,7 @@ typedef struct {
   float* out_f32; int64_t out_ld;      /* VMLP_EPI_ATOMIC destination [M, N] (caller zero-fills) */
   int32_t split_k;                     /* 0 = choose automatically */
   int32_t block_n;                     /* 0 = choose automatically (256 or 128) */
+  int32_t cta_group;                   /* 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile */
 } vmlp_gemm_args;
 
 int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream);

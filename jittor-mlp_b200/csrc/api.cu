@@ -7,6 +7,7 @@
 #include "spatial2.cuh"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <atomic>
@@ -93,36 +94,54 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t rows, int64
   return VMLP_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
                   const GemmParams& p, int grid, cudaStream_t st) {
-  auto kern = gemm_bf16_sm100<BN, EPI>;
+  auto kern = gemm_bf16_sm100<BN, EPI, CG>;
+  using SM = GemmSmem<BN, EPI, CG>;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, EPI>::TOTAL));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set[dev & 63] = true;
   }
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN, EPI>::TOTAL, st>>>(ta, tb, td, td2, p);
+  if (CG == 1) {
+    kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ta, tb, td, td2, p);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = SM::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;   // CTA pair: tcgen05 cta_group::2
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, td2, p));
+  }
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
                    const CUtensorMap& td2, const GemmParams& p, int grid, cudaStream_t st) {
   switch (epi) {
-    case EPI_STORE: return launch_gemm_t<BN, EPI_STORE>(ta, tb, td, td2, p, grid, st);
-    case EPI_GELU: return launch_gemm_t<BN, EPI_GELU>(ta, tb, td, td2, p, grid, st);
-    case EPI_RESID: return launch_gemm_t<BN, EPI_RESID>(ta, tb, td, td2, p, grid, st);
-    case EPI_DGELU: return launch_gemm_t<BN, EPI_DGELU>(ta, tb, td, td2, p, grid, st);
-    case EPI_ATOMIC: return launch_gemm_t<BN, EPI_ATOMIC>(ta, tb, td, td2, p, grid, st);
-    case EPI_MUL: return launch_gemm_t<BN, EPI_MUL>(ta, tb, td, td2, p, grid, st);
-    case EPI_GELU_ONLY: return launch_gemm_t<BN, EPI_GELU_ONLY>(ta, tb, td, td2, p, grid, st);
-    case EPI_RESID_DUAL: return launch_gemm_t<BN, EPI_RESID_DUAL>(ta, tb, td, td2, p, grid, st);
-    case EPI_MUL_DUAL: return launch_gemm_t<BN, EPI_MUL_DUAL>(ta, tb, td, td2, p, grid, st);
+    case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_DGELU: return launch_gemm_t<BN, EPI_DGELU, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_ATOMIC: return launch_gemm_t<BN, EPI_ATOMIC, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_MUL: return launch_gemm_t<BN, EPI_MUL, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_GELU_ONLY: return launch_gemm_t<BN, EPI_GELU_ONLY, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_RESID_DUAL: return launch_gemm_t<BN, EPI_RESID_DUAL, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_MUL_DUAL: return launch_gemm_t<BN, EPI_MUL_DUAL, CG>(ta, tb, td, td2, p, grid, st);
   }
   return fail(VMLP_EINVAL, "unknown epilogue %d", epi);
 }
@@ -138,6 +157,14 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   int bn = g.block_n;
   if (bn == 0) bn = (g.N <= 128) ? 128 : 256;
   if (bn != 128 && bn != 256) return fail(VMLP_EINVAL, "block_n must be 128 or 256");
+
+  // CTA-pair kernel (cta_group::2, 256 x 256 tiles) for the large un-batched GEMMs: channel-mixing fwd/dgrad/wgrad
+  const bool one_output = (g.batch == 1 || g.contract_batch);
+  int cg = g.cta_group;
+  if (cg == 0) cg = (bn == 256 && one_output && (g.M % 256 == 0 || g.M >= 4096) && g.M >= 512) ? 2 : 1;
+  if (const char* e = getenv("VMLP_FORCE_CTA_GROUP")) cg = atoi(e) == 2 ? ((bn == 256) ? 2 : 1) : 1;
+  if (cg != 1 && cg != 2) return fail(VMLP_EINVAL, "cta_group must be 0, 1 or 2");
+  if (cg == 2 && bn != 256) return fail(VMLP_EINVAL, "cta_group 2 needs block_n 256");
 
   // operand views
   const bool a_mn = g.A.major != 0, b_mn = g.B.major != 0;
@@ -159,14 +186,14 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
                 a_mn ? GEMM_BK : GEMM_BM);
   if (rc) return rc;
   rc = make_map(&tb, g.B.ptr, g.B.cols, g.B.rows, b_batched ? g.batch : 1, g.B.ld, g.B.batch_stride, 64,
-                b_mn ? GEMM_BK : bn);
+                b_mn ? GEMM_BK : bn / cg);
   if (rc) return rc;
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = g.M;
   p.N = g.N;
-  p.tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_m = (g.M + GEMM_BM * cg - 1) / (GEMM_BM * cg);
   p.tiles_n = (g.N + bn - 1) / bn;
   p.kbatch = g.contract_batch ? 1 : 0;
   p.batch = p.kbatch ? 1 : g.batch;
@@ -200,7 +227,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   int split = 1;
   if (epi == EPI_ATOMIC) {
     if (!g.out_f32) return fail(VMLP_EINVAL, "EPI_ATOMIC needs out_f32");
-    split = g.split_k > 0 ? g.split_k : (dv.sms / base_tiles);
+    split = g.split_k > 0 ? g.split_k : ((dv.sms / cg) / base_tiles);
     if (split < 1) split = 1;
     if (split > p.k_blocks) split = p.k_blocks;
     const int per = (p.k_blocks + split - 1) / split;
@@ -217,9 +244,11 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   }
   p.split_k = split;
   const long long total = (long long)base_tiles * split;
-  const int grid = (int)(total < dv.sms ? total : dv.sms);
-  if (bn == 256) return launch_gemm_bn<256>(epi, ta, tb, td, td2, p, grid, st);
-  return launch_gemm_bn<128>(epi, ta, tb, td, td2, p, grid, st);
+  const long long clusters = dv.sms / cg;
+  const int grid = (int)(total < clusters ? total : clusters) * cg;
+  if (cg == 2) return launch_gemm_bn<256, 2>(epi, ta, tb, td, td2, p, grid, st);
+  if (bn == 256) return launch_gemm_bn<256, 1>(epi, ta, tb, td, td2, p, grid, st);
+  return launch_gemm_bn<128, 1>(epi, ta, tb, td, td2, p, grid, st);
 }
 
 int rw_grid(long long rows) {

@@ -63,10 +63,13 @@ struct GemmParams {
   long long out_ld;
 };
 
-template <int BN, int EPI>
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile;
+// each CTA stages its own 128 rows of A and HALF of the B tile, so the per-SM L2->SMEM traffic per MMA drops by a
+// third and two more pipeline stages fit.
+template <int BN, int EPI, int CG = 1>
 struct GemmSmem {
-  static constexpr int STAGES = (EPI == EPI_ATOMIC) ? 4 : 3;
-  static constexpr int STAGE_B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGES = (CG == 2) ? ((EPI == EPI_ATOMIC) ? 6 : 5) : ((EPI == EPI_ATOMIC) ? 4 : 3);
+  static constexpr int STAGE_B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_OFF = PIPE_BYTES;
@@ -78,23 +81,27 @@ struct GemmSmem {
 struct TileCoord {
   int m0, n0, b_idx, s_idx;
 };
-template <int BN>
-__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+// m0 is THIS CTA's first row (for CG = 2 the pair's tile is 256 rows and cta_rank selects the half)
+template <int BN, int CG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int cta_rank) {
   TileCoord c;
   int t = tile;
   c.n0 = (t % p.tiles_n) * BN; t /= p.tiles_n;
-  c.m0 = (t % p.tiles_m) * GEMM_BM; t /= p.tiles_m;
+  c.m0 = (t % p.tiles_m) * (GEMM_BM * CG) + cta_rank * GEMM_BM; t /= p.tiles_m;
   c.b_idx = t % p.batch;
   c.s_idx = t / p.batch;
   return c;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
                 const GemmParams p) {
-  using L = GemmSmem<BN, EPI>;
+  using L = GemmSmem<BN, EPI, CG>;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool is_leader = (cta_rank == 0);
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
   constexpr int STAGES = L::STAGES;
   constexpr int NCHUNK = BN / 64;
   constexpr bool HAS_AUX = (epi_is_resid(EPI) || EPI == EPI_DGELU || epi_is_mul(EPI));
@@ -122,16 +129,17 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], GEMM_EPI_WARPS);
+      mbar_init(&tmem_empty[a], GEMM_EPI_WARPS * CG);   // the leader's barrier collects both CTAs' epilogue warps
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);   // 2 accumulator stages x BN fp32 columns (power of two: 256 / 512)
-    tmem_relinquish();
+    // 2 accumulator stages x BN fp32 columns (power of two: 256 / 512); for CG = 2 one warp of EACH CTA takes part
+    if (CG == 2) { tmem_alloc_2cta(tmem_slot, 2 * BN); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -143,32 +151,38 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile<BN>(p, tile);
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const TileCoord tc = decode_tile<BN, CG>(p, tile, cta_rank);
         const int kb0 = tc.s_idx * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
+        const int nb0 = tc.n0 + cta_rank * (BN / CG);      // this CTA's slice of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          // CG = 2: both CTAs' TMA loads complete_tx on the LEADER's full barrier, which expects both stages' bytes
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES * CG);
           const int kc = (kb % p.kpb) * GEMM_BK;
           const int kbatch = p.kbatch ? (kb / p.kpb) : tc.b_idx;
           const int ba = p.a_batched ? kbatch : 0;
           const int bb = p.b_batched ? kbatch : 0;
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
+          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2) {
+            if (CG == 2) tma_load_3d_2cta(dst, m, &full_bar[stage], c0, c1, c2);
+            else tma_load_3d(dst, m, &full_bar[stage], c0, c1, c2);
+          };
           if (!p.a_mn) {
-            tma_load_3d(sa, &tmA, &full_bar[stage], kc, tc.m0, ba);   // box (64 k, 128 m)
+            load(sa, &tmA, kc, tc.m0, ba);                            // box (64 k, 128 m)
           } else {
 #pragma unroll
             for (int a = 0; a < GEMM_BM / 64; ++a)                    // box (64 m, 64 k) per MN atom
-              tma_load_3d(sa + a * (GEMM_BK * 128), &tmA, &full_bar[stage], tc.m0 + a * 64, kc, ba);
+              load(sa + a * (GEMM_BK * 128), &tmA, tc.m0 + a * 64, kc, ba);
           }
           if (!p.b_mn) {
-            tma_load_3d(sb, &tmB, &full_bar[stage], kc, tc.n0, bb);   // box (64 k, BN n)
+            load(sb, &tmB, kc, nb0, bb);                              // box (64 k, BN / CG n)
           } else {
 #pragma unroll
-            for (int a = 0; a < BN / 64; ++a)
-              tma_load_3d(sb + a * (GEMM_BK * 128), &tmB, &full_bar[stage], tc.n0 + a * 64, kc, bb);
+            for (int a = 0; a < BN / CG / 64; ++a)
+              load(sb + a * (GEMM_BK * 128), &tmB, nb0 + a * 64, kc, bb);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -176,15 +190,15 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, p.a_mn, p.b_mn);
+    if (lane == 0 && is_leader) {
+      const uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN, p.a_mn, p.b_mn);
       // K-major : 8-row groups 1024 B apart (SBO); one 128B swizzle atom along K (LBO unused).
       // MN-major: 8-k groups 1024 B apart (SBO); 64-wide MN atoms BK*128 B apart (LBO).
       const uint32_t a_lbo = p.a_mn ? GEMM_BK * 128 : 0, b_lbo = p.b_mn ? GEMM_BK * 128 : 0;
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
       uint32_t stage = 0, phase = 0;
       int tc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tc) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tc) {
         const int s_idx = tile / tiles_per_split;
         const int kb0 = s_idx * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
@@ -201,10 +215,17 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = umma_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CG == 2) umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                   // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tmem_full[as]);   // accumulator complete -> epilogue
+          // frees the smem slot (in both CTAs for CG = 2) when these MMAs retire; last k-block: accumulator complete
+          if (CG == 2) {
+            umma_commit_2cta_mc(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_2cta_mc(&tmem_full[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -225,7 +246,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int g = 0; g < 4; ++g) dst[g] = make_uint4(0, 0, 0, 0);
       if (!HAS_AUX || tile >= total_tiles) return;
-      const TileCoord t = decode_tile<BN>(p, tile);
+      const TileCoord t = decode_tile<BN, CG>(p, tile, cta_rank);
       const int grow = t.m0 + row;
       const int col = t.n0 + c * 64 + h * 32;
       if (grow >= p.M) return;
@@ -234,11 +255,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int g = 0; g < 4; ++g)
         if (col + g * 8 < p.N) dst[g] = ldg_v4(src + g * 8);
     };
-    if (HAS_AUX) load_aux(blockIdx.x, par, 0, aux_nxt);
+    if (HAS_AUX) load_aux(cluster_id, par, 0, aux_nxt);
 
     int tcnt = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcnt) {
-      const TileCoord tc = decode_tile<BN>(p, tile);
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcnt) {
+      const TileCoord tc = decode_tile<BN, CG>(p, tile, cta_rank);
       const int grow = tc.m0 + row;
       const bool row_ok = grow < p.M;
       const int as = tcnt & 1;
@@ -272,7 +293,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // prefetch the aux operand of this warp's NEXT work item (next half / chunk / tile)
             if (h == 0) load_aux(tile, c, 1, aux_nxt);
             else if (!last_chunk) load_aux(tile, c + 2, 0, aux_nxt);
-            else load_aux(tile + gridDim.x, par, 0, aux_nxt);
+            else load_aux(tile + num_clusters, par, 0, aux_nxt);
           }
           uint32_t v[32];
           if (chunk_live) {
@@ -283,7 +304,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) {
+              if (is_leader) mbar_arrive(&tmem_empty[as]);
+              else mbar_arrive_remote(&tmem_empty[as], 0);     // the MMA issuer lives in the leader CTA
+            }
           }
           if (!chunk_live) continue;
           const int colh = col0 + h * 32;
@@ -391,10 +415,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // neither CTA may exit while its peer still uses it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 

@@ -39,7 +39,7 @@ def operand(t, major, batched=None):
 
 
 def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=None, D2=None, bias=None,
-         bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0):
+         bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0, cta_group=0):
     """Generic fused GEMM, see vmlp_gemm_bf16 in include/vmlp_b200.h.  A/B are L.Operand."""
     g = L.GemmArgs()
     g.M, g.N, g.K, g.batch, g.contract_batch = M, N, K, batch, int(contract_batch)
@@ -62,7 +62,7 @@ def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=N
     if out_f32 is not None:
         _chk(out_f32, "out_f32", torch.float32)
         g.out_f32, g.out_ld = out_f32.data_ptr(), out_f32.stride(0)
-    g.split_k, g.block_n = split_k, block_n
+    g.split_k, g.block_n, g.cta_group = split_k, block_n, cta_group
     L.check(L.lib().vmlp_gemm_bf16(ctypes.byref(g), L.stream_ptr()))
 
 

@@ -151,3 +151,38 @@ def test_bad_arguments_raise():
     with pytest.raises(TypeError):
         ops.gemm(128, 128, 64, ops.operand(rnd(128, 64), 0), ops.operand(rnd(128, 64), 0), L.EPI_STORE,
                  D=torch.zeros(128, 128, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------ cta_group::2 (CTA pair)
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (1024, 768, 768), (600, 520, 200), (256 * 9, 256 * 5, 512)])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_cta_pair_plain_store(M, N, K, a_major, b_major):
+    A, Af = make_operand(M, K, a_major, 0, 1)
+    B, Bf = make_operand(N, K, b_major, 0, 2)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(M, N, K, ops.operand(A, a_major), ops.operand(B, b_major), L.EPI_STORE, D=D, cta_group=2)
+    torch.cuda.synchronize()
+    assert rel(D, Af @ Bf.t()) < 5e-3
+
+
+def test_cta_pair_epilogues_and_split_k():
+    M, N, K = 1024 + 64, 512, 320
+    A, Af = make_operand(M, K, 0, 0, 1)
+    B, Bf = make_operand(N, K, 0, 0, 2)
+    A, Af = A * 0.1, Af * 0.1
+    bias, aux = rnd(N, seed=3), rnd(M, N, seed=5)
+    acc = A.float() @ Bf.t()
+    Z, H = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV), torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_GELU, D=Z, D2=H, bias=bias, bias_mode=1, cta_group=2)
+    assert rel(Z, acc + bias.float()) < 5e-3 and rel(H, gelu(Z.float())) < 5e-3
+    D = torch.zeros_like(Z)
+    ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_DGELU, D=D, aux=aux, cta_group=2)
+    assert rel(D, acc * dgelu(aux.float())) < 5e-3
+    ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_RESID, D=D, aux=aux, bias=bias, bias_mode=1, cta_group=2)
+    assert rel(D, acc + bias.float() + aux.float()) < 5e-3
+    R, Dout, Din = 3000, 512, 264
+    dY, X = rnd(R, Dout, seed=1), rnd(R, Din, seed=2)
+    for sk in (0, 1, 5):
+        out = torch.zeros(Dout, Din, dtype=torch.float32, device=DEV)
+        ops.gemm(Dout, Din, R, ops.operand(dY, 1), ops.operand(X, 1), L.EPI_ATOMIC, out_f32=out, split_k=sk, cta_group=2)
+        assert rel(out, dY.float().t() @ X.float()) < 2e-3
