@@ -149,7 +149,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // The whole warp walks the pipeline (warp-uniform control flow); one elected lane issues the TMA instructions.
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const TileCoord tc = decode_tile<BN, CG>(p, tile, cta_rank);
@@ -158,6 +159,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int nb0 = tc.n0 + cta_rank * (BN / CG);      // this CTA's slice of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one_sync()) {
           // CG = 2: both CTAs' TMA loads complete_tx on the LEADER's full barrier, which expects both stages' bytes
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES * CG);
           const int kc = (kb % p.kpb) * GEMM_BK;
@@ -184,13 +186,16 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int a = 0; a < BN / CG / 64; ++a)
               load(sb + a * (GEMM_BK * 128), &tmB, nb0 + a * 64, kc, bb);
           }
+          }   // elected lane
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && is_leader) {
+    // Whole warp, warp-uniform control flow; one elected lane issues the MMAs and commits.
+    if (is_leader) {
       const uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN, p.a_mn, p.b_mn);
       // K-major : 8-row groups 1024 B apart (SBO); one 128B swizzle atom along K (LBO unused).
       // MN-major: 8-k groups 1024 B apart (SBO); 64-wide MN atoms BK*128 B apart (LBO).
@@ -212,7 +217,10 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t b_base = a_base + GEMM_STAGE_A_BYTES;
           const int ksteps = ((kb % p.kpb) == p.kpb - 1) ? p.last_ksteps : (GEMM_BK / 16);
-          for (int k = 0; k < ksteps; ++k) {
+          if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            if (k >= ksteps) break;
             const uint64_t adesc = umma_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
             if (CG == 2) umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
@@ -226,6 +234,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             umma_commit(&empty_bar[stage]);
             if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
           }
+          }   // elected lane
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -237,6 +247,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int par = ew >> 2;                // this warp handles 64-col chunks with (chunk & 1) == par
     const int row = q * 32 + lane;          // accumulator row owned by this thread
     uint8_t* my_staging = staging + ew * 2 * GEMM_WARP_STAGING;
+    const bool store_lane = elect_one_sync() != 0;   // this lane owns the warp's TMA-store bulk groups for the whole kernel
     constexpr int MY_CHUNKS = (NCHUNK + 1) / 2;   // chunks per tile for this warp (BN=128: 1, BN=256: 2)
     uint32_t nstore = 0;
 
@@ -278,7 +289,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint8_t* st1 = my_staging + GEMM_WARP_STAGING;
         if (chunk_live && EPI != EPI_ATOMIC) {
           // the staging buffer about to be overwritten must have been drained by its TMA store
-          if (lane == 0) {
+          if (store_lane) {
             if (DUAL) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
           __syncwarp();
@@ -403,7 +414,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (chunk_live && EPI != EPI_ATOMIC) {
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (store_lane) {
             tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
             if (DUAL) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
             tma_store_commit();
@@ -411,7 +422,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-    if (EPI != EPI_ATOMIC && lane == 0) tma_store_wait_all<0>();
+    if (EPI != EPI_ATOMIC && store_lane) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
