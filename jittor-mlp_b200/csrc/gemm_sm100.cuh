@@ -23,7 +23,7 @@ namespace vmlp {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGE_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
 constexpr int GEMM_WARP_STAGING = 32 * 64 * 2;              // 32 rows x 64 bf16 cols = 4 KB
@@ -61,6 +61,8 @@ struct GemmParams {
   long long aux_ld, aux_bs;       // row stride, batch stride (elements)
   float* out_f32;                 // EPI_ATOMIC destination
   long long out_ld;
+  __nv_bfloat16* d2;              // second output of the *_DUAL / GELU epilogues (direct stores)
+  long long d2_ld, d2_bs;
 };
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile;
@@ -73,7 +75,7 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_OFF = PIPE_BYTES;
-  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * 2 * GEMM_WARP_STAGING;
+  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * GEMM_WARP_STAGING;
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
 };
@@ -122,7 +124,6 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
-    if (DUAL) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -241,32 +242,35 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..9)
-    const int ew = warp - 2;                // 0..7
+    // ===================================================================== epilogue (warps 2..17)
+    // 16 warps = 4 per scheduler: the epilogue math (GELU / GELU') is latency-bound with fewer.  Warp (q, c) owns the
+    // 32 accumulator rows of TMEM lane quarter q = warp % 4 and the 64-column chunk c = (warp - 2) / 4 of every tile, walks
+    // it in four 16-column steps (tcgen05.ld.x16 keeps the live registers < 113), stages the bf16 result in its private
+    // 4 KB 128B-swizzled buffer and issues its own TMA store.  A second output (pre-activation / gate value) goes out as
+    // direct 32-byte-sector stores.
+    const int ew = warp - 2;                // 0..15
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int par = ew >> 2;                // this warp handles 64-col chunks with (chunk & 1) == par
+    const int c = ew >> 2;                  // 64-column chunk owned by this warp
+    const bool has_chunk = c < NCHUNK;
     const int row = q * 32 + lane;          // accumulator row owned by this thread
-    uint8_t* my_staging = staging + ew * 2 * GEMM_WARP_STAGING;
+    uint8_t* st0 = staging + ew * GEMM_WARP_STAGING;
     const bool store_lane = elect_one_sync() != 0;   // this lane owns the warp's TMA-store bulk groups for the whole kernel
-    constexpr int MY_CHUNKS = (NCHUNK + 1) / 2;   // chunks per tile for this warp (BN=128: 1, BN=256: 2)
-    uint32_t nstore = 0;
 
-    // ---- auxiliary-operand prefetch (registers): 32 columns of this thread's row = 4 x 16 B
-    uint4 aux_nxt[4];
-    auto load_aux = [&](int tile, int c, int h, uint4 (&dst)[4]) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) dst[g] = make_uint4(0, 0, 0, 0);
-      if (!HAS_AUX || tile >= total_tiles) return;
+    // ---- auxiliary-operand prefetch (registers): 16 columns of this thread's row = 2 x 16 B, one step ahead
+    uint4 aux_nxt[2];
+    auto load_aux = [&](int tile, int step, uint4 (&dst)[2]) {
+      dst[0] = make_uint4(0, 0, 0, 0);
+      dst[1] = make_uint4(0, 0, 0, 0);
+      if (!HAS_AUX || !has_chunk || tile >= total_tiles) return;
       const TileCoord t = decode_tile<BN, CG>(p, tile, cta_rank);
       const int grow = t.m0 + row;
-      const int col = t.n0 + c * 64 + h * 32;
+      const int col = t.n0 + c * 64 + step * 16;
       if (grow >= p.M) return;
       const __nv_bfloat16* src = p.aux + (long long)t.b_idx * p.aux_bs + (long long)grow * p.aux_ld + col;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        if (col + g * 8 < p.N) dst[g] = ldg_v4(src + g * 8);
+      if (col < p.N) dst[0] = ldg_v4(src);
+      if (col + 8 < p.N) dst[1] = ldg_v4(src + 8);
     };
-    if (HAS_AUX) load_aux(cluster_id, par, 0, aux_nxt);
+    if (HAS_AUX) load_aux(cluster_id, 0, aux_nxt);
 
     int tcnt = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcnt) {
@@ -278,147 +282,133 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       float rbias = 0.f;
       if (p.bias_mode == 2 && row_ok) rbias = __bfloat162float(p.bias[grow]);
-
-#pragma unroll 1
-      for (int ci = 0; ci < MY_CHUNKS; ++ci) {
-        const int c = ci * 2 + par;
-        const bool last_chunk = (ci == MY_CHUNKS - 1);
-        const int col0 = tc.n0 + c * 64;
-        const bool chunk_live = (c < NCHUNK) && (col0 < p.N);   // ragged N: dead chunks are skipped entirely
-        uint8_t* st0 = my_staging + (DUAL ? 0 : (nstore & 1) * GEMM_WARP_STAGING);
-        uint8_t* st1 = my_staging + GEMM_WARP_STAGING;
-        if (chunk_live && EPI != EPI_ATOMIC) {
-          // the staging buffer about to be overwritten must have been drained by its TMA store
-          if (store_lane) {
-            if (DUAL) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
-          }
-          __syncwarp();
-          ++nstore;
+      const int col0 = tc.n0 + c * 64;
+      const bool chunk_live = has_chunk && (col0 < p.N);   // ragged N: dead chunks are skipped entirely
+      if (chunk_live && EPI != EPI_ATOMIC) {
+        // the staging buffer must have been drained by the TMA store of the previous tile (a whole tile ago)
+        if (store_lane) tma_store_wait_read<0>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int st = 0; st < 4; ++st) {
+        uint4 aux_cur[2];
+        if (HAS_AUX) {
+          aux_cur[0] = aux_nxt[0];
+          aux_cur[1] = aux_nxt[1];
+          if (st < 3) load_aux(tile, st + 1, aux_nxt);
+          else load_aux(tile + num_clusters, 0, aux_nxt);
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint4 aux_cur[4];
-          if (HAS_AUX) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) aux_cur[g] = aux_nxt[g];
-            // prefetch the aux operand of this warp's NEXT work item (next half / chunk / tile)
-            if (h == 0) load_aux(tile, c, 1, aux_nxt);
-            else if (!last_chunk) load_aux(tile, c + 2, 0, aux_nxt);
-            else load_aux(tile + num_clusters, par, 0, aux_nxt);
+        uint32_t v[16];
+        if (chunk_live) {
+          tmem_ld_32x32b_x16(tmem_base + as * BN + c * 64 + st * 16 + (uint32_t(q * 32) << 16), v);
+          tmem_ld_wait();
+        }
+        if (st == 3) {
+          // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (is_leader) mbar_arrive(&tmem_empty[as]);
+            else mbar_arrive_remote(&tmem_empty[as], 0);     // the MMA issuer lives in the leader CTA
           }
-          uint32_t v[32];
-          if (chunk_live) {
-            tmem_ld_32x32b_x32(tmem_base + as * BN + c * 64 + h * 32 + (uint32_t(q * 32) << 16), v);
-            tmem_ld_wait();
+        }
+        if (!chunk_live) continue;
+        const int cols = col0 + st * 16;
+        if (EPI == EPI_ATOMIC) {
+          if (row_ok) {
+            float* orow = p.out_f32 + (long long)grow * p.out_ld;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cols + j < p.N) red_add_f32(orow + cols + j, __uint_as_float(v[j]));
           }
-          if (last_chunk && h == 1) {
-            // last TMEM read of this accumulator stage by this warp: hand it back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (is_leader) mbar_arrive(&tmem_empty[as]);
-              else mbar_arrive_remote(&tmem_empty[as], 0);     // the MMA issuer lives in the leader CTA
-            }
-          }
-          if (!chunk_live) continue;
-          const int colh = col0 + h * 32;
-          if (EPI == EPI_ATOMIC) {
-            if (row_ok) {
-              float* orow = p.out_f32 + (long long)grow * p.out_ld;
+          continue;
+        }
+        float f[16];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (colh + j < p.N) red_add_f32(orow + colh + j, __uint_as_float(v[j]));
-            }
-            continue;
-          }
-          float f[32];
-          uint32_t o2[16];
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + rbias;
+        if (p.bias_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + rbias;
-          if (p.bias_mode == 1) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (colh + g * 8 < p.N) {
-                const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + colh + g * 8);
-                const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[g * 8 + 2 * e] += bf16lo(w[e]);
-                  f[g * 8 + 2 * e + 1] += bf16hi(w[e]);
-                }
-              }
-            }
-          }
-          if (epi_is_resid(EPI) && DUAL) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);   // un-scaled branch output
-          }
-          if (epi_is_resid(EPI) && p.colscale != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (colh + g * 8 < p.N) {
-                const uint4 sv = *reinterpret_cast<const uint4*>(p.colscale + colh + g * 8);
-                const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  f[g * 8 + 2 * e] *= bf16lo(w[e]);
-                  f[g * 8 + 2 * e + 1] *= bf16hi(w[e]);
-                }
-              }
-            }
-          }
-          uint32_t o[16];
-          if (epi_is_mul(EPI) && DUAL) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);   // gate value before the product
-          }
-          if (HAS_AUX) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t w[4] = {aux_cur[g].x, aux_cur[g].y, aux_cur[g].z, aux_cur[g].w};
+          for (int g = 0; g < 2; ++g) {
+            if (cols + g * 8 < p.N) {
+              const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + cols + g * 8);
+              const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
-                const float a0 = bf16lo(w[e]), a1 = bf16hi(w[e]);
-                if (epi_is_resid(EPI)) { x0 += a0; x1 += a1; }
-                if (epi_is_mul(EPI)) { x0 *= a0; x1 *= a1; }
-                if (EPI == EPI_DGELU) { x0 *= dgelu_erf(a0); x1 *= dgelu_erf(a1); }
-                o[g * 4 + e] = pack_bf16x2(x0, x1);
+                f[g * 8 + 2 * e] += bf16lo(w[e]);
+                f[g * 8 + 2 * e + 1] += bf16hi(w[e]);
               }
             }
-          } else if (EPI == EPI_GELU) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-              // gelu is applied to the bf16-rounded pre-activation that backward will re-read
-              o2[e] = pack_bf16x2(gelu_erf(bf16lo(o[e])), gelu_erf(bf16hi(o[e])));
-            }
-          } else if (EPI == EPI_GELU_ONLY) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(gelu_erf(f[2 * e]), gelu_erf(f[2 * e + 1]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-          }
-          // staging tile = [32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7) (matches SWIZZLE_128B)
-          const uint32_t srow = smem_u32(st0) + lane * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = (h * 4 + g) ^ (lane & 7);
-            st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
-            if (DUAL)
-              st_shared_v4(smem_u32(st1) + lane * 128 + chunk * 16,
-                           make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
           }
         }
-        if (chunk_live && EPI != EPI_ATOMIC) {
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (store_lane) {
-            tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
-            if (DUAL) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
-            tma_store_commit();
+        uint32_t o[8], o2[8];
+        if ((epi_is_resid(EPI) || epi_is_mul(EPI)) && DUAL) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o2[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);   // branch output before scale / gate
+        }
+        if (epi_is_resid(EPI) && p.colscale != nullptr) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (cols + g * 8 < p.N) {
+              const uint4 sv = *reinterpret_cast<const uint4*>(p.colscale + cols + g * 8);
+              const uint32_t w[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f[g * 8 + 2 * e] *= bf16lo(w[e]);
+                f[g * 8 + 2 * e + 1] *= bf16hi(w[e]);
+              }
+            }
           }
+        }
+        if (HAS_AUX) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t w[4] = {aux_cur[g].x, aux_cur[g].y, aux_cur[g].z, aux_cur[g].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x0 = f[g * 8 + 2 * e], x1 = f[g * 8 + 2 * e + 1];
+              const float a0 = bf16lo(w[e]), a1 = bf16hi(w[e]);
+              if (epi_is_resid(EPI)) { x0 += a0; x1 += a1; }
+              if (epi_is_mul(EPI)) { x0 *= a0; x1 *= a1; }
+              if (EPI == EPI_DGELU) { x0 *= dgelu_erf(a0); x1 *= dgelu_erf(a1); }
+              o[g * 4 + e] = pack_bf16x2(x0, x1);
+            }
+          }
+        } else if (EPI == EPI_GELU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+            // gelu is applied to the bf16-rounded pre-activation that backward will re-read
+            o2[e] = pack_bf16x2(gelu_erf(bf16lo(o[e])), gelu_erf(bf16hi(o[e])));
+          }
+        } else if (EPI == EPI_GELU_ONLY) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(gelu_erf(f[2 * e]), gelu_erf(f[2 * e + 1]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+        }
+        // staging tile = [32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7) (matches SWIZZLE_128B)
+        const uint32_t srow = smem_u32(st0) + lane * 128;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int chunk = (st * 2 + g) ^ (lane & 7);
+          st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
+        }
+        if (DUAL && row_ok) {
+          // second output: this thread's 32 contiguous bytes (one full sector) straight to global memory
+          __nv_bfloat16* drow = p.d2 + (long long)tc.b_idx * p.d2_bs + (long long)grow * p.d2_ld + cols;
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            if (cols + g * 8 < p.N)
+              *reinterpret_cast<uint4*>(drow + g * 8) = make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]);
+        }
+      }
+      if (chunk_live && EPI != EPI_ATOMIC) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (store_lane) {
+          tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
+          tma_store_commit();
         }
       }
     }
