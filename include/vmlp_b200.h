@@ -65,9 +65,9 @@ typedef struct {
 
 enum {
   VMLP_EPI_STORE = 0,     /* D = acc (+bias)                                  */
-  VMLP_EPI_GELU = 1,      /* D = acc + bias ; D2 = gelu_erf(D)                */
+  VMLP_EPI_GELU = 1,      /* z = acc + bias ; D = gelu_erf'(z) ; D2 = gelu_erf(z) */
   VMLP_EPI_RESID = 2,     /* D = (acc + bias) * colscale + aux                */
-  VMLP_EPI_DGELU = 3,     /* D = acc * gelu_erf'(aux)                         */
+  VMLP_EPI_DGELU = 3,     /* D = acc * aux  (aux = the gelu_erf'(z) saved by EPI_GELU) */
   VMLP_EPI_ATOMIC = 4,    /* out_f32 += acc   (split-K, weight gradients)     */
   VMLP_EPI_MUL = 5,       /* D = (acc + bias) * aux                           */
   VMLP_EPI_GELU_ONLY = 6, /* D = gelu_erf(acc + bias)                         */
@@ -121,8 +121,8 @@ int vmlp_pad_rows(const void* src, void* dst, int32_t rows, int32_t cols, int32_
 int vmlp_add_bf16(const void* a, const void* b, void* dst, int64_t n, vmlp_stream_t stream);
 /* Strided elementwise helpers over [rows, C] views (row strides in elements, C % 8 == 0):
  *   vmlp_mul_colvec : out = a * v[c]                   (ResMLP layer-scale backward, res_mlp.py:54,56)
- *   vmlp_dgelu_mul  : out = a * gelu_erf'(z)
- *   vmlp_gate_bwd   : out = dg * vt * gelu_erf'(zp_u) ; out2 = dg * u     (gMLP SGU gate, g_mlp.py:21) */
+ *   vmlp_dgelu_mul  : out = a * g            (g = saved gelu_erf'(z))
+ *   vmlp_gate_bwd   : out = dg * vt * g_u ; out2 = dg * u                 (gMLP SGU gate, g_mlp.py:21) */
 int vmlp_mul_colvec(const void* a, int64_t a_ld, const void* v, void* out, int64_t out_ld, int64_t rows, int32_t C,
                     vmlp_stream_t stream);
 int vmlp_dgelu_mul(const void* a, int64_t a_ld, const void* z, int64_t z_ld, void* out, int64_t out_ld, int64_t rows,
@@ -193,7 +193,8 @@ int vmlp_hire_combine(const void* base, const void* oh, const void* ow, void* ou
 int vmlp_hire_restore_adj(const void* dout, void* dzh, void* dzw, const vmlp_hire_dims* d, vmlp_stream_t stream);
 
 /* ConvMixer depthwise k x k convolution, padding "same", channels-last (conv_mixer.py:24); K in {3, 5, 7, 9}.
- * weight: bf16 [C, 1, K, K].  fwd writes z = conv + bias and a = gelu_erf(z); dgrad is the 180-degree-rotated stencil;
+ * weight: bf16 [C, 1, K, K].  fwd writes z = gelu_erf'(conv + bias) (for backward) and a = gelu_erf(conv + bias);
+ * dgrad is the 180-degree-rotated stencil;
  * wgrad accumulates fp32 dW [C, K, K] (caller zero-fills). */
 int vmlp_dwconv_fwd(const void* x, const void* weight, const void* bias, void* z, void* a, int32_t B, int32_t H,
                     int32_t W, int32_t C, int32_t K, vmlp_stream_t stream);

@@ -238,10 +238,8 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
     if (rc) return rc;
     if (epi_is_dual(epi)) {
       if (!g.D2) return fail(VMLP_EINVAL, "dual-output epilogue needs D2");
-      if (!aligned16(g.D2) || (g.d2_ld % 8) || (g.d2_bs % 8)) return fail(VMLP_EALIGN, "D2 alignment");
-      p.d2 = static_cast<__nv_bfloat16*>(g.D2);
-      p.d2_ld = g.d2_ld;
-      p.d2_bs = g.d2_bs;
+      rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 64, 32);
+      if (rc) return rc;
     }
   }
   p.split_k = split;

@@ -30,9 +30,9 @@ constexpr int GEMM_WARP_STAGING = 32 * 64 * 2;              // 32 rows x 64 bf16
 
 enum GemmEpilogue : int {
   EPI_STORE = 0,    // D = acc (+bias)                                       -> bf16 via TMA store
-  EPI_GELU = 1,     // D = acc + bias (pre-activation), D2 = gelu(D)         -> two bf16 TMA stores
+  EPI_GELU = 1,     // z = acc + bias; D = gelu'(z) (kept for backward), D2 = gelu(z) -> two bf16 TMA stores
   EPI_RESID = 2,    // D = (acc + bias) * colscale + aux                     -> bf16 (aux = residual)
-  EPI_DGELU = 3,    // D = acc * gelu'(aux)                                  -> bf16 (aux = saved pre-activation)
+  EPI_DGELU = 3,    // D = acc * aux                                         -> bf16 (aux = gelu'(z) saved by EPI_GELU)
   EPI_ATOMIC = 4,   // out_f32[m, n] += acc                                  (split-K weight gradients)
   EPI_MUL = 5,      // D = (acc + bias) * aux                                -> bf16 (gMLP spatial gate)
   EPI_GELU_ONLY = 6,  // D = gelu(acc + bias)                                -> bf16 (no pre-activation saved)
@@ -70,12 +70,14 @@ struct GemmParams {
 // third and two more pipeline stages fit.
 template <int BN, int EPI, int CG = 1>
 struct GemmSmem {
-  static constexpr int STAGES = (CG == 2) ? ((EPI == EPI_ATOMIC) ? 6 : 5) : ((EPI == EPI_ATOMIC) ? 4 : 3);
+  static constexpr bool DUAL = (EPI == EPI_GELU || EPI == EPI_RESID_DUAL || EPI == EPI_MUL_DUAL);
+  // dual-output epilogues need a second staging buffer per warp; they are epilogue-bound, so fewer stages are enough
+  static constexpr int STAGES = (CG == 2) ? (DUAL ? 3 : (EPI == EPI_ATOMIC) ? 6 : 5) : (DUAL ? 2 : (EPI == EPI_ATOMIC) ? 4 : 3);
   static constexpr int STAGE_B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_OFF = PIPE_BYTES;
-  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * GEMM_WARP_STAGING;
+  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * GEMM_WARP_STAGING * (DUAL ? 2 : 1);
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
 };
@@ -124,6 +126,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
+    if (DUAL) tma_prefetch_desc(&tmD2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -245,15 +248,15 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================================================================== epilogue (warps 2..17)
     // 16 warps = 4 per scheduler: the epilogue math (GELU / GELU') is latency-bound with fewer.  Warp (q, c) owns the
     // 32 accumulator rows of TMEM lane quarter q = warp % 4 and the 64-column chunk c = (warp - 2) / 4 of every tile, walks
-    // it in four 16-column steps (tcgen05.ld.x16 keeps the live registers < 113), stages the bf16 result in its private
-    // 4 KB 128B-swizzled buffer and issues its own TMA store.  A second output (pre-activation / gate value) goes out as
-    // direct 32-byte-sector stores.
+    // it in four 16-column steps (tcgen05.ld.x16 keeps the live registers < 113), stages the bf16 result(s) in its
+    // private 4 KB 128B-swizzled buffer(s) and issues its own TMA store(s).
     const int ew = warp - 2;                // 0..15
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int c = ew >> 2;                  // 64-column chunk owned by this warp
     const bool has_chunk = c < NCHUNK;
     const int row = q * 32 + lane;          // accumulator row owned by this thread
-    uint8_t* st0 = staging + ew * GEMM_WARP_STAGING;
+    uint8_t* st0 = staging + ew * GEMM_WARP_STAGING * (DUAL ? 2 : 1);
+    uint8_t* st1 = st0 + GEMM_WARP_STAGING;
     const bool store_lane = elect_one_sync() != 0;   // this lane owns the warp's TMA-store bulk groups for the whole kernel
 
     // ---- auxiliary-operand prefetch (registers): 16 columns of this thread's row = 2 x 16 B, one step ahead
@@ -369,16 +372,18 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const float a0 = bf16lo(w[e]), a1 = bf16hi(w[e]);
               if (epi_is_resid(EPI)) { x0 += a0; x1 += a1; }
               if (epi_is_mul(EPI)) { x0 *= a0; x1 *= a1; }
-              if (EPI == EPI_DGELU) { x0 *= dgelu_erf(a0); x1 *= dgelu_erf(a1); }
+              if (EPI == EPI_DGELU) { x0 *= a0; x1 *= a1; }
               o[g * 4 + e] = pack_bf16x2(x0, x1);
             }
           }
         } else if (EPI == EPI_GELU) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
-            // gelu is applied to the bf16-rounded pre-activation that backward will re-read
-            o2[e] = pack_bf16x2(gelu_erf(bf16lo(o[e])), gelu_erf(bf16hi(o[e])));
+            // one erf/exp evaluation yields both gelu(z) and gelu'(z); backward then only multiplies by the saved gelu'
+            float d0, d1;
+            const float g0 = gelu_erf_t<true>(f[2 * e], d0), g1 = gelu_erf_t<true>(f[2 * e + 1], d1);
+            o[e] = pack_bf16x2(d0, d1);
+            o2[e] = pack_bf16x2(g0, g1);
           }
         } else if (EPI == EPI_GELU_ONLY) {
 #pragma unroll
@@ -394,13 +399,13 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int chunk = (st * 2 + g) ^ (lane & 7);
           st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
         }
-        if (DUAL && row_ok) {
-          // second output: this thread's 32 contiguous bytes (one full sector) straight to global memory
-          __nv_bfloat16* drow = p.d2 + (long long)tc.b_idx * p.d2_bs + (long long)grow * p.d2_ld + cols;
+        if (DUAL) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g)
-            if (cols + g * 8 < p.N)
-              *reinterpret_cast<uint4*>(drow + g * 8) = make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]);
+          for (int g = 0; g < 2; ++g) {
+            const int chunk = (st * 2 + g) ^ (lane & 7);
+            st_shared_v4(smem_u32(st1) + lane * 128 + chunk * 16,
+                         make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
+          }
         }
       }
       if (chunk_live && EPI != EPI_ATOMIC) {
@@ -408,6 +413,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (store_lane) {
           tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
+          if (DUAL) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
           tma_store_commit();
         }
       }

@@ -337,8 +337,8 @@ __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_
 // --------------------------------------------------------------------------- strided elementwise helpers
 // All take [rows, C] views with explicit row strides (elements); C % 8 == 0.
 // MODE 0: out = a * colvec[c]                                  (ResMLP: dF = dY * gamma, res_mlp.py:54,56)
-// MODE 1: out = a * gelu'(b)                                   (gMLP: d(pre-activation) of the v half)
-// MODE 2: out = a * b * gelu'(c3) ; out2 = a * d4              (gMLP gate backward: dZp_u = dG*vt*gelu'(Zp_u), dVt = dG*u)
+// MODE 1: out = a * b          (b = gelu'(z) saved by the forward epilogue: d(pre-activation) = d(activation) * gelu')
+// MODE 2: out = a * b * c3 ; out2 = a * d4   (gMLP gate backward: dZp_u = dG * vt * gelu'(Zp_u), dVt = dG * u)
 template <int MODE>
 __global__ void __launch_bounds__(RW_THREADS)
 ew_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bfloat16* __restrict__ b, long long b_ld,
@@ -359,14 +359,14 @@ ew_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bfloat
     } else if (MODE == 1) {
       unpack8(ldg_nc_v4(b + r * b_ld + col), y);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = x[e] * dgelu_erf(y[e]);
+      for (int e = 0; e < 8; ++e) o[e] = x[e] * y[e];
     } else {
       float z[8], u[8], o2[8];
       unpack8(ldg_nc_v4(b + r * b_ld + col), y);
       unpack8(ldg_nc_v4(c3 + r * c3_ld + col), z);
       unpack8(ldg_nc_v4(d4 + r * d4_ld + col), u);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { o[e] = x[e] * y[e] * dgelu_erf(z[e]); o2[e] = x[e] * u[e]; }
+      for (int e = 0; e < 8; ++e) { o[e] = x[e] * y[e] * z[e]; o2[e] = x[e] * u[e]; }
       *reinterpret_cast<uint4*>(out2 + r * out2_ld + col) = pack8(o2);
     }
     *reinterpret_cast<uint4*>(out + r * out_ld + col) = pack8(o);

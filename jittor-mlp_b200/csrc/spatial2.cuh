@@ -143,7 +143,7 @@ hire_restore_adj_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* _
 // nn.Conv2d(dim, dim, k, groups=dim, padding="same") on [B, H, W, C] (conv_mixer.py:24): a shared-memory stencil.
 // Block = 8x8 output pixels x 64 channels; thread = (channel, 2 output rows); each tap row is slid over a register
 // window so every shared-memory load feeds K FMAs.  FLIP = 1 evaluates the same stencil with the kernel rotated by
-// 180 degrees, which is the input gradient.  EPI = 1 adds the bias and writes z (pre-activation) and gelu(z).
+// 180 degrees, which is the input gradient.  EPI = 1 adds the bias and writes gelu'(z) (for backward) and gelu(z).
 constexpr int DW_TILE = 8;
 constexpr int DW_CH = 64;
 template <int K>
@@ -224,9 +224,14 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
           const int ww = w0 + q;
           if (ww >= W) continue;
           const long long o = ((b * H + hh) * W + ww) * C + c;
-          const __nv_bfloat16 zb = __float2bfloat16(acc[r][q]);
-          out[o] = zb;
-          if (EPI) out2[o] = __float2bfloat16(gelu_erf(__bfloat162float(zb)));
+          if (EPI) {            // out = gelu'(z) (kept for backward), out2 = gelu(z)
+            float d;
+            const float gz = gelu_erf_t<true>(acc[r][q], d);
+            out[o] = __float2bfloat16(d);
+            out2[o] = __float2bfloat16(gz);
+          } else {
+            out[o] = __float2bfloat16(acc[r][q]);
+          }
         }
       }
     }

@@ -81,15 +81,15 @@ def test_gelu_dual_output_and_dgelu_and_resid_and_mul():
     Z = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
     H = torch.zeros_like(Z)
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_GELU, D=Z, D2=H, bias=bias, bias_mode=1)
-    assert rel(Z, z_ref) < 5e-3
-    assert rel(H, gelu(Z.float())) < 5e-3           # gelu of the stored (bf16) pre-activation
+    assert rel(Z, dgelu(z_ref)) < 5e-3              # D  = gelu'(z): what backward multiplies by
+    assert rel(H, gelu(z_ref)) < 5e-3               # D2 = gelu(z)
     H2 = torch.zeros_like(Z)
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_GELU_ONLY, D=H2, bias=bias, bias_mode=1)
     assert rel(H2, gelu(z_ref)) < 5e-3
     aux = rnd(M, N, seed=5)
     D = torch.zeros_like(Z)
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_DGELU, D=D, aux=aux)
-    assert rel(D, acc * dgelu(aux.float())) < 5e-3
+    assert rel(D, acc * aux.float()) < 5e-3         # aux holds the saved gelu'(z)
     cs = rnd(N, seed=6)
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_RESID, D=D, aux=aux, bias=bias, bias_mode=1, colscale=cs)
     assert rel(D, z_ref * cs.float()[None, :] + aux.float()) < 5e-3
@@ -174,10 +174,10 @@ def test_cta_pair_epilogues_and_split_k():
     acc = A.float() @ Bf.t()
     Z, H = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV), torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_GELU, D=Z, D2=H, bias=bias, bias_mode=1, cta_group=2)
-    assert rel(Z, acc + bias.float()) < 5e-3 and rel(H, gelu(Z.float())) < 5e-3
+    assert rel(Z, dgelu(acc + bias.float())) < 5e-3 and rel(H, gelu(acc + bias.float())) < 5e-3
     D = torch.zeros_like(Z)
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_DGELU, D=D, aux=aux, cta_group=2)
-    assert rel(D, acc * dgelu(aux.float())) < 5e-3
+    assert rel(D, acc * aux.float()) < 5e-3
     ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_RESID, D=D, aux=aux, bias=bias, bias_mode=1, cta_group=2)
     assert rel(D, acc + bias.float() + aux.float()) < 5e-3
     R, Dout, Din = 3000, 512, 264
