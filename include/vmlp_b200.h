@@ -203,6 +203,13 @@ int vmlp_dwconv_dgrad(const void* dz, const void* weight, void* dx, int32_t B, i
 int vmlp_dwconv_wgrad(const void* x, const void* dz, float* dw, int32_t B, int32_t H, int32_t W, int32_t C, int32_t K,
                       vmlp_stream_t stream);
 
+/* Patch-embedding stem: Conv2d(Cin, C, kernel = stride = P) as a GEMM over non-overlapping patches
+ * (mlp_mixer.py:58-60,68-71).  x: NCHW bf16; rows: [B * (H/P) * (W/P), Cin * P * P] with column order (ci, i, j) = the
+ * Conv2d weight's own [C, Cin*P*P] layout.  P % 8 == 0.  forward != 0 gathers rows from x; forward == 0 scatters
+ * d(rows) back into d(x) (exact inverse). */
+int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t P, int32_t forward,
+                  vmlp_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------
  * MLP-Mixer block: models_pytorch/mlp_mixer.py:35-40
  *     u = x + TokenFF(LN1(x))   (FeedForward with Conv1d(k=1) over tokens, :16-27,:37)

@@ -134,6 +134,7 @@ SYMBOLS = [
                                   c_int32, c_void_p]),
     ("vmlp_dwconv_dgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_dwconv_wgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_patchify", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_mixer_block_fwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, _P(MixerSaved), c_void_p]),
     ("vmlp_mixer_grad_elems", c_int64, [_P(MixerParams)]),
     ("vmlp_mixer_bwd_workspace_elems", c_int64, [_P(MixerParams)]),

@@ -767,6 +767,19 @@ int vmlp_dwconv_wgrad(const void* x, const void* dz, float* dw, int32_t B, int32
                      (dwconv_wgrad_launch<7>(x, dz, dw, B, H, W, C, st)), (dwconv_wgrad_launch<9>(x, dz, dw, B, H, W, C, st)));
 }
 
+int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t P, int32_t forward,
+                  vmlp_stream_t stream) {
+  if (!src || !dst || B <= 0 || Cin <= 0 || P <= 0 || (P % 8) || (H % P) || (W % P)) return fail(VMLP_EINVAL, "patchify args");
+  if (!aligned16(src) || !aligned16(dst)) return fail(VMLP_EALIGN, "patchify alignment");
+  const long long total = (long long)B * Cin * H * W / 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (forward) patchify_kernel<1><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)src, (bf)dst, B, Cin, H, W, P);
+  else patchify_kernel<0><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)src, (bf)dst, B, Cin, H, W, P);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
 // ============================================================================================ MLP-Mixer block
 static int mixer_check(const vmlp_mixer_params* p) {
   if (!p) return fail(VMLP_EINVAL, "null params");

@@ -190,6 +190,30 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int a = 0; a < BN / CG / 64; ++a)
               load(sb + a * (GEMM_BK * 128), &tmB, nb0 + a * 64, kc, bb);
           }
+            // L2 prefetch of the SAME k-block of this CTA's NEXT tile (one whole tile of lookahead beyond the SMEM ring)
+            const int ntile = tile + num_clusters;
+            if (ntile < total_tiles) {
+              const TileCoord nt = decode_tile<BN, CG>(p, ntile, cta_rank);
+              if (nt.s_idx == tc.s_idx) {
+                const int nbatch = p.kbatch ? (kb / p.kpb) : nt.b_idx;
+                const int nba = p.a_batched ? nbatch : 0, nbb = p.b_batched ? nbatch : 0;
+                const int nnb0 = nt.n0 + cta_rank * (BN / CG);
+                if (nt.m0 != tc.m0 || nba != ba) {
+                  if (!p.a_mn) tma_prefetch_l2_3d(&tmA, kc, nt.m0, nba);
+                  else {
+#pragma unroll
+                    for (int a = 0; a < GEMM_BM / 64; ++a) tma_prefetch_l2_3d(&tmA, nt.m0 + a * 64, kc, nba);
+                  }
+                }
+                if (nnb0 != nb0 || nbb != bb) {
+                  if (!p.b_mn) tma_prefetch_l2_3d(&tmB, kc, nnb0, nbb);
+                  else {
+#pragma unroll
+                    for (int a = 0; a < BN / CG / 64; ++a) tma_prefetch_l2_3d(&tmB, nnb0 + a * 64, kc, nbb);
+                  }
+                }
+              }
+            }
           }   // elected lane
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -89,6 +89,13 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tile (no shared memory, no completion tracking): lets the producer run a whole output tile ahead of
+// the SMEM ring, so the later cp.async.bulk.tensor of the same box is an L2 hit instead of an HBM round trip.
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // 3-D tiled store, shared -> global (bulk async group).
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1,
                                              int c2) {

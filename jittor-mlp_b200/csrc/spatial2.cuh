@@ -301,3 +301,28 @@ dwconv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __
 }
 
 }  // namespace vmlp
+
+// ============================================================================================ patch embedding (stem)
+// Conv2d(Cin, C, kernel = stride = P) == GEMM over non-overlapping patches (mlp_mixer.py:58-60,68-71):
+//   rows[(b, ph, pw), (ci, i, j)] = x[b, ci, ph*P + i, pw*P + j]        (x NCHW; P % 8 == 0 so each j-run is 16-byte vectors)
+// FWD = 1 gathers the patch rows; FWD = 0 is the exact inverse (scatter of d(rows) back to d(x), one-to-one).
+namespace vmlp {
+template <int FWD>
+__global__ void __launch_bounds__(RW_THREADS)
+patchify_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int Cin, int H, int W, int P) {
+  const int nph = H / P, npw = W / P, vp = P / 8;
+  const long long total = (long long)B * nph * npw * Cin * P * vp;
+  for (long long idx = (long long)blockIdx.x * RW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * RW_THREADS) {
+    long long t = idx;
+    const int jv = static_cast<int>(t % vp); t /= vp;
+    const int i = static_cast<int>(t % P); t /= P;
+    const int ci = static_cast<int>(t % Cin); t /= Cin;
+    const int pw = static_cast<int>(t % npw); t /= npw;
+    const int ph = static_cast<int>(t % nph);
+    const long long b = t / nph;
+    const long long xoff = ((b * Cin + ci) * H + ph * P + i) * W + pw * P + jv * 8;
+    if (FWD) *reinterpret_cast<uint4*>(dst + idx * 8) = ldg_nc_v4(src + xoff);
+    else *reinterpret_cast<uint4*>(dst + xoff) = ldg_nc_v4(src + idx * 8);
+  }
+}
+}  // namespace vmlp

@@ -265,3 +265,48 @@ def axial_shift(x, shift_size, dim):
         groups.append((g * cs, s, 0) if dim == 2 else (g * cs, 0, s))
     groups.append((C, 0, 0))
     return ShiftFn.apply(x, groups, False)
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """Conv2d(Cin, C, kernel = stride = P) + permute(0,2,3,1).view(B, -1, C) of the Mixer / ResMLP / gMLP stems
+    (mlp_mixer.py:58-60,68-71) as one gather + one GEMM producing the contiguous [B, N, C] block input directly."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _chk(x, "x"); _chk(w, "w"); _chk(b, "b")
+        B, Cin, H, W = x.shape
+        C, P = w.shape[0], w.shape[-1]
+        N, Kd = (H // P) * (W // P), Cin * P * P
+        rows = _new(B * N, Kd, like=x)
+        L.check(L.lib().vmlp_patchify(x.data_ptr(), rows.data_ptr(), B, Cin, H, W, P, 1, L.stream_ptr()))
+        y = _new(B, N, C, like=x)
+        gemm(B * N, C, Kd, operand(rows, 0), operand(w.view(C, Kd), 0), L.EPI_STORE, D=y.view(B * N, C), bias=b, bias_mode=1)
+        ctx.save_for_backward(rows, w)
+        ctx.xshape, ctx.has_b = tuple(x.shape), b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, w = ctx.saved_tensors
+        B, Cin, H, W = ctx.xshape
+        C, P = w.shape[0], w.shape[-1]
+        dy2 = dy.contiguous().view(-1, C)
+        gw, gb = _param_grads(dy2, rows, w, w.new_empty(C) if ctx.has_b else None)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            drows = torch.empty_like(rows)
+            gemm(rows.shape[0], rows.shape[1], C, operand(dy2, 0), operand(w.view(C, -1), 1), L.EPI_STORE, D=drows)
+            dx = torch.empty(ctx.xshape, dtype=BF16, device=dy.device)
+            L.check(L.lib().vmlp_patchify(drows.data_ptr(), dx.data_ptr(), B, Cin, H, W, P, 0, L.stream_ptr()))
+        return dx, gw, gb
+
+
+def patch_embed(x, conv):
+    """Stem dispatcher: the GEMM path needs a square kernel == stride with width % 8 == 0 and no padding; any other
+    stem geometry keeps cuDNN (stems are outside the fused block path)."""
+    kh, kw = conv.kernel_size
+    if kh == kw and conv.stride == (kh, kw) and kh % 8 == 0 and conv.padding == (0, 0) and conv.groups == 1:
+        return PatchEmbedFn.apply(x.contiguous(), conv.weight, conv.bias)
+    p = conv(x)
+    b, c = p.shape[0], p.shape[1]
+    return p.permute(0, 2, 3, 1).reshape(b, -1, c)

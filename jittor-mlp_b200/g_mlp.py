@@ -5,7 +5,7 @@ Drop-in for /root/reference/models_pytorch/g_mlp.py (same classes, constructor s
 """
 from torch import nn
 
-from . import ops
+from . import fn, ops
 from .utils import check_sizes
 
 
@@ -52,10 +52,7 @@ class gMLPForImageClassification(gMLP):
         self.mlp_head = nn.Sequential(nn.Linear(d_model, num_classes))
 
     def forward(self, x):
-        patches = self.patcher(x)
-        batch_size, num_channels, _, _ = patches.shape
-        patches = patches.permute(0, 2, 3, 1)
-        patches = patches.view(batch_size, -1, num_channels)
+        patches = fn.patch_embed(x, self.patcher[0])        # stem conv as gather + GEMM -> contiguous [B, N, C]
         embedding = self.model(patches)
         embedding = embedding.mean(dim=1)
         return self.mlp_head(embedding)

@@ -7,7 +7,7 @@ keys).  Quirks preserved: the token-mixing residual is taken afte
 import torch
 from torch import nn
 
-from . import ops
+from . import fn, ops
 from .utils import check_sizes
 
 
@@ -74,10 +74,7 @@ class ResMLPForImageClassification(ResMLP):
         self.mlp_head = nn.Sequential(nn.Linear(d_model, num_classes))
 
     def forward(self, x):
-        patches = self.patcher(x)
-        batch_size, num_channels, _, _ = patches.shape
-        patches = patches.permute(0, 2, 3, 1)
-        patches = patches.view(batch_size, -1, num_channels)
+        patches = fn.patch_embed(x, self.patcher[0])        # stem conv as gather + GEMM -> contiguous [B, N, C]
         embedding = self.model(patches)
         embedding = embedding.mean(dim=1)
         return self.mlp_head(embedding)
