@@ -74,7 +74,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 // 3-D bf16 tensor map: dims (inner, rows, batch), 128B swizzle, zero OOB fill.
 int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t rows, int64_t batch, int64_t ld,
-             int64_t bstride, int box_inner, int box_rows) {
+             int64_t bstride, int box_inner, int box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return fail(VMLP_ELAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
   if (!aligned16(ptr) || (ld % 8) != 0 || (batch > 1 && (bstride % 8) != 0))
@@ -86,7 +86,7 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t rows, int64
   cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(VMLP_EINVAL, "cuTensorMapEncodeTiled failed (%d): inner %lld rows %lld batch %lld ld %lld", (int)r,
@@ -234,11 +234,11 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
     split = (p.k_blocks + per - 1) / per;     // no empty split
   } else {
     if (!g.D) return fail(VMLP_EINVAL, "null output");
-    rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 64, 32);   // per-warp store box: 64 cols x 32 rows
+    rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);   // per-warp store box: 32 cols x 32 rows
     if (rc) return rc;
     if (epi_is_dual(epi)) {
       if (!g.D2) return fail(VMLP_EINVAL, "dual-output epilogue needs D2");
-      rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 64, 32);
+      rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
   }

@@ -26,7 +26,7 @@ constexpr int GEMM_BK = 64;       // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_EPI_WARPS = 16;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_STAGE_A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
-constexpr int GEMM_WARP_STAGING = 32 * 64 * 2;              // 32 rows x 64 bf16 cols = 4 KB
+constexpr int GEMM_WARP_STAGING = 32 * 32 * 2;              // 32 rows x 32 bf16 cols = 2 KB (64-byte rows, SWIZZLE_64B)
 
 enum GemmEpilogue : int {
   EPI_STORE = 0,    // D = acc (+bias)                                       -> bf16 via TMA store
@@ -72,7 +72,9 @@ template <int BN, int EPI, int CG = 1>
 struct GemmSmem {
   static constexpr bool DUAL = (EPI == EPI_GELU || EPI == EPI_RESID_DUAL || EPI == EPI_MUL_DUAL);
   // dual-output epilogues need a second staging buffer per warp; they are epilogue-bound, so fewer stages are enough
-  static constexpr int STAGES = (CG == 2) ? (DUAL ? 3 : (EPI == EPI_ATOMIC) ? 6 : 5) : (DUAL ? 2 : (EPI == EPI_ATOMIC) ? 4 : 3);
+  // the main loop is TMA-latency bound (refill latency ~2800 cycles vs 512 cycles of MMA per stage): every byte of shared
+  // memory not needed by the epilogue staging goes to pipeline stages
+  static constexpr int STAGES = (CG == 2) ? (DUAL ? 5 : (EPI == EPI_ATOMIC) ? 7 : 6) : (DUAL ? 3 : 4);
   static constexpr int STAGE_B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
@@ -272,8 +274,8 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ===================================================================== epilogue (warps 2..17)
     // 16 warps = 4 per scheduler: the epilogue math (GELU / GELU') is latency-bound with fewer.  Warp (q, c) owns the
     // 32 accumulator rows of TMEM lane quarter q = warp % 4 and the 64-column chunk c = (warp - 2) / 4 of every tile, walks
-    // it in four 16-column steps (tcgen05.ld.x16 keeps the live registers < 113), stages the bf16 result(s) in its
-    // private 4 KB 128B-swizzled buffer(s) and issues its own TMA store(s).
+    // it in four 16-column steps (tcgen05.ld.x16 keeps the live registers < 113), stages each 32-column half of the bf16
+    // result(s) in its private 2 KB 64B-swizzled buffer(s) and issues its own TMA store(s).
     const int ew = warp - 2;                // 0..15
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int c = ew >> 2;                  // 64-column chunk owned by this warp
@@ -311,11 +313,6 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (p.bias_mode == 2 && row_ok) rbias = __bfloat162float(p.bias[grow]);
       const int col0 = tc.n0 + c * 64;
       const bool chunk_live = has_chunk && (col0 < p.N);   // ragged N: dead chunks are skipped entirely
-      if (chunk_live && EPI != EPI_ATOMIC) {
-        // the staging buffer must have been drained by the TMA store of the previous tile (a whole tile ago)
-        if (store_lane) tma_store_wait_read<0>();
-        __syncwarp();
-      }
 #pragma unroll
       for (int st = 0; st < 4; ++st) {
         uint4 aux_cur[2];
@@ -324,6 +321,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           aux_cur[1] = aux_nxt[1];
           if (st < 3) load_aux(tile, st + 1, aux_nxt);
           else load_aux(tile + num_clusters, 0, aux_nxt);
+        }
+        if (chunk_live && EPI != EPI_ATOMIC && (st & 1) == 0) {
+          // the 2 KB staging buffer(s) must have been drained by the previous 32-column TMA store of this warp
+          if (store_lane) tma_store_wait_read<0>();
+          __syncwarp();
         }
         uint32_t v[16];
         if (chunk_live) {
@@ -416,29 +418,28 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
         }
-        // staging tile = [32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7) (matches SWIZZLE_128B)
-        const uint32_t srow = smem_u32(st0) + lane * 128;
+        // staging tile = [32 rows][64 B]; 16-byte chunk c of row r lives at c ^ ((r >> 1) & 3) (matches SWIZZLE_64B)
+        const uint32_t srow = lane * 64;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const int chunk = (st * 2 + g) ^ (lane & 7);
-          st_shared_v4(srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
-        }
-        if (DUAL) {
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int chunk = (st * 2 + g) ^ (lane & 7);
-            st_shared_v4(smem_u32(st1) + lane * 128 + chunk * 16,
+          const int chunk = ((st & 1) * 2 + g) ^ ((lane >> 1) & 3);
+          st_shared_v4(smem_u32(st0) + srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
+          if (DUAL)
+            st_shared_v4(smem_u32(st1) + srow + chunk * 16,
                          make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
-          }
         }
-      }
-      if (chunk_live && EPI != EPI_ATOMIC) {
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (store_lane) {
-          tma_store_3d(&tmD, st0, col0, tc.m0 + q * 32, tc.b_idx);
-          if (DUAL) tma_store_3d(&tmD2, st1, col0, tc.m0 + q * 32, tc.b_idx);
-          tma_store_commit();
+        if (st & 1) {
+          // a 32-column half of the chunk is complete: hand it to the TMA engine
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (store_lane) {
+            const int colh = col0 + (st >> 1) * 32;
+            if (colh < p.N) {
+              tma_store_3d(&tmD, st0, colh, tc.m0 + q * 32, tc.b_idx);
+              if (DUAL) tma_store_3d(&tmD2, st1, colh, tc.m0 + q * 32, tc.b_idx);
+            }
+            tma_store_commit();
+          }
         }
       }
     }
