@@ -213,6 +213,10 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   p.aux_bs = g.aux_bs;
   p.out_f32 = g.out_f32;
   p.out_ld = g.out_ld;
+  {
+    static const int pf = getenv("VMLP_L2_PREFETCH") ? atoi(getenv("VMLP_L2_PREFETCH")) : 0;
+    p.l2_prefetch = pf;
+  }
   if (p.bias_mode == 1 && !aligned16(g.bias)) return fail(VMLP_EALIGN, "bias must be 16-byte aligned");
   if (p.colscale && !aligned16(p.colscale)) return fail(VMLP_EALIGN, "colscale must be 16-byte aligned");
   const bool needs_aux = (epi_is_resid(epi) || epi == EPI_DGELU || epi_is_mul(epi));
@@ -545,7 +549,15 @@ int vmlp_chan_lin(const void* p, const void* q, const void* z, const float* A, c
   if (!aligned16(p) || !aligned16(out) || (q && !aligned16(q)) || (z && !aligned16(z))) return fail(VMLP_EALIGN, "chan_lin alignment");
   const long long total = rows * (C / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = ew_grid(total);
+  // grid * 256 must be a multiple of C/8 (see the kernel): round up to a multiple of nvec / gcd(nvec, 256)
+  int grid = ew_grid(total);
+  {
+    const int nvec = C / 8;
+    int g = nvec, r = RW_THREADS;
+    while (r) { const int t = g % r; g = r; r = t; }
+    const int step = nvec / g;
+    grid = ((grid + step - 1) / step) * step;
+  }
   if (q && z) chan_lin_kernel<1, 1><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);
   else if (q) chan_lin_kernel<1, 0><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);
   else if (z) chan_lin_kernel<0, 1><<<grid, RW_THREADS, 0, st>>>((cbf)p, (cbf)q, (cbf)z, A, Bq, Cc, (bf)out, total, C);

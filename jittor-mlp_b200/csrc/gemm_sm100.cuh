@@ -61,6 +61,7 @@ struct GemmParams {
   long long aux_ld, aux_bs;       // row stride, batch stride (elements)
   float* out_f32;                 // EPI_ATOMIC destination
   long long out_ld;
+  int l2_prefetch;                // producer also L2-prefetches the next tile's operand boxes
   __nv_bfloat16* d2;              // second output of the *_DUAL / GELU epilogues (direct stores)
   long long d2_ld, d2_bs;
 };
@@ -194,7 +195,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
             // L2 prefetch of the SAME k-block of this CTA's NEXT tile (one whole tile of lookahead beyond the SMEM ring)
             const int ntile = tile + num_clusters;
-            if (ntile < total_tiles) {
+            if (p.l2_prefetch && ntile < total_tiles) {
               const TileCoord nt = decode_tile<BN, CG>(p, ntile, cta_rank);
               if (nt.s_idx == tc.s_idx) {
                 const int nbatch = p.kbatch ? (kb / p.kpb) : nt.b_idx;

@@ -245,18 +245,28 @@ __global__ void __launch_bounds__(RW_THREADS)
 chan_lin_kernel(const __nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ q,
                 const __nv_bfloat16* __restrict__ z, const float* __restrict__ A, const float* __restrict__ Bq,
                 const float* __restrict__ Cc, __nv_bfloat16* __restrict__ out, long long total_vec, int C) {
+  // the host sizes the grid so that (gridDim.x * RW_THREADS) % (C / 8) == 0: every thread then stays on ONE channel
+  // vector for its whole grid-stride loop and keeps its 8 (x3) fp32 coefficients in registers
   const int nvec = C >> 3;
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total_vec; i += (long long)gridDim.x * RW_THREADS) {
-    const int c0 = static_cast<int>(i % nvec) * 8;
+  const long long start = (long long)blockIdx.x * RW_THREADS + threadIdx.x;
+  const int c0 = static_cast<int>(start % nvec) * 8;
+  float a[8], bq[8], cc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a[e] = A[c0 + e];
+    cc[e] = Cc[c0 + e];
+    bq[e] = HAS_Q ? Bq[c0 + e] : 0.f;
+  }
+  for (long long i = start; i < total_vec; i += (long long)gridDim.x * RW_THREADS) {
     float pv[8], qv[8], zv[8], o[8];
     unpack8(ldg_nc_v4(p + i * 8), pv);
     if (HAS_Q) unpack8(ldg_nc_v4(q + i * 8), qv);
     if (DGELU) unpack8(ldg_nc_v4(z + i * 8), zv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float v = A[c0 + e] * pv[e] + Cc[c0 + e];
-      if (HAS_Q) v += Bq[c0 + e] * qv[e];
-      if (DGELU) v *= dgelu_erf(zv[e]);
+      float v = fmaf(a[e], pv[e], cc[e]);
+      if (HAS_Q) v = fmaf(bq[e], qv[e], v);
+      if (DGELU) v *= zv[e];        // z holds the saved gelu'(pre-activation)
       o[e] = v;
     }
     *reinterpret_cast<uint4*>(out + i * 8) = pack8(o);

@@ -1,0 +1,49 @@
+"""Run under torchrun with 2+ ranks (NCCL): data-parallel fwd+bwd of a small Mixer on batch shards must give every rank
+the same averaged gradients as ONE process running the concatenated batch."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import jittor_mlp_b200 as J  # noqa: E402
+from jittor_mlp_b200 import dp  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+kw = dict(d_model=256, depth=3, image_size=64, patch_size=8, num_classes=32)
+torch.manual_seed(100 + rank)                     # replicas start different: the wrapper must broadcast rank 0's
+model = J.MLPMixerForImageClassification(**kw).to(dev).bfloat16().train()
+ddp = dp.DataParallel(model)
+per = 8
+xs = torch.randn(per * world, 3, 64, 64, generator=torch.Generator().manual_seed(7)).to(dev).bfloat16()
+loss_fn = lambda o: o.float().square().mean()
+model.zero_grad(set_to_none=True)
+ddp.step_fwd_bwd(xs[rank * per:(rank + 1) * per], loss_fn)
+torch.cuda.synchronize()
+dp_grads = {k: p.grad.float().clone() for k, p in model.named_parameters()}
+# reference: same (broadcast) weights, whole batch, no communication
+model.zero_grad(set_to_none=True)
+loss_fn(model(xs)).backward()
+torch.cuda.synchronize()
+worst = 0.0
+for k, p in model.named_parameters():
+    ref = p.grad.float()
+    err = float((dp_grads[k] - ref).norm() / ref.norm().clamp_min(1e-20))
+    worst = max(worst, err)
+t = torch.tensor([worst], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+# every rank must also hold IDENTICAL averaged gradients
+flat = torch.cat([g.flatten() for g in dp_grads.values()])
+ref0 = flat.clone()
+dist.broadcast(ref0, src=0)
+same = torch.tensor([float(torch.equal(flat, ref0))], device=dev)
+dist.all_reduce(same, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"dp_check world={world}: max rel-L2(dp grad, big-batch grad) = {float(t):.3e}; identical across ranks = {bool(same.item())}")
+    assert float(t) < 2e-2 and bool(same.item())
+dist.barrier()
+dist.destroy_process_group()
