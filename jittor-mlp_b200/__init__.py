@@ -8,3 +8,4 @@ from .s2_mlp import S2MLPv1, S2MLPv1_deep, S2MLPv1_wide, S2MLPv2  # noqa: F401
 from .as_mlp import AS_MLP  # noqa: F401
 from .hire_mlp import HireMLP  # noqa: F401
 from .conv_mixer import ConvMixer  # noqa: F401
+from .graph import GraphedStep  # noqa: F401

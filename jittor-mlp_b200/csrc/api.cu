@@ -717,7 +717,11 @@ template <int K, int FLIP, int EPI>
 static int dwconv_launch(const void* x, const void* w, const void* bias, void* o1, void* o2, int B, int H, int W, int C,
                          cudaStream_t st) {
   auto kern = dwconv_kernel<K, FLIP, EPI>;
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+    attr_done = true;
+  }
   const long long tiles = (long long)B * ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
   const int cb = (C + DW_CH - 1) / DW_CH;
   long long gx = ((long long)device_info().sms * 3 + cb - 1) / cb;
@@ -730,7 +734,11 @@ static int dwconv_launch(const void* x, const void* w, const void* bias, void* o
 template <int K>
 static int dwconv_wgrad_launch(const void* x, const void* dz, float* dw, int B, int H, int W, int C, cudaStream_t st) {
   auto kern = dwconv_wgrad_kernel<K>;
-  CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+    attr_done = true;
+  }
   const long long tiles = (long long)B * ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
   const int cb = (C + DW_CH - 1) / DW_CH;
   long long gx = ((long long)device_info().sms * 3 + cb - 1) / cb;

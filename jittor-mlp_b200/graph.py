@@ -1,0 +1,36 @@
+"""CUDA-graph capture of one forward+backward step.
+
+The shift-family blocks are sequenced from Python (hundreds of C-ABI launches per step, ~30 us of host time each), so at
+moderate batch sizes the GPU waits for the host; the whole step is static-shaped and free of host synchronisation,
+which makes it capturable once and replayable with a single launch.  Every kernel of the library runs on torch's
+current stream, so it lands in the capture like any ATen op; TMA descriptors are encoded on the host at capture time and
+are baked into the graph's kernel parameters (activations come from the graph's private memory pool, parameters keep
+their addresses).
+"""
+import torch
+
+
+class GraphedStep:
+    """loss = loss_fn(model(x)); loss.backward() as one CUDA graph.  Gradients land in ``p.grad`` (static tensors)."""
+
+    def __init__(self, model, example_x, loss_fn, warmup=3):
+        self.model, self.loss_fn = model, loss_fn
+        self.static_x = example_x.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the default stream (allocator, lazy inits)
+            for _ in range(warmup):
+                model.zero_grad(set_to_none=True)
+                loss_fn(model(self.static_x)).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        model.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.static_loss = loss_fn(model(self.static_x))
+            self.static_loss.backward()
+
+    def run(self, x=None, non_blocking=True):
+        if x is not None:
+            self.static_x.copy_(x, non_blocking=non_blocking)
+        self.graph.replay()
+        return self.static_loss

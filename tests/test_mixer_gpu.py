@@ -82,3 +82,24 @@ def test_unsupported_inputs_raise():
     m = J.MLPMixerForImageClassification(d_model=64, depth=1, image_size=32, patch_size=8).to(DEV)
     with pytest.raises(TypeError):          # fp32 parameters: no silent fallback
         m(torch.randn(1, 3, 32, 32, device=DEV))
+
+
+def test_cuda_graph_step_matches_eager():
+    """GraphedStep replays the same kernels: loss and gradients equal the eager step (up to fp32-atomic ordering)."""
+    torch.manual_seed(0)
+    kw = dict(d_model=128, depth=2, image_size=64, patch_size=8, num_classes=10)
+    m = J.MLPMixerForImageClassification(**kw).to(DEV).bfloat16().train()
+    x = torch.randn(8, 3, 64, 64, device=DEV).bfloat16()
+    loss_fn = lambda o: o.float().square().mean()
+    m.zero_grad(set_to_none=True)
+    l0 = loss_fn(m(x))
+    l0.backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters()}
+    gs = J.GraphedStep(m, x, loss_fn)
+    x2 = torch.randn(8, 3, 64, 64, device=DEV).bfloat16()
+    gs.run(x2)                                   # different input through the same graph
+    l1 = gs.run(x)
+    torch.cuda.synchronize()
+    assert abs(float(l1) - float(l0)) < 1e-3 * abs(float(l0))
+    for k, p in m.named_parameters():
+        assert restate.rel_l2(p.grad.cpu(), ref[k].cpu()) < 2e-3, k
