@@ -90,6 +90,8 @@ typedef struct {
   int32_t split_k;                     /* 0 = choose automatically */
   int32_t block_n;                     /* 0 = choose automatically (256 or 128) */
   int32_t cta_group;                   /* 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile */
+  float* red_out; int32_t red_mode;    /* optional: += sums of the stored D per column (1) or per row (2): the bias
+                                          gradient when D is d(pre-activation); caller zero-fills */
 } vmlp_gemm_args;
 
 int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream);

@@ -64,7 +64,7 @@ class GemmArgs(ctypes.Structure):
                 ("bias", c_void_p), ("bias_mode", c_int32), ("colscale", c_void_p),
                 ("aux", c_void_p), ("aux_ld", c_int64), ("aux_bs", c_int64),
                 ("out_f32", c_void_p), ("out_ld", c_int64), ("split_k", c_int32), ("block_n", c_int32),
-                ("cta_group", c_int32)]
+                ("cta_group", c_int32), ("red_out", c_void_p), ("red_mode", c_int32)]
 
 
 class MixerParams(ctypes.Structure):

@@ -213,6 +213,9 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   p.aux_bs = g.aux_bs;
   p.out_f32 = g.out_f32;
   p.out_ld = g.out_ld;
+  p.red_out = g.red_out;
+  p.red_mode = g.red_out ? g.red_mode : 0;
+  if (p.red_mode < 0 || p.red_mode > 2 || (p.red_mode && epi == EPI_ATOMIC)) return fail(VMLP_EINVAL, "bad red_mode");
   {
     static const int pf = getenv("VMLP_L2_PREFETCH") ? atoi(getenv("VMLP_L2_PREFETCH")) : 0;
     p.l2_prefetch = pf;
@@ -338,9 +341,21 @@ int vmlp_layernorm_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
   const DeviceInfo& dv = device_info();
   long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
   const int grid = (int)(blocks < dv.sms * 6 ? blocks : dv.sms * 6);
-  DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL><<<grid, RW_THREADS, 16 * VPL * 32 * sizeof(float), st>>>(
-                      (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
-                      dbeta, rows, C)));
+  if (C <= 1536) {
+    // warp-private column partials: 8 warps x 16 x NV floats (<= 96 KB) needs the dynamic-smem opt-in
+    DISPATCH_VPL(C, {
+      auto kern = layernorm_bwd_kernel<VPL, 1>;
+      const size_t sh = (size_t)RW_WARPS * 16 * VPL * 32 * sizeof(float);
+      static bool done = false;
+      if (!done) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); done = true; }
+      kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
+                                         dx_ld, dgamma, dbeta, rows, C);
+    });
+  } else {
+    DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL, 0><<<grid, RW_THREADS, 16 * VPL * 32 * sizeof(float), st>>>(
+                        (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
+                        dbeta, rows, C)));
+  }
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -911,6 +926,7 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
   {  // dZ2 = (dY * W2c) .* gelu'(Z2)            [R, Dc];  W2c [C, Dc] is the MN-major B operand
     vmlp_gemm_args g = gemm_args((int)R, Dc, C, 1, opnd(dy, R, C, C, 0, 0), opnd(p->w2c, C, Dc, Dc, 0, 1), VMLP_EPI_DGELU);
     g.D = dZ; g.d_ld = Dc; g.aux = s->z2; g.aux_ld = Dc;
+    g.red_out = g_b1c; g.red_mode = 1;            // db1c = column sums of dZ2, fused into the epilogue
     if ((rc = gemm_impl(g, st))) return rc;
   }
   {  // dW2c [C, Dc] += dY^T * H2     (contraction over the R token rows: both operands MN-major)
@@ -929,7 +945,6 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     g.out_f32 = g_w1c; g.out_ld = C;
     if ((rc = gemm_impl(g, st))) return rc;
   }
-  if ((rc = vmlp_colsum(dZ, Dc, nullptr, 0, g_b1c, R, Dc, stream))) return rc;
   // dU = dY + LN2'(dXhat2)
   if ((rc = vmlp_layernorm_bwd(dXh, C, s->u, C, mean2, rstd2, p->ln2_w, dy, C, dU, C, g_ln2w, g_ln2b, R, C, stream))) return rc;
 
@@ -944,6 +959,7 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(p->w2t, N, Ds, Ds, 0, 1), opnd(dU, N, C, C, (long long)N * C, 1), VMLP_EPI_DGELU);
     g.D = dZ; g.d_ld = C; g.d_bs = (long long)Ds * C;
     g.aux = s->z1; g.aux_ld = C; g.aux_bs = (long long)Ds * C;
+    g.red_out = g_b1t; g.red_mode = 2;            // db1t[m] = sum over (batch, channels) of dZ1: per output row
     if ((rc = gemm_impl(g, st))) return rc;
   }
   {  // dW2t [N, Ds] += sum_b dU[b] [N, C] * H1[b]^T [C, Ds]    (contraction over batch and channels)
@@ -962,7 +978,6 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     g.contract_batch = 1; g.out_f32 = g_w1t; g.out_ld = N;
     if ((rc = gemm_impl(g, st))) return rc;
   }
-  if ((rc = vmlp_rowsum_batched(dZ, g_b1t, B, Ds, C, stream))) return rc;
   // dX = dU + LN1'(dXhat1)
   if ((rc = vmlp_layernorm_bwd(dXh, C, x, C, mean1, rstd1, p->ln1_w, dU, C, dx, C, g_ln1w, g_ln1b, R, C, stream))) return rc;
   return VMLP_OK;

@@ -62,6 +62,8 @@ struct GemmParams {
   float* out_f32;                 // EPI_ATOMIC destination
   long long out_ld;
   int l2_prefetch;                // producer also L2-prefetches the next tile's operand boxes
+  float* red_out;                 // optional fp32 accumulator of the bf16-rounded D: per column (red_mode 1) or per row (2)
+  int red_mode;                   //   = bias gradient of the layer whose d(pre-activation) this GEMM produces
   __nv_bfloat16* d2;              // second output of the *_DUAL / GELU epilogues (direct stores)
   long long d2_ld, d2_bs;
 };
@@ -418,6 +420,39 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+        }
+        if (p.red_mode != 0) {
+          // bias gradient fused into the epilogue: sums of the (bf16-rounded) values this GEMM stores
+          float rv[16];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool ok = row_ok && (cols + 2 * e < p.N);
+            rv[2 * e] = ok ? bf16lo(o[e]) : 0.f;
+            rv[2 * e + 1] = ok ? bf16hi(o[e]) : 0.f;
+          }
+          if (p.red_mode == 2) {
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rs += rv[j];
+            if (row_ok) red_add_f32(p.red_out + grow, rs);          // token mixing: bias index = output row
+          } else {
+            // channel mixing: bias index = output column.  Butterfly transpose-reduce over the warp's 32 rows:
+            // after the 4 halving steps lane l holds column ((l >> 1) & 15)'s sum over 16 rows, one more step pairs them.
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1) {
+              const bool upper = (lane & (w * 2)) != 0;
+#pragma unroll
+              for (int j = 0; j < w; ++j) {
+                const float send = upper ? rv[j] : rv[j + w];
+                const float keep = upper ? rv[j + w] : rv[j];
+                rv[j] = keep + __shfl_xor_sync(0xffffffffu, send, w * 2);
+              }
+            }
+            rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
+            // lane bits (4,3,2,1) select which column survived: bit set => upper half at that step
+            const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0 && cols + cidx < p.N) red_add_f32(p.red_out + cols + cidx, rv[0]);
+          }
         }
         // staging tile = [32 rows][64 B]; 16-byte chunk c of row r lives at c ^ ((r >> 1) & 3) (matches SWIZZLE_64B)
         const uint32_t srow = lane * 64;

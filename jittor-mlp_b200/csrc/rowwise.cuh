@@ -106,20 +106,23 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, const 
 // HBM-bound (3 reads + 1 write per element): rows stay packed (bf16) in registers so that 3-4 blocks fit per
 // SM and enough loads are in flight; the per-column partials of a block live in shared memory
 // ([e][vector] layout => conflict-free red.shared) and are flushed with one global red.add per column.
-template <int VPL>
+// PRIV = 1: every warp owns a private [2][8][NV] fp32 slice of shared memory and updates it with plain ld/add/st
+// (conflict-free, no atomic-unit serialisation); PRIV = 0 (rows longer than 1536): one slice per block, red.shared.
+template <int VPL, int PRIV>
 __global__ void __launch_bounds__(RW_THREADS, (VPL <= 4) ? 3 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, const __nv_bfloat16* __restrict__ x,
                      long long x_ld, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ add,
                      long long add_ld, __nv_bfloat16* __restrict__ dx, long long dx_ld,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
-  extern __shared__ float sh[];           // [2][8][NV]  (NV = VPL * 32 vectors)
+  extern __shared__ float sh[];           // [PRIV ? warps : 1][2][8][NV]  (NV = VPL * 32 vectors)
   constexpr int NV = VPL * 32;
-  float* sh_g = sh;
-  float* sh_b = sh + 8 * NV;
+  constexpr int SLICES = PRIV ? RW_WARPS : 1;
+  float* sh_g = sh + (PRIV ? (threadIdx.x >> 5) * 16 * NV : 0);
+  float* sh_b = sh_g + 8 * NV;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  for (int i = threadIdx.x; i < 16 * NV; i += RW_THREADS) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < SLICES * 16 * NV; i += RW_THREADS) sh[i] = 0.f;
   __syncthreads();
   const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * RW_WARPS;
@@ -149,8 +152,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
           const float g = d[e] * gm[e];
           s1 += g;
           s2 += g * xh;
-          atomicAdd(&sh_g[e * NV + vi], d[e] * xh);
-          atomicAdd(&sh_b[e * NV + vi], d[e]);
+          if (PRIV) {
+            sh_g[e * NV + vi] += d[e] * xh;
+            sh_b[e * NV + vi] += d[e];
+          } else {
+            atomicAdd(&sh_g[e * NV + vi], d[e] * xh);
+            atomicAdd(&sh_b[e * NV + vi], d[e]);
+          }
         }
       }
     }
@@ -179,8 +187,14 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
   __syncthreads();
   for (int i = threadIdx.x; i < nvec * 8; i += RW_THREADS) {
     const int vi = i >> 3, e = i & 7;
-    red_add_f32(dgamma + i, sh_g[e * NV + vi]);
-    red_add_f32(dbeta + i, sh_b[e * NV + vi]);
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int w = 0; w < SLICES; ++w) {
+      sg += sh[w * 16 * NV + e * NV + vi];
+      sb += sh[w * 16 * NV + 8 * NV + e * NV + vi];
+    }
+    red_add_f32(dgamma + i, sg);
+    red_add_f32(dbeta + i, sb);
   }
 }
 

@@ -122,11 +122,15 @@ class MlpFn(torch.autograd.Function):
         x2, w1m, w2m, dy2 = _rows(x), _w2d(w1), _w2d(w2), _rows(dy)
         R, Ci, Dh, Co = x2.shape[0], x2.shape[1], w1m.shape[0], w2m.shape[0]
         dz = _new(R, Dh, like=x)
-        gemm(R, Dh, Co, operand(dy2, 0), operand(w2m, 1), L.EPI_DGELU, D=dz, aux=z)
+        f1 = _f32(Dh * Ci + (Dh if hb1 else 0), x.device)      # dW1 | db1 (db1 comes out of the dgrad epilogue)
+        gemm(R, Dh, Co, operand(dy2, 0), operand(w2m, 1), L.EPI_DGELU, D=dz, aux=z,
+             red_out=(f1[Dh * Ci:] if hb1 else None), red_mode=1)
         gw2, gb2 = _param_grads(dy2, h, w2, w2.new_empty(Co) if hb2 else None)
         dx = torch.empty_like(x)
         gemm(R, Ci, Dh, operand(dz, 0), operand(w1m, 1), L.EPI_STORE, D=_rows(dx))
-        gw1, gb1 = _param_grads(dz, x2, w1, w1.new_empty(Dh) if hb1 else None)
+        gemm(Dh, Ci, R, operand(dz, 1), operand(x2, 1), L.EPI_ATOMIC, out_f32=f1[:Dh * Ci].view(Dh, Ci))
+        g1 = cast_f32_to_bf16(f1)
+        gw1, gb1 = g1[:Dh * Ci].view(w1.shape), (g1[Dh * Ci:] if hb1 else None)
         return dx, gw1, gb1, gw2, gb2, (dy if hres else None)
 
 

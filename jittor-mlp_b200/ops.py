@@ -39,7 +39,7 @@ def operand(t, major, batched=None):
 
 
 def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=None, D2=None, bias=None,
-         bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0, cta_group=0):
+         bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0, cta_group=0, red_out=None, red_mode=0):
     """Generic fused GEMM, see vmlp_gemm_bf16 in include/vmlp_b200.h.  A/B are L.Operand."""
     g = L.GemmArgs()
     g.M, g.N, g.K, g.batch, g.contract_batch = M, N, K, batch, int(contract_batch)
@@ -63,6 +63,9 @@ def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=N
         _chk(out_f32, "out_f32", torch.float32)
         g.out_f32, g.out_ld = out_f32.data_ptr(), out_f32.stride(0)
     g.split_k, g.block_n, g.cta_group = split_k, block_n, cta_group
+    if red_out is not None:
+        _chk(red_out, "red_out", torch.float32)
+        g.red_out, g.red_mode = red_out.data_ptr(), red_mode
     L.check(L.lib().vmlp_gemm_bf16(ctypes.byref(g), L.stream_ptr()))
 
 

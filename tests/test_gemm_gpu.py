@@ -186,3 +186,26 @@ def test_cta_pair_epilogues_and_split_k():
         out = torch.zeros(Dout, Din, dtype=torch.float32, device=DEV)
         ops.gemm(Dout, Din, R, ops.operand(dY, 1), ops.operand(X, 1), L.EPI_ATOMIC, out_f32=out, split_k=sk, cta_group=2)
         assert rel(out, dY.float().t() @ X.float()) < 2e-3
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_fused_bias_gradient_reductions(cg):
+    """red_mode 1/2: column / row sums of the stored (bf16) output, accumulated in fp32 by the epilogue."""
+    M, N, K = 1000, 520, 256
+    A, Af = make_operand(M, K, 0, 0, 1)
+    B, Bf = make_operand(N, K, 0, 0, 2)
+    aux = rnd(M, N, seed=5)
+    for mode in (1, 2):
+        D = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        red = torch.zeros(N if mode == 1 else M, dtype=torch.float32, device=DEV)
+        ops.gemm(M, N, K, ops.operand(A, 0), ops.operand(B, 0), L.EPI_DGELU, D=D, aux=aux, red_out=red, red_mode=mode, cta_group=cg)
+        assert rel(D, (Af @ Bf.t()) * aux.float()) < 5e-3
+        assert rel(red, D.float().sum(0 if mode == 1 else 1)) < 1e-4      # exact sums of what was stored
+    # batched (token-mixing shape): rows summed over batch and columns
+    Bn, Nt, C, Ds = 3, 40, 64, 136
+    W = rnd(Nt, Ds, seed=7)
+    dU, G = rnd(Bn, Nt, C, seed=8), rnd(Bn, Ds, C, seed=9)
+    dZ = torch.zeros(Bn, Ds, C, dtype=torch.bfloat16, device=DEV)
+    red = torch.zeros(Ds, dtype=torch.float32, device=DEV)
+    ops.gemm(Ds, C, Nt, ops.operand(W, 1), ops.operand(dU, 1), L.EPI_DGELU, batch=Bn, D=dZ, aux=G, red_out=red, red_mode=2, cta_group=1)
+    assert rel(red, dZ.float().sum((0, 2))) < 1e-4
