@@ -226,6 +226,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   if (needs_aux) {
     if (!g.aux) return fail(VMLP_EINVAL, "epilogue %d needs aux", epi);
     if (!aligned16(g.aux) || (g.aux_ld % 8) || (g.aux_bs % 8)) return fail(VMLP_EALIGN, "aux alignment");
+    if (g.batch > 1 && !g.contract_batch && g.aux_bs == 0) return fail(VMLP_EINVAL, "batched output needs a batched aux operand");
   } else {
     p.aux = nullptr;
   }
@@ -243,6 +244,11 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
     if (!g.D) return fail(VMLP_EINVAL, "null output");
     rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);   // per-warp store box: 32 cols x 32 rows
     if (rc) return rc;
+    if (needs_aux && !epi_is_dual(epi)) {
+      // single-output aux epilogues: the aux operand is fetched by TMA (32 x 32 boxes); its map rides in the D2 slot
+      rc = make_map(&td2, g.aux, g.N, g.M, (g.aux_bs != 0 ? p.batch : 1), g.aux_ld, g.aux_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
     if (epi_is_dual(epi)) {
       if (!g.D2) return fail(VMLP_EINVAL, "dual-output epilogue needs D2");
       rc = make_map(&td2, g.D2, g.N, g.M, p.batch, g.d2_ld, g.d2_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);

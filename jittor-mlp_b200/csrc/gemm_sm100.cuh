@@ -74,17 +74,21 @@ struct GemmParams {
 template <int BN, int EPI, int CG = 1>
 struct GemmSmem {
   static constexpr bool DUAL = (EPI == EPI_GELU || EPI == EPI_RESID_DUAL || EPI == EPI_MUL_DUAL);
+  // single-output epilogues with an aux operand fetch it by TMA into a second staging buffer and transform it in place
+  static constexpr bool TMA_AUX = (EPI == EPI_RESID || EPI == EPI_DGELU || EPI == EPI_MUL);
+  static constexpr bool TWO_BUF = DUAL || TMA_AUX;
   // dual-output epilogues need a second staging buffer per warp; they are epilogue-bound, so fewer stages are enough
   // the main loop is TMA-latency bound (refill latency ~2800 cycles vs 512 cycles of MMA per stage): every byte of shared
   // memory not needed by the epilogue staging goes to pipeline stages
-  static constexpr int STAGES = (CG == 2) ? (DUAL ? 5 : (EPI == EPI_ATOMIC) ? 7 : 6) : (DUAL ? 3 : 4);
+  static constexpr int STAGES = (CG == 2) ? (TWO_BUF ? 5 : (EPI == EPI_ATOMIC) ? 7 : 6) : (TWO_BUF ? 3 : 4);
   static constexpr int STAGE_B_BYTES = (BN / CG) * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_STAGE_A_BYTES + STAGE_B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STAGING_OFF = PIPE_BYTES;
-  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * GEMM_WARP_STAGING * (DUAL ? 2 : 1);
+  static constexpr int STAGING_BYTES = (EPI == EPI_ATOMIC) ? 0 : GEMM_EPI_WARPS * GEMM_WARP_STAGING * (TWO_BUF ? 2 : 1);
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + slack for 1024B alignment
+  static constexpr int AUX_BAR_OFF = BAR_OFF + 192;    // 2 per epilogue warp (TMA_AUX only)
+  static constexpr int TOTAL = BAR_OFF + 512 + 1024;   // barriers + slack for 1024B alignment
 };
 
 struct TileCoord {
@@ -115,6 +119,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int NCHUNK = BN / 64;
   constexpr bool HAS_AUX = (epi_is_resid(EPI) || EPI == EPI_DGELU || epi_is_mul(EPI));
   constexpr bool DUAL = epi_is_dual(EPI);
+  constexpr bool TMA_AUX = L::TMA_AUX;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + L::STAGING_OFF;
@@ -123,6 +128,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_bar_base = reinterpret_cast<uint64_t*>(smem + L::AUX_BAR_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -131,7 +137,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
-    if (DUAL) tma_prefetch_desc(&tmD2);
+    if (DUAL || TMA_AUX) tma_prefetch_desc(&tmD2);   // second output, or (TMA_AUX) the aux operand's map
+    if (TMA_AUX)
+      for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(&aux_bar_base[i], 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -284,8 +292,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int c = ew >> 2;                  // 64-column chunk owned by this warp
     const bool has_chunk = c < NCHUNK;
     const int row = q * 32 + lane;          // accumulator row owned by this thread
-    uint8_t* st0 = staging + ew * GEMM_WARP_STAGING * (DUAL ? 2 : 1);
+    uint8_t* st0 = staging + ew * GEMM_WARP_STAGING * (L::TWO_BUF ? 2 : 1);
     uint8_t* st1 = st0 + GEMM_WARP_STAGING;
+    uint64_t* aux_bar = aux_bar_base + ew * 2;
     const bool store_lane = elect_one_sync() != 0;   // this lane owns the warp's TMA-store bulk groups for the whole kernel
 
     // ---- auxiliary-operand prefetch (registers): 16 columns of this thread's row = 2 x 16 B, one step ahead
@@ -293,7 +302,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     auto load_aux = [&](int tile, int step, uint4 (&dst)[2]) {
       dst[0] = make_uint4(0, 0, 0, 0);
       dst[1] = make_uint4(0, 0, 0, 0);
-      if (!HAS_AUX || !has_chunk || tile >= total_tiles) return;
+      if (!HAS_AUX || TMA_AUX || !has_chunk || tile >= total_tiles) return;
       const TileCoord t = decode_tile<BN, CG>(p, tile, cta_rank);
       const int grow = t.m0 + row;
       const int col = t.n0 + c * 64 + step * 16;
@@ -302,7 +311,24 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (col < p.N) dst[0] = ldg_v4(src);
       if (col + 8 < p.N) dst[1] = ldg_v4(src + 8);
     };
-    if (HAS_AUX) load_aux(cluster_id, 0, aux_nxt);
+    if (HAS_AUX && !TMA_AUX) load_aux(cluster_id, 0, aux_nxt);
+    // ---- TMA path: the aux sub-chunk (32 rows x 32 cols) of this warp's NEXT work item lands in the idle staging buffer
+    auto chunk_is_live = [&](int tile) {
+      return has_chunk && (decode_tile<BN, CG>(p, tile, cta_rank).n0 + c * 64 < p.N);
+    };
+    auto next_live_tile = [&](int tile) {
+      while (tile < total_tiles && !chunk_is_live(tile)) tile += num_clusters;
+      return tile;
+    };
+    auto issue_aux = [&](int tile, int half, uint32_t subidx) {
+      if (tile >= total_tiles || !store_lane) return;
+      const TileCoord t = decode_tile<BN, CG>(p, tile, cta_rank);
+      const uint32_t b = subidx & 1;
+      mbar_arrive_expect_tx(&aux_bar[b], GEMM_WARP_STAGING);
+      tma_load_3d(st0 + b * GEMM_WARP_STAGING, &tmD2, &aux_bar[b], t.n0 + c * 64 + half * 32, t.m0 + q * 32, t.b_idx);
+    };
+    uint32_t sub = 0;                      // sub-chunks done by this warp: selects buffer (sub & 1) and barrier parity
+    if (TMA_AUX) issue_aux(next_live_tile(cluster_id), 0, 0);
 
     int tcnt = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tcnt) {
@@ -319,16 +345,21 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int st = 0; st < 4; ++st) {
         uint4 aux_cur[2];
-        if (HAS_AUX) {
+        if (HAS_AUX && !TMA_AUX) {
           aux_cur[0] = aux_nxt[0];
           aux_cur[1] = aux_nxt[1];
           if (st < 3) load_aux(tile, st + 1, aux_nxt);
           else load_aux(tile + num_clusters, 0, aux_nxt);
         }
+        uint8_t* bufp = st0 + (TMA_AUX ? (sub & 1) * GEMM_WARP_STAGING : 0);   // staging buffer of this sub-chunk
         if (chunk_live && EPI != EPI_ATOMIC && (st & 1) == 0) {
-          // the 2 KB staging buffer(s) must have been drained by the previous 32-column TMA store of this warp
-          if (store_lane) tma_store_wait_read<0>();
-          __syncwarp();
+          if (TMA_AUX) {
+            mbar_wait(&aux_bar[sub & 1], (sub >> 1) & 1);       // aux sub-chunk has landed in bufp
+          } else {
+            // the 2 KB staging buffer(s) must have been drained by the previous 32-column TMA store of this warp
+            if (store_lane) tma_store_wait_read<0>();
+            __syncwarp();
+          }
         }
         uint32_t v[16];
         if (chunk_live) {
@@ -392,6 +423,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
         }
         if (HAS_AUX) {
+          if (TMA_AUX) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              aux_cur[g] = ld_shared_v4(smem_u32(bufp) + lane * 64 + ((((st & 1) * 2 + g) ^ ((lane >> 1) & 3)) * 16));
+          }
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const uint32_t w[4] = {aux_cur[g].x, aux_cur[g].y, aux_cur[g].z, aux_cur[g].w};
@@ -459,7 +495,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int chunk = ((st & 1) * 2 + g) ^ ((lane >> 1) & 3);
-          st_shared_v4(smem_u32(st0) + srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
+          st_shared_v4(smem_u32(bufp) + srow + chunk * 16, make_uint4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]));
           if (DUAL)
             st_shared_v4(smem_u32(st1) + srow + chunk * 16,
                          make_uint4(o2[g * 4], o2[g * 4 + 1], o2[g * 4 + 2], o2[g * 4 + 3]));
@@ -471,10 +507,18 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (store_lane) {
             const int colh = col0 + (st >> 1) * 32;
             if (colh < p.N) {
-              tma_store_3d(&tmD, st0, colh, tc.m0 + q * 32, tc.b_idx);
+              tma_store_3d(&tmD, bufp, colh, tc.m0 + q * 32, tc.b_idx);
               if (DUAL) tma_store_3d(&tmD2, st1, colh, tc.m0 + q * 32, tc.b_idx);
             }
             tma_store_commit();
+            // TMA_AUX: the OTHER buffer's store is the previous bulk group -> once it is drained, refill it with the aux
+            // operand of this warp's next sub-chunk (second half of this chunk, or first half of the next live tile)
+            if (TMA_AUX) tma_store_wait_read<1>();
+          }
+          if (TMA_AUX) {
+            if (st == 1) issue_aux(tile, 1, sub + 1);
+            else issue_aux(next_live_tile(tile + num_clusters), 0, sub + 1);
+            ++sub;
           }
         }
       }
