@@ -244,7 +244,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
     if (!g.D) return fail(VMLP_EINVAL, "null output");
     rc = make_map(&td, g.D, g.N, g.M, p.batch, g.d_ld, g.d_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);   // per-warp store box: 32 cols x 32 rows
     if (rc) return rc;
-    if (needs_aux && !epi_is_dual(epi)) {
+    if (epi == EPI_DGELU || epi == EPI_MUL) {
       // single-output aux epilogues: the aux operand is fetched by TMA (32 x 32 boxes); its map rides in the D2 slot
       rc = make_map(&td2, g.aux, g.N, g.M, (g.aux_bs != 0 ? p.batch : 1), g.aux_ld, g.aux_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;

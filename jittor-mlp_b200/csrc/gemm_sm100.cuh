@@ -75,7 +75,8 @@ template <int BN, int EPI, int CG = 1>
 struct GemmSmem {
   static constexpr bool DUAL = (EPI == EPI_GELU || EPI == EPI_RESID_DUAL || EPI == EPI_MUL_DUAL);
   // single-output epilogues with an aux operand fetch it by TMA into a second staging buffer and transform it in place
-  static constexpr bool TMA_AUX = (EPI == EPI_RESID || EPI == EPI_DGELU || EPI == EPI_MUL);
+  // (where the aux tensor is as large as the output; the small residual of EPI_RESID keeps the register path and a 4th/6th stage)
+  static constexpr bool TMA_AUX = (EPI == EPI_DGELU || EPI == EPI_MUL);
   static constexpr bool TWO_BUF = DUAL || TMA_AUX;
   // dual-output epilogues need a second staging buffer per warp; they are epilogue-bound, so fewer stages are enough
   // the main loop is TMA-latency bound (refill latency ~2800 cycles vs 512 cycles of MMA per stage): every byte of shared
