@@ -456,6 +456,14 @@ int vmlp_pad_rows(const void* src, void* dst, int32_t rows, int32_t cols, int32_
   ++g_launches;
   return VMLP_OK;
 }
+// grid for kernels that put the batch on blockIdx.y and walk a per-sample vector index with an int grid-stride loop
+static dim3 sample_grid(long long per_sample_vec, int B) {
+  long long gx = (per_sample_vec + RW_THREADS - 1) / RW_THREADS;
+  const long long cap = ((long long)device_info().sms * 16 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)B);
+}
 static int ew_grid(long long total_vec) {
   long long blocks = (total_vec + RW_THREADS - 1) / RW_THREADS;
   const long long cap = (long long)device_info().sms * 16;
@@ -507,11 +515,12 @@ int vmlp_shift_nhwc(const void* in, void* out, int32_t B, int32_t H, int32_t W, 
   t.ngroups = ngroups;
   for (int g = 0; g < ngroups; ++g) { t.start[g] = start[g]; t.dh[g] = dh[g]; t.dw[g] = dw[g]; }
   t.start[ngroups] = start[ngroups];
-  const long long total = (long long)B * H * W * (C / 8);
+  if ((long long)H * W * (C / 8) >= (1 << 22) || B > 65535) return fail(VMLP_EINVAL, "shift_nhwc: sample too large");
+  const dim3 grid = sample_grid((long long)H * W * (C / 8), B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (mode == 0) shift_nhwc_kernel<0><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
-  else if (mode == 1) shift_nhwc_kernel<1><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
-  else shift_nhwc_kernel<2><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
+  if (mode == 0) shift_nhwc_kernel<0><<<grid, RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
+  else if (mode == 1) shift_nhwc_kernel<1><<<grid, RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
+  else shift_nhwc_kernel<2><<<grid, RW_THREADS, 0, st>>>((cbf)in, (bf)out, B, H, W, C, t);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -539,8 +548,9 @@ int vmlp_gn_apply(const void* x, const float* acc, const void* gamma, const void
   if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta)) return fail(VMLP_EALIGN, "gn_apply alignment");
   const long long psv = P * (C / 8), total = psv * B;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (gelu) gn_apply_kernel<1><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)y, psv, C, eps, total);
-  else gn_apply_kernel<0><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)y, psv, C, eps, total);
+  if (psv >= (1 << 22) || B > 65535) return fail(VMLP_EINVAL, "gn_apply: sample too large");
+  if (gelu) gn_apply_kernel<1><<<sample_grid(psv, B), RW_THREADS, 0, st>>>((cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)y, psv, C, eps, total);
+  else gn_apply_kernel<0><<<sample_grid(psv, B), RW_THREADS, 0, st>>>((cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)y, psv, C, eps, total);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -559,7 +569,8 @@ int vmlp_gn_bwd(const void* dy, const void* x, const float* acc, const void* gam
   else gn_bwd_reduce_kernel<0><<<gn_grid(B, psv), RW_THREADS, sh, st>>>((cbf)dy, (cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)dn, acc2, dgamma, dbeta, psv, C, eps);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
-  gn_bwd_apply_kernel<<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)dn, (cbf)x, acc, acc2, (cbf)gamma, (bf)dx, psv, C, eps, total);
+  if (psv >= (1 << 22) || B > 65535) return fail(VMLP_EINVAL, "gn_bwd: sample too large");
+  gn_bwd_apply_kernel<<<sample_grid(psv, B), RW_THREADS, 0, st>>>((cbf)dn, (cbf)x, acc, acc2, (cbf)gamma, (bf)dx, psv, C, eps, total);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -636,7 +647,7 @@ int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int3
   int rc = s2v2_check(t, out, B, H, W, C);
   if (rc) return rc;
   if (!hat || !aligned16(hat)) return fail(VMLP_EALIGN, "s2v2 hat");
-  s2v2_combine_kernel<<<ew_grid((long long)B * H * W * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  s2v2_combine_kernel<<<sample_grid((long long)H * W * (C / 8), B), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)t, (cbf)hat, (bf)out, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -656,7 +667,7 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
   s2v2_softmax_bwd_kernel<<<(int)((nv + 127) / 128), 128, 0, st>>>((cbf)hat, dbar_f32, (bf)dhat, B, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
-  s2v2_dt_kernel<0><<<ew_grid((long long)B * H * W * (C / 8)), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, (bf)dt, B, H, W, C);
+  s2v2_dt_kernel<0><<<sample_grid((long long)H * W * (C / 8), B), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, (bf)dt, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -664,7 +675,7 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
 int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
   int rc = s2v2_check(da, dt, B, H, W, C);
   if (rc) return rc;
-  s2v2_dt_kernel<1><<<ew_grid((long long)B * H * W * (C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  s2v2_dt_kernel<1><<<sample_grid((long long)H * W * (C / 8), B), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)da, nullptr, (bf)dt, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -676,6 +687,7 @@ static int hire_dims(const vmlp_hire_dims* d, HireDims& o) {
   o.B = d->B; o.H = d->H; o.W = d->W; o.C = d->C;
   o.nh = d->h; o.Hp = d->H + (d->h - d->H % d->h); o.Gh = o.Hp / d->h; o.step_h = d->step_h;
   o.nw = d->w; o.Wp = d->W + (d->w - d->W % d->w); o.Gw = o.Wp / d->w; o.step_w = d->step_w;
+  if ((long long)o.Hp * o.Wp * (o.C / 8) * 2 >= (1 << 22) || o.B > 65535) return fail(VMLP_EINVAL, "hire: sample too large");
   return VMLP_OK;
 }
 int vmlp_hire_build(const void* x, void* zh, void* zw, const vmlp_hire_dims* d, vmlp_stream_t stream) {
@@ -685,10 +697,10 @@ int vmlp_hire_build(const void* x, void* zh, void* zw, const vmlp_hire_dims* d, 
   if (!x || !zh || !zw || !aligned16(x) || !aligned16(zh) || !aligned16(zw)) return fail(VMLP_EALIGN, "hire_build pointers");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long nv = hd.C / 8;
-  hire_build_kernel<0><<<ew_grid((long long)hd.B * hd.Gh * hd.W * hd.nh * nv), RW_THREADS, 0, st>>>((cbf)x, (bf)zh, hd);
+  hire_build_kernel<0><<<sample_grid((long long)hd.Gh * hd.W * hd.nh * nv, hd.B), RW_THREADS, 0, st>>>((cbf)x, (bf)zh, hd);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
-  hire_build_kernel<1><<<ew_grid((long long)hd.B * hd.H * hd.Gw * hd.nw * nv), RW_THREADS, 0, st>>>((cbf)x, (bf)zw, hd);
+  hire_build_kernel<1><<<sample_grid((long long)hd.H * hd.Gw * hd.nw * nv, hd.B), RW_THREADS, 0, st>>>((cbf)x, (bf)zw, hd);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -698,7 +710,7 @@ int vmlp_hire_build_adj(const void* dzh, const void* dzw, void* dx, const vmlp_h
   int rc = hire_dims(d, hd);
   if (rc) return rc;
   if (!dzh || !dzw || !dx || !aligned16(dzh) || !aligned16(dzw) || !aligned16(dx)) return fail(VMLP_EALIGN, "hire_build_adj pointers");
-  hire_build_adj_kernel<<<ew_grid((long long)hd.B * hd.H * hd.W * (hd.C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  hire_build_adj_kernel<<<sample_grid((long long)hd.H * hd.W * (hd.C / 8), hd.B), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)dzh, (cbf)dzw, (bf)dx, hd);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -711,7 +723,7 @@ int vmlp_hire_combine(const void* base, const void* oh, const void* ow, void* ou
   if (rc) return rc;
   if (!base || !oh || !ow || !out || !aligned16(base) || !aligned16(oh) || !aligned16(ow) || !aligned16(out))
     return fail(VMLP_EALIGN, "hire_combine pointers");
-  hire_combine_kernel<<<ew_grid((long long)hd.B * hd.H * hd.W * (hd.C / 8)), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  hire_combine_kernel<<<sample_grid((long long)hd.H * hd.W * (hd.C / 8), hd.B), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)base, (cbf)oh, (cbf)ow, (bf)out, hd);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -724,10 +736,10 @@ int vmlp_hire_restore_adj(const void* dout, void* dzh, void* dzw, const vmlp_hir
   if (!dout || !dzh || !dzw || !aligned16(dout) || !aligned16(dzh) || !aligned16(dzw)) return fail(VMLP_EALIGN, "hire_restore_adj pointers");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long nv = hd.C / 8;
-  hire_restore_adj_kernel<0><<<ew_grid((long long)hd.B * hd.Gh * hd.W * hd.nh * nv), RW_THREADS, 0, st>>>((cbf)dout, (bf)dzh, hd);
+  hire_restore_adj_kernel<0><<<sample_grid((long long)hd.Gh * hd.W * hd.nh * nv, hd.B), RW_THREADS, 0, st>>>((cbf)dout, (bf)dzh, hd);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
-  hire_restore_adj_kernel<1><<<ew_grid((long long)hd.B * hd.H * hd.Gw * hd.nw * nv), RW_THREADS, 0, st>>>((cbf)dout, (bf)dzw, hd);
+  hire_restore_adj_kernel<1><<<sample_grid((long long)hd.H * hd.Gw * hd.nw * nv, hd.B), RW_THREADS, 0, st>>>((cbf)dout, (bf)dzw, hd);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -812,10 +824,11 @@ int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H,
                   vmlp_stream_t stream) {
   if (!src || !dst || B <= 0 || Cin <= 0 || P <= 0 || (P % 8) || (H % P) || (W % P)) return fail(VMLP_EINVAL, "patchify args");
   if (!aligned16(src) || !aligned16(dst)) return fail(VMLP_EALIGN, "patchify alignment");
-  const long long total = (long long)B * Cin * H * W / 8;
+  const long long per = (long long)Cin * H * W / 8;
+  if (per >= (1 << 22) || B > 65535) return fail(VMLP_EINVAL, "patchify: sample too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (forward) patchify_kernel<1><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)src, (bf)dst, B, Cin, H, W, P);
-  else patchify_kernel<0><<<ew_grid(total), RW_THREADS, 0, st>>>((cbf)src, (bf)dst, B, Cin, H, W, P);
+  if (forward) patchify_kernel<1><<<sample_grid(per, B), RW_THREADS, 0, st>>>((cbf)src, (bf)dst, B, Cin, H, W, P);
+  else patchify_kernel<0><<<sample_grid(per, B), RW_THREADS, 0, st>>>((cbf)src, (bf)dst, B, Cin, H, W, P);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

@@ -24,6 +24,35 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
                     pack_bf16x2(f[6], f[7]));
 }
 
+// Division-free index helpers.  A 64-bit div/mod per 16-byte vector costs ~100 instructions and turned the elementwise
+// kernels instruction-bound; FastDiv (float reciprocal + one correction, exact for 0 <= n < 2^22) and VecIter (one
+// division per THREAD, then incremental row/col updates along the grid-stride) replace them.
+struct FastDiv {
+  int d;
+  float inv;
+  __host__ __device__ explicit FastDiv(int d_) : d(d_), inv(1.0f / static_cast<float>(d_)) {}
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = __float2int_rz(static_cast<float>(n) * inv);
+    r = n - q * d;
+    if (r < 0) { r += d; --q; }
+    else if (r >= d) { r -= d; ++q; }
+  }
+};
+struct VecIter {   // walks a [rows, nvec] grid of vectors: element index = row * nvec + col
+  long long row, drow;
+  int col, dcol, nvec;
+  __device__ __forceinline__ explicit VecIter(int nvec_) : nvec(nvec_) {
+    const long long start = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    row = start / nvec; col = static_cast<int>(start % nvec);
+    drow = stride / nvec; dcol = static_cast<int>(stride % nvec);
+  }
+  __device__ __forceinline__ void next() {
+    row += drow; col += dcol;
+    if (col >= nvec) { col -= nvec; ++row; }
+  }
+};
+
 // Flush per-lane column partials (VPL vectors x 8 columns, lane-strided) of all warps of the block
 // into global fp32 with one red.add per column per block.
 template <int VPL>
@@ -204,9 +233,10 @@ __global__ void __launch_bounds__(RW_THREADS)
 affine_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ alpha,
                   const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long nvec_total,
                   int nvec_row) {
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < nvec_total;
-       i += (long long)gridDim.x * RW_THREADS) {
-    const int c = static_cast<int>(i % nvec_row) * 8;
+  const long long rows = nvec_total / nvec_row;
+  for (VecIter it(nvec_row); it.row < rows; it.next()) {
+    const long long i = it.row * nvec_row + it.col;
+    const int c = it.col * 8;
     float xv[8], a[8], b[8], o[8];
     unpack8(ldg_nc_v4(x + i * 8), xv);
     unpack8(*reinterpret_cast<const uint4*>(alpha + c), a);
@@ -360,10 +390,9 @@ ew_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bfloat
           __nv_bfloat16* __restrict__ out, long long out_ld, __nv_bfloat16* __restrict__ out2, long long out2_ld,
           long long rows, int C) {
   const int nvr = C >> 3;
-  const long long total = rows * nvr;
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * RW_THREADS) {
-    const long long r = i / nvr;
-    const int col = static_cast<int>(i % nvr) * 8;
+  for (VecIter it(nvr); it.row < rows; it.next()) {
+    const long long r = it.row;
+    const int col = it.col * 8;
     float x[8], y[8], o[8];
     unpack8(ldg_nc_v4(a + r * a_ld + col), x);
     if (MODE == 0) {

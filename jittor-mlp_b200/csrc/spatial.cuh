@@ -55,14 +55,15 @@ __global__ void __launch_bounds__(RW_THREADS)
 shift_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                   const ShiftTable tab) {
   const int nvec = C >> 3;
-  const long long total = (long long)B * H * W * nvec;
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * RW_THREADS) {
-    const int c0 = static_cast<int>(i % nvec) * 8;
-    long long r = i / nvec;
-    const int w = static_cast<int>(r % W); r /= W;
-    const int h = static_cast<int>(r % H);
-    const long long b = r / H;
-    const long long img = b * (long long)H * W * C;
+  const FastDiv dv(nvec), dw_(W);
+  const long long b = blockIdx.y;
+  const long long img = b * (long long)H * W * C;
+  const int per_img = H * W * nvec;
+  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < per_img; i += gridDim.x * RW_THREADS) {
+    int pos, cv, h, w;
+    dv.divmod(i, pos, cv);
+    dw_.divmod(pos, h, w);
+    const int c0 = cv * 8;
     const int g0 = shift_group(tab, c0), g1 = shift_group(tab, c0 + 7);
     float o[8];
     bool done = false;
@@ -132,12 +133,17 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ a
                 const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                 __nv_bfloat16* __restrict__ y, long long per_sample_vec, int C, float eps, long long total_vec) {
   const int nvec = C >> 3;
+  const FastDiv dv(nvec);
   const float n = static_cast<float>(per_sample_vec * 8);
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total_vec; i += (long long)gridDim.x * RW_THREADS) {
-    const long long b = i / per_sample_vec;
-    const int c0 = static_cast<int>(i % nvec) * 8;
-    float mean, rstd;
-    gn_mean_rstd(acc, b, n, eps, mean, rstd);
+  const long long b = blockIdx.y;
+  float mean, rstd;
+  gn_mean_rstd(acc, b, n, eps, mean, rstd);
+  (void)total_vec;
+  for (int j = blockIdx.x * RW_THREADS + threadIdx.x; j < per_sample_vec; j += gridDim.x * RW_THREADS) {
+    int pos, cv;
+    dv.divmod(j, pos, cv);
+    const int c0 = cv * 8;
+    const long long i = b * per_sample_vec + j;
     float v[8], g[8], bt[8], o[8];
     unpack8(ldg_nc_v4(x + i * 8), v);
     unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
@@ -170,9 +176,11 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   gn_mean_rstd(acc, b, n, eps, mean, rstd);
   const long long base = b * per_sample_vec;
   float s1 = 0.f, s2 = 0.f;
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < per_sample_vec;
-       i += (long long)gridDim.x * RW_THREADS) {
-    const int c0 = static_cast<int>(i % nvec) * 8;
+  const FastDiv dv(nvec);
+  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < per_sample_vec; i += gridDim.x * RW_THREADS) {
+    int pos, cv;
+    dv.divmod(i, pos, cv);
+    const int c0 = cv * 8;
     float d[8], v[8], g[8], bt[8], o[8];
     unpack8(ldg_nc_v4(dy + (base + i) * 8), d);
     unpack8(ldg_nc_v4(x + (base + i) * 8), v);
@@ -216,13 +224,18 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dn, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ dx, long long per_sample_vec,
                     int C, float eps, long long total_vec) {
   const int nvec = C >> 3;
+  const FastDiv dv(nvec);
   const float n = static_cast<float>(per_sample_vec * 8);
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total_vec; i += (long long)gridDim.x * RW_THREADS) {
-    const long long b = i / per_sample_vec;
-    const int c0 = static_cast<int>(i % nvec) * 8;
-    float mean, rstd;
-    gn_mean_rstd(acc, b, n, eps, mean, rstd);
-    const float m1 = acc2[2 * b] / n, m2 = acc2[2 * b + 1] / n;
+  const long long b = blockIdx.y;
+  float mean, rstd;
+  gn_mean_rstd(acc, b, n, eps, mean, rstd);
+  const float m1 = acc2[2 * b] / n, m2 = acc2[2 * b + 1] / n;
+  (void)total_vec;
+  for (int j = blockIdx.x * RW_THREADS + threadIdx.x; j < per_sample_vec; j += gridDim.x * RW_THREADS) {
+    int pos, cv;
+    dv.divmod(j, pos, cv);
+    const int c0 = cv * 8;
+    const long long i = b * per_sample_vec + j;
     float d[8], v[8], g[8], o[8];
     unpack8(ldg_nc_v4(dn + i * 8), d);
     unpack8(ldg_nc_v4(x + i * 8), v);
@@ -433,13 +446,14 @@ __global__ void __launch_bounds__(RW_THREADS)
 s2v2_combine_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ hat,
                     __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
   const int nvec = C >> 3;
-  const long long total = (long long)B * H * W * nvec;
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * RW_THREADS) {
-    const int c0 = static_cast<int>(i % nvec) * 8;
-    long long r = i / nvec;
-    const int w = static_cast<int>(r % W); r /= W;
-    const int h = static_cast<int>(r % H);
-    const long long b = r / H;
+  const FastDiv dv(nvec), dw_(W);
+  const long long b = blockIdx.y;
+  (void)B;
+  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < H * W * nvec; i += gridDim.x * RW_THREADS) {
+    int pos, cv, h, w;
+    dv.divmod(i, pos, cv);
+    dw_.divmod(pos, h, w);
+    const int c0 = cv * 8;
     float bar[3][8], o[8];
     s2_softmax3(hat, b, c0, C, bar);
 #pragma unroll
@@ -482,13 +496,14 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
                __nv_bfloat16* __restrict__ dt, int B, int H, int W, int C) {
   const int nvec = C >> 3;
   const int qs = C >> 2;
-  const long long total = (long long)B * H * W * nvec;
-  for (long long i = (long long)blockIdx.x * RW_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * RW_THREADS) {
-    const int c0 = static_cast<int>(i % nvec) * 8;
-    long long r = i / nvec;
-    const int w = static_cast<int>(r % W); r /= W;
-    const int h = static_cast<int>(r % H);
-    const long long b = r / H;
+  const FastDiv dv(nvec), dw_(W);
+  const long long b = blockIdx.y;
+  (void)B;
+  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < H * W * nvec; i += gridDim.x * RW_THREADS) {
+    int pos, cv, h, w;
+    dv.divmod(i, pos, cv);
+    dw_.divmod(pos, h, w);
+    const int c0 = cv * 8;
     float bar[3][8];
     if (MODE == 0) s2_softmax3(hat, b, c0, C, bar);
     float dav[8];

@@ -28,23 +28,18 @@ hire_build_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
   const int nvec = d.C >> 3;
   const int n = DIR ? d.nw : d.nh, G = DIR ? d.Gw : d.Gh;
   const int L = DIR ? d.H : d.W;
-  const long long total = (long long)d.B * G * L * n * nvec;
-  for (long long idx = (long long)blockIdx.x * RW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * RW_THREADS) {
-    long long t = idx;
-    const int c0 = static_cast<int>(t % nvec) * 8; t /= nvec;
-    const int i = static_cast<int>(t % n); t /= n;
+  const int per = G * L * n * nvec;                 // vectors per sample (batch on blockIdx.y, division-free decode)
+  const FastDiv dv(nvec), dn(n), dl(DIR ? G : d.W);
+  const long long b = blockIdx.y;
+  for (int idx = blockIdx.x * RW_THREADS + threadIdx.x; idx < per; idx += gridDim.x * RW_THREADS) {
+    int t, cv, t2, i, hi, lo;
+    dv.divmod(idx, t, cv);
+    dn.divmod(t, t2, i);
+    dl.divmod(t2, hi, lo);
     int r, w;
-    if (DIR == 0) {
-      w = static_cast<int>(t % d.W); t /= d.W;
-      const int g = static_cast<int>(t % G); t /= G;
-      r = pmod(i * G + g - d.step_h, d.Hp) % d.H;
-    } else {
-      const int g = static_cast<int>(t % G); t /= G;
-      r = static_cast<int>(t % d.H); t /= d.H;
-      w = pmod(i * G + g - d.step_w, d.Wp) % d.W;
-    }
-    const long long b = t;
-    *reinterpret_cast<uint4*>(z + idx * 8) = ldg_nc_v4(x + ((b * d.H + r) * d.W + w) * d.C + c0);
+    if (DIR == 0) { w = lo; r = pmod(i * G + hi - d.step_h, d.Hp) % d.H; }        // t2 = g * W + w
+    else { r = hi; w = pmod(i * G + lo - d.step_w, d.Wp) % d.W; }                 // t2 = r * G + g
+    *reinterpret_cast<uint4*>(z + (b * per + idx) * 8) = ldg_nc_v4(x + ((b * d.H + r) * d.W + w) * d.C + cv * 8);
   }
 }
 // adjoint of both builds: dx[b, r, w, c] = sum over padded copies of r of dZh[...] + sum over copies of w of dZw[...]
@@ -52,13 +47,15 @@ __global__ void __launch_bounds__(RW_THREADS)
 hire_build_adj_kernel(const __nv_bfloat16* __restrict__ dzh, const __nv_bfloat16* __restrict__ dzw,
                       __nv_bfloat16* __restrict__ dx, const HireDims d) {
   const int nvec = d.C >> 3;
-  const long long total = (long long)d.B * d.H * d.W * nvec;
-  for (long long idx = (long long)blockIdx.x * RW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * RW_THREADS) {
-    long long t = idx;
-    const int c0 = static_cast<int>(t % nvec) * 8; t /= nvec;
-    const int w = static_cast<int>(t % d.W); t /= d.W;
-    const int r = static_cast<int>(t % d.H);
-    const long long b = t / d.H;
+  const int per = d.H * d.W * nvec;
+  const FastDiv dv(nvec), dw_(d.W);
+  const long long b = blockIdx.y;
+  for (int i0 = blockIdx.x * RW_THREADS + threadIdx.x; i0 < per; i0 += gridDim.x * RW_THREADS) {
+    int pos, cv, r, w;
+    dv.divmod(i0, pos, cv);
+    dw_.divmod(pos, r, w);
+    const int c0 = cv * 8;
+    const long long idx = b * per + i0;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -87,13 +84,15 @@ __global__ void __launch_bounds__(RW_THREADS)
 hire_combine_kernel(const __nv_bfloat16* __restrict__ base, const __nv_bfloat16* __restrict__ oh,
                     const __nv_bfloat16* __restrict__ ow, __nv_bfloat16* __restrict__ out, const HireDims d) {
   const int nvec = d.C >> 3;
-  const long long total = (long long)d.B * d.H * d.W * nvec;
-  for (long long idx = (long long)blockIdx.x * RW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * RW_THREADS) {
-    long long t = idx;
-    const int c0 = static_cast<int>(t % nvec) * 8; t /= nvec;
-    const int w = static_cast<int>(t % d.W); t /= d.W;
-    const int r = static_cast<int>(t % d.H);
-    const long long b = t / d.H;
+  const int per = d.H * d.W * nvec;
+  const FastDiv dv(nvec), dw_(d.W);
+  const long long b = blockIdx.y;
+  for (int i0 = blockIdx.x * RW_THREADS + threadIdx.x; i0 < per; i0 += gridDim.x * RW_THREADS) {
+    int pos, cv, r, w;
+    dv.divmod(i0, pos, cv);
+    dw_.divmod(pos, r, w);
+    const int c0 = cv * 8;
+    const long long idx = b * per + i0;
     float a[8], v[8];
     unpack8(ldg_nc_v4(base + idx * 8), a);
     const int rr = pmod(r + d.step_h, d.Hp);
@@ -114,28 +113,21 @@ hire_restore_adj_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* _
   const int nvec = d.C >> 3;
   const int n = DIR ? d.nw : d.nh, G = DIR ? d.Gw : d.Gh;
   const int L = DIR ? d.H : d.W;
-  const long long total = (long long)d.B * G * L * n * nvec;
-  for (long long idx = (long long)blockIdx.x * RW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * RW_THREADS) {
-    long long t = idx;
-    const int c0 = static_cast<int>(t % nvec) * 8; t /= nvec;
-    const int i = static_cast<int>(t % n); t /= n;
+  const int per = G * L * n * nvec;
+  const FastDiv dv(nvec), dn(n), dl(DIR ? G : d.W);
+  const long long b = blockIdx.y;
+  for (int idx = blockIdx.x * RW_THREADS + threadIdx.x; idx < per; idx += gridDim.x * RW_THREADS) {
+    int t, cv, t2, i, hi, lo;
+    dv.divmod(idx, t, cv);
+    dn.divmod(t, t2, i);
+    dl.divmod(t2, hi, lo);
     int r, w;
     bool live;
-    if (DIR == 0) {
-      w = static_cast<int>(t % d.W); t /= d.W;
-      const int g = static_cast<int>(t % G); t /= G;
-      r = pmod(i * G + g - d.step_h, d.Hp);
-      live = r < d.H;
-    } else {
-      const int g = static_cast<int>(t % G); t /= G;
-      r = static_cast<int>(t % d.H); t /= d.H;
-      w = pmod(i * G + g - d.step_w, d.Wp);
-      live = w < d.W;
-    }
-    const long long b = t;
+    if (DIR == 0) { w = lo; r = pmod(i * G + hi - d.step_h, d.Hp); live = r < d.H; }
+    else { r = hi; w = pmod(i * G + lo - d.step_w, d.Wp); live = w < d.W; }
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (live) v = ldg_nc_v4(dout + ((b * d.H + r) * d.W + w) * d.C + c0);
-    *reinterpret_cast<uint4*>(dz + idx * 8) = v;
+    if (live) v = ldg_nc_v4(dout + ((b * d.H + r) * d.W + w) * d.C + cv * 8);
+    *reinterpret_cast<uint4*>(dz + (b * per + idx) * 8) = v;
   }
 }
 
@@ -311,15 +303,17 @@ template <int FWD>
 __global__ void __launch_bounds__(RW_THREADS)
 patchify_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int Cin, int H, int W, int P) {
   const int nph = H / P, npw = W / P, vp = P / 8;
-  const long long total = (long long)B * nph * npw * Cin * P * vp;
-  for (long long idx = (long long)blockIdx.x * RW_THREADS + threadIdx.x; idx < total; idx += (long long)gridDim.x * RW_THREADS) {
-    long long t = idx;
-    const int jv = static_cast<int>(t % vp); t /= vp;
-    const int i = static_cast<int>(t % P); t /= P;
-    const int ci = static_cast<int>(t % Cin); t /= Cin;
-    const int pw = static_cast<int>(t % npw); t /= npw;
-    const int ph = static_cast<int>(t % nph);
-    const long long b = t / nph;
+  const int per = nph * npw * Cin * P * vp;
+  const FastDiv d1(vp), d2(P), d3(Cin), d4(npw);
+  const long long b = blockIdx.y;
+  (void)B;
+  for (int i0 = blockIdx.x * RW_THREADS + threadIdx.x; i0 < per; i0 += gridDim.x * RW_THREADS) {
+    int t, jv, t2, i, t3, ci, ph, pw;
+    d1.divmod(i0, t, jv);
+    d2.divmod(t, t2, i);
+    d3.divmod(t2, t3, ci);
+    d4.divmod(t3, ph, pw);
+    const long long idx = b * per + i0;
     const long long xoff = ((b * Cin + ci) * H + ph * P + i) * W + pw * P + jv * 8;
     if (FWD) *reinterpret_cast<uint4*>(dst + idx * 8) = ldg_nc_v4(src + xoff);
     else *reinterpret_cast<uint4*>(dst + xoff) = ldg_nc_v4(src + idx * 8);
