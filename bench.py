@@ -37,6 +37,10 @@ PRESETS = {
     "convmixer_768_32": ("ConvMixer", dict(dim=768, depth=32, kernel_size=7, patch_size=7), None, 41.24, 0.2312),
 }
 METRIC = "images/sec fwd+bwd MLP-Mixer-B/16 224px"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of tools/one_block.py (B/16 shapes, batch 256):
+# profiles/r01_ncu_full_mixer_block_gemms_v3_summary.csv.  Algorithmic bytes of the wgrad: 77.1 + 308.3 MB in, 9.4 MB out.
+NCU_TRAFFIC_BYTES = {"chan_wgrad": 398.7e6, "chan_dgrad1": 376.2e6, "chan_fc2_resid": 460.6e6, "chan_fc1_gelu": 640.5e6,
+                     "chan_dgrad2_dgelu": 663.9e6}
 
 
 def peaks():
@@ -171,6 +175,26 @@ def kernel_rooflines(B, N, C, Ds, Dc, pk):
         res[k] = {"ms": round(t * 1e3, 4), "tflops": round(flops / t / 1e12, 1),
                   "frac_of_sustained_peak": round(flops / t / 1e12 / pk["bf16_tflops_sustained"], 3)}
     return res
+
+
+def eager_torch_images_per_s(model, x_dev, steps=5, warm=2):
+    """Library baseline: the SAME module tree and weights run through stock ATen ops in bf16
+    (cuDNN Conv2d stem, cuDNN/cuBLAS Conv1d + Linear, native LayerNorm / GELU), unfused, eager -- exactly what
+    models_pytorch/mlp_mixer.py:12-13,19-25,67-76 executes on this GPU.  MLP-Mixer family only."""
+    def fwd(x):
+        p = model.patcher(x)
+        b, c = p.shape[0], p.shape[1]
+        t = p.permute(0, 2, 3, 1).reshape(b, -1, c)
+        for blk in model.model:
+            for half in (blk[0], blk[1]):
+                t = half.fn.net(half.norm(t)) + t
+        return model.mlp_head(model.active(t).mean(dim=1))
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss_fn(fwd(x_dev)).backward()
+    t = timed_steps(step, steps, warm, lambda: None)
+    return x_dev.shape[0] * steps / t
 
 
 def cpu_port_images_per_s(name, batch, iters, warm=1):
@@ -329,12 +353,19 @@ def main():
         flops = ks[dom]["tflops"] * ks[dom]["ms"] * 1e9
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_sm100 " + dom, "achieved": ks[dom]["tflops"],
                             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                            "frac": round(ks[dom]["tflops"] / pk["bf16_tflops_sustained"], 3), "traffic": None,
+                            "frac": round(ks[dom]["tflops"] / pk["bf16_tflops_sustained"], 3),
+                            "traffic": NCU_TRAFFIC_BYTES.get(dom.split("<")[0]),
                             "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed in a back-to-back loop)",
                             "algorithmic_flops_per_launch": flops}
         line["kernels"] = ks
         blk_ms = sum(v["ms"] * (2 if "wgrad" in k else 1) for k, v in ks.items())
         line["block_gemm_ms"] = round(blk_ms, 3)
+    if rank == 0 and world == 1 and args.model.startswith("mixer") and not args.no_kernels:
+        try:
+            line["eager_torch_bf16"] = {"value": round(eager_torch_images_per_s(model, x_dev), 1), "unit": "images/s",
+                                        "what": "same modules/weights through stock ATen (cuDNN/cuBLAS) ops, unfused, same GPU"}
+        except Exception as e:
+            line["eager_torch_bf16"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ips, secs = cpu_port_images_per_s(args.model, 16, 2)
         line["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",

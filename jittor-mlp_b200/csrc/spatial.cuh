@@ -74,8 +74,9 @@ shift_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
       if (MODE == 0) inside = (hs >= 0 && hs < H && ws >= 0 && ws < W);
       else { hs = min(max(hs, 0), H - 1); ws = min(max(ws, 0), W - 1); }
       if (inside) {
+        // L1-allocating load: neighbouring positions re-read the other half of each 32-byte sector (group width 40 B)
         *reinterpret_cast<uint4*>(out + img + ((long long)h * W + w) * C + c0) =
-            ldg_nc_v4(in + img + ((long long)hs * W + ws) * C + c0);
+            ldg_v4(in + img + ((long long)hs * W + ws) * C + c0);
       } else {
         *reinterpret_cast<uint4*>(out + img + ((long long)h * W + w) * C + c0) = make_uint4(0, 0, 0, 0);
       }
