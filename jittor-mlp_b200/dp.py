@@ -25,6 +25,12 @@ class DataParallel(torch.nn.Module):
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         # NCCL averages in the collective; gloo (CPU tests of this host logic) has no AVG: sum, then scale
         self._nccl = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
+        import os
+        # "overlap": each block's bucket is reduced on NCCL's stream while the backward of earlier blocks runs;
+        # "end": all buckets are reduced back-to-back after backward (the GEMMs are persistent 1-CTA/SM kernels with a
+        # static tile schedule, so an SM borrowed by a NCCL CTA stretches the whole GEMM; VMLP_DP_MODE picks)
+        self.mode = os.environ.get("VMLP_DP_MODE", "overlap")
+        self._deferred = []
         self._pending = []      # (work handle, flat bucket tensor)
         self._bucketed = set()  # data_ptrs already covered by an in-flight bucket
         if self.world > 1:
@@ -38,6 +44,9 @@ class DataParallel(torch.nn.Module):
     def reduce_bucket_async(self, flat):
         if self.world == 1:
             return
+        if self.mode == "end":          # exchange after the whole backward: no SM contention with the persistent GEMMs
+            self._deferred.append(flat)
+            return
         work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM, group=self.group,
                                async_op=True)
         self._pending.append((work, flat))
@@ -46,6 +55,7 @@ class DataParallel(torch.nn.Module):
         global _active
         _active = self
         self._pending.clear()
+        self._deferred.clear()
         return self
 
     def __exit__(self, *exc):
@@ -57,6 +67,11 @@ class DataParallel(torch.nn.Module):
         """Reduce what the block buckets did not cover, then join the communication stream."""
         if self.world == 1:
             return
+        for flat in self._deferred:
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM, group=self.group,
+                                   async_op=True)
+            self._pending.append((work, flat))
+        self._deferred.clear()
         covered = []
         for _, flat in self._pending:
             covered.append((flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()))
