@@ -13,7 +13,8 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libvmlp_b200.so")
+# VMLP_LIB_PATH: development knob for A/B-timing two builds of the same C ABI on one GPU box
+LIB_PATH = os.environ.get("VMLP_LIB_PATH") or os.path.join(_HERE, "libvmlp_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(_ROOT, "include")
 

@@ -216,10 +216,6 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   p.red_out = g.red_out;
   p.red_mode = g.red_out ? g.red_mode : 0;
   if (p.red_mode < 0 || p.red_mode > 2 || (p.red_mode && epi == EPI_ATOMIC)) return fail(VMLP_EINVAL, "bad red_mode");
-  {
-    static const int pf = getenv("VMLP_L2_PREFETCH") ? atoi(getenv("VMLP_L2_PREFETCH")) : 0;
-    p.l2_prefetch = pf;
-  }
   if (p.bias_mode == 1 && !aligned16(g.bias)) return fail(VMLP_EALIGN, "bias must be 16-byte aligned");
   if (p.colscale && !aligned16(p.colscale)) return fail(VMLP_EALIGN, "colscale must be 16-byte aligned");
   const bool needs_aux = (epi_is_resid(epi) || epi == EPI_DGELU || epi_is_mul(epi));
@@ -257,6 +253,10 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   }
   p.split_k = split;
   const long long total = (long long)base_tiles * split;
+  if (total >= (1ll << 22)) return fail(VMLP_EINVAL, "%lld output tiles exceed the 2^22 limit of the tile decode", total);
+  p.inv_tiles_n = 1.0f / (float)p.tiles_n;
+  p.inv_tiles_m = 1.0f / (float)p.tiles_m;
+  p.inv_batch = 1.0f / (float)p.batch;
   const long long clusters = dv.sms / cg;
   const int grid = (int)(total < clusters ? total : clusters) * cg;
   if (cg == 2) return launch_gemm_bn<256, 2>(epi, ta, tb, td, td2, p, grid, st);

@@ -61,12 +61,21 @@ struct GemmParams {
   long long aux_ld, aux_bs;       // row stride, batch stride (elements)
   float* out_f32;                 // EPI_ATOMIC destination
   long long out_ld;
-  int l2_prefetch;                // producer also L2-prefetches the next tile's operand boxes
   float* red_out;                 // optional fp32 accumulator of the bf16-rounded D: per column (red_mode 1) or per row (2)
   int red_mode;                   //   = bias gradient of the layer whose d(pre-activation) this GEMM produces
   __nv_bfloat16* d2;              // second output of the *_DUAL / GELU epilogues (direct stores)
   long long d2_ld, d2_bs;
+  float inv_tiles_n, inv_tiles_m, inv_batch;   // reciprocals for the division-free tile decode (host checks tiles < 2^22)
 };
+
+// q = n / d, r = n % d for 0 <= n < 2^22 through the float reciprocal and one correction step (a hardware integer
+// division is ~40 instructions; decode_tile runs up to five times per tile per epilogue warp).
+__device__ __forceinline__ void fast_divmod(int n, int d, float inv, int& q, int& r) {
+  q = __float2int_rz(static_cast<float>(n) * inv);
+  r = n - q * d;
+  if (r < 0) { r += d; --q; }
+  else if (r >= d) { r -= d; ++q; }
+}
 
 // CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) owns a 256 x BN tile;
 // each CTA stages its own 128 rows of A and HALF of the B tile, so the per-SM L2->SMEM traffic per MMA drops by a
@@ -99,11 +108,12 @@ struct TileCoord {
 template <int BN, int CG>
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int cta_rank) {
   TileCoord c;
-  int t = tile;
-  c.n0 = (t % p.tiles_n) * BN; t /= p.tiles_n;
-  c.m0 = (t % p.tiles_m) * (GEMM_BM * CG) + cta_rank * GEMM_BM; t /= p.tiles_m;
-  c.b_idx = t % p.batch;
-  c.s_idx = t / p.batch;
+  int t, ni, mi;
+  fast_divmod(tile, p.tiles_n, p.inv_tiles_n, t, ni);
+  fast_divmod(t, p.tiles_m, p.inv_tiles_m, t, mi);
+  fast_divmod(t, p.batch, p.inv_batch, c.s_idx, c.b_idx);
+  c.n0 = ni * BN;
+  c.m0 = mi * (GEMM_BM * CG) + cta_rank * GEMM_BM;
   return c;
 }
 
@@ -168,70 +178,51 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ===================================================================== TMA producer
     // The whole warp walks the pipeline (warp-uniform control flow); one elected lane issues the TMA instructions.
-    {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const TileCoord tc = decode_tile<BN, CG>(p, tile, cta_rank);
-        const int kb0 = tc.s_idx * kb_per_split;
-        const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
-        const int nb0 = tc.n0 + cta_rank * (BN / CG);      // this CTA's slice of the B tile
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (elect_one_sync()) {
+    // The loop body is kept to a few dozen instructions: this warp shares its scheduler with four epilogue warps, and
+    // with the previous body (two integer divisions + descriptor rebuilds per k-block, ~130 instructions at IPC ~0.2)
+    // it needed more cycles per k-block than the 512 the MMAs of that k-block take (ncu, GELU GEMM: 1165 cycles).
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t fb_local = smem_u32(full_bar);
+    const uint32_t fb_sig = (CG == 2) ? leader_cta_addr(fb_local) : fb_local;   // where the TMA bytes are signalled
+    const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
+    const int a_bmask = p.a_batched ? -1 : 0, b_bmask = p.b_batched ? -1 : 0;
+    uint32_t stage = 0, phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const TileCoord tc = decode_tile<BN, CG>(p, tile, cta_rank);
+      const int kb0 = tc.s_idx * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
+      const int nb0 = tc.n0 + cta_rank * (BN / CG);      // this CTA's slice of the B tile
+      // running K coordinates: kin = k-block inside its group of kpb blocks, kbat = batch element the group belongs to
+      int kbat = tc.b_idx, kin = kb0;
+      if (p.kbatch) { kbat = kb0 / p.kpb; kin = kb0 - kbat * p.kpb; }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
+          const uint32_t sa = sbase + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
+          const uint32_t bar = fb_sig + stage * 8;
           // CG = 2: both CTAs' TMA loads complete_tx on the LEADER's full barrier, which expects both stages' bytes
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES * CG);
-          const int kc = (kb % p.kpb) * GEMM_BK;
-          const int kbatch = p.kbatch ? (kb / p.kpb) : tc.b_idx;
-          const int ba = p.a_batched ? kbatch : 0;
-          const int bb = p.b_batched ? kbatch : 0;
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          uint8_t* sb = sa + GEMM_STAGE_A_BYTES;
-          auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2) {
-            if (CG == 2) tma_load_3d_2cta(dst, m, &full_bar[stage], c0, c1, c2);
-            else tma_load_3d(dst, m, &full_bar[stage], c0, c1, c2);
-          };
+          if (is_leader) mbar_arrive_expect_tx_u32(fb_local + stage * 8, L::STAGE_BYTES * CG);
+          const int kc = kin * GEMM_BK;
+          const int ba = kbat & a_bmask, bb = kbat & b_bmask;
           if (!p.a_mn) {
-            load(sa, &tmA, kc, tc.m0, ba);                            // box (64 k, 128 m)
+            tma_load_3d_u32<CG>(sa, mapA, bar, kc, tc.m0, ba);                            // box (64 k, 128 m)
           } else {
 #pragma unroll
-            for (int a = 0; a < GEMM_BM / 64; ++a)                    // box (64 m, 64 k) per MN atom
-              load(sa + a * (GEMM_BK * 128), &tmA, tc.m0 + a * 64, kc, ba);
+            for (int a = 0; a < GEMM_BM / 64; ++a)                                        // box (64 m, 64 k) per MN atom
+              tma_load_3d_u32<CG>(sa + a * (GEMM_BK * 128), mapA, bar, tc.m0 + a * 64, kc, ba);
           }
           if (!p.b_mn) {
-            load(sb, &tmB, kc, nb0, bb);                              // box (64 k, BN / CG n)
+            tma_load_3d_u32<CG>(sb, mapB, bar, kc, nb0, bb);                              // box (64 k, BN / CG n)
           } else {
 #pragma unroll
             for (int a = 0; a < BN / CG / 64; ++a)
-              load(sb + a * (GEMM_BK * 128), &tmB, nb0 + a * 64, kc, bb);
+              tma_load_3d_u32<CG>(sb + a * (GEMM_BK * 128), mapB, bar, nb0 + a * 64, kc, bb);
           }
-            // L2 prefetch of the SAME k-block of this CTA's NEXT tile (one whole tile of lookahead beyond the SMEM ring)
-            const int ntile = tile + num_clusters;
-            if (p.l2_prefetch && ntile < total_tiles) {
-              const TileCoord nt = decode_tile<BN, CG>(p, ntile, cta_rank);
-              if (nt.s_idx == tc.s_idx) {
-                const int nbatch = p.kbatch ? (kb / p.kpb) : nt.b_idx;
-                const int nba = p.a_batched ? nbatch : 0, nbb = p.b_batched ? nbatch : 0;
-                const int nnb0 = nt.n0 + cta_rank * (BN / CG);
-                if (nt.m0 != tc.m0 || nba != ba) {
-                  if (!p.a_mn) tma_prefetch_l2_3d(&tmA, kc, nt.m0, nba);
-                  else {
-#pragma unroll
-                    for (int a = 0; a < GEMM_BM / 64; ++a) tma_prefetch_l2_3d(&tmA, nt.m0 + a * 64, kc, nba);
-                  }
-                }
-                if (nnb0 != nb0 || nbb != bb) {
-                  if (!p.b_mn) tma_prefetch_l2_3d(&tmB, kc, nnb0, nbb);
-                  else {
-#pragma unroll
-                    for (int a = 0; a < BN / CG / 64; ++a) tma_prefetch_l2_3d(&tmB, nnb0 + a * 64, kc, nbb);
-                  }
-                }
-              }
-            }
-          }   // elected lane
-          __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+        }   // elected lane
+        __syncwarp();
+        if (++kin == p.kpb) { kin = 0; ++kbat; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -239,16 +230,22 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // Whole warp, warp-uniform control flow; one elected lane issues the MMAs and commits.
     if (is_leader) {
       const uint32_t idesc = umma_idesc_bf16(GEMM_BM * CG, BN, p.a_mn, p.b_mn);
+      // Shared-memory descriptors (umma_smem_desc_sw128): the high word is a constant, the low word is
+      // (address >> 4) | (LBO >> 4) << 16, so stepping a stage or a k-step is one integer add on the low word.
       // K-major : 8-row groups 1024 B apart (SBO); one 128B swizzle atom along K (LBO unused).
       // MN-major: 8-k groups 1024 B apart (SBO); 64-wide MN atoms BK*128 B apart (LBO).
-      const uint32_t a_lbo = p.a_mn ? GEMM_BK * 128 : 0, b_lbo = p.b_mn ? GEMM_BK * 128 : 0;
-      const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t sbase = smem_u32(smem);
+      const uint32_t a_lo0 = (sbase >> 4) | ((p.a_mn ? (GEMM_BK * 128u) >> 4 : 0u) << 16);
+      const uint32_t b_lo0 = ((sbase + GEMM_STAGE_A_BYTES) >> 4) | ((p.b_mn ? (GEMM_BK * 128u) >> 4 : 0u) << 16);
+      const uint32_t a_kinc = (p.a_mn ? 16u * 128u : 32u) >> 4, b_kinc = (p.b_mn ? 16u * 128u : 32u) >> 4;
       uint32_t stage = 0, phase = 0;
       int tc = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++tc) {
-        const int s_idx = tile / tiles_per_split;
+        const int s_idx = decode_tile<BN, CG>(p, tile, 0).s_idx;
         const int kb0 = s_idx * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
+        int kin = p.kbatch ? (kb0 % p.kpb) : kb0;
         const int as = tc & 1;
         mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -256,28 +253,25 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t b_base = a_base + GEMM_STAGE_A_BYTES;
-          const int ksteps = ((kb % p.kpb) == p.kpb - 1) ? p.last_ksteps : (GEMM_BK / 16);
+          const uint32_t a_lo = a_lo0 + stage * (L::STAGE_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (L::STAGE_BYTES >> 4);
+          const int ksteps = (kin == p.kpb - 1) ? p.last_ksteps : (GEMM_BK / 16);
           if (elect_one_sync()) {
+            umma_bf16_lo<CG>(d_tmem, a_lo, b_lo, DESC_HI, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            if (k >= ksteps) break;
-            const uint64_t adesc = umma_smem_desc_sw128(a_base + k * a_kstep, a_lbo, 1024);
-            const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * b_kstep, b_lbo, 1024);
-            if (CG == 2) umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
-          // frees the smem slot (in both CTAs for CG = 2) when these MMAs retire; last k-block: accumulator complete
-          if (CG == 2) {
-            umma_commit_2cta_mc(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit_2cta_mc(&tmem_full[as]);
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
-          }
+            for (int k = 1; k < GEMM_BK / 16; ++k)
+              if (k < ksteps) umma_bf16_lo<CG>(d_tmem, a_lo + k * a_kinc, b_lo + k * b_kinc, DESC_HI, idesc, 1u);
+            // frees the smem slot (in both CTAs for CG = 2) when these MMAs retire; last k-block: accumulator complete
+            if (CG == 2) {
+              umma_commit_2cta_mc(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit_2cta_mc(&tmem_full[as]);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (kb == kb1 - 1) umma_commit(&tmem_full[as]);
+            }
           }   // elected lane
           __syncwarp();
+          if (++kin == p.kpb) kin = 0;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -314,9 +308,12 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     };
     if (HAS_AUX && !TMA_AUX) load_aux(cluster_id, 0, aux_nxt);
     // ---- TMA path: the aux sub-chunk (32 rows x 32 cols) of this warp's NEXT work item lands in the idle staging buffer
-    auto chunk_is_live = [&](int tile) {
-      return has_chunk && (decode_tile<BN, CG>(p, tile, cta_rank).n0 + c * 64 < p.N);
+    // a work item (this warp's 32 rows x 64 columns of a tile) is dead when it lies entirely outside the output: ragged N
+    // (columns) or ragged M (token GEMMs: M = 784 = 6.125 tiles -> three of the last tile's four row quarters are padding)
+    auto item_live = [&](const TileCoord& t) {
+      return has_chunk && (t.n0 + c * 64 < p.N) && (t.m0 + q * 32 < p.M);
     };
+    auto chunk_is_live = [&](int tile) { return item_live(decode_tile<BN, CG>(p, tile, cta_rank)); };
     auto next_live_tile = [&](int tile) {
       while (tile < total_tiles && !chunk_is_live(tile)) tile += num_clusters;
       return tile;
@@ -342,7 +339,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float rbias = 0.f;
       if (p.bias_mode == 2 && row_ok) rbias = __bfloat162float(p.bias[grow]);
       const int col0 = tc.n0 + c * 64;
-      const bool chunk_live = has_chunk && (col0 < p.N);   // ragged N: dead chunks are skipped entirely
+      const bool chunk_live = item_live(tc);               // dead work items are skipped entirely
 #pragma unroll
       for (int st = 0; st < 4; ++st) {
         uint4 aux_cur[2];
@@ -442,53 +439,52 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               o[g * 4 + e] = pack_bf16x2(x0, x1);
             }
           }
-        } else if (EPI == EPI_GELU) {
+        } else if (EPI == EPI_GELU || EPI == EPI_GELU_ONLY) {
+          // packed fp32x2 path (bias add included; f[] above is dead code for these epilogues).  One erf/exp evaluation
+          // yields both gelu(z) and gelu'(z); backward then only multiplies by the saved gelu'.
+          f32x2 z[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) z[e] = pack2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+          if (p.bias_mode == 2) {
+            const f32x2 rb = pack2(rbias, rbias);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) z[e] = add2(z[e], rb);
+          } else if (p.bias_mode == 1) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              if (cols + g * 8 < p.N) {
+                const uint4 bv = *reinterpret_cast<const uint4*>(p.bias + cols + g * 8);
+                const uint32_t w[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) z[g * 4 + e] = add2(z[g * 4 + e], pack2(bf16lo(w[e]), bf16hi(w[e])));
+              }
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            // one erf/exp evaluation yields both gelu(z) and gelu'(z); backward then only multiplies by the saved gelu'
-            float d0, d1;
-            const float g0 = gelu_erf_t<true>(f[2 * e], d0), g1 = gelu_erf_t<true>(f[2 * e + 1], d1);
-            o[e] = pack_bf16x2(d0, d1);
-            o2[e] = pack_bf16x2(g0, g1);
+            f32x2 gl, dg;
+            gelu_erf_pair<EPI == EPI_GELU>(z[e], gl, dg);
+            if (EPI == EPI_GELU) {
+              o[e] = pack_bf16x2_f2(dg);
+              o2[e] = pack_bf16x2_f2(gl);
+            } else {
+              o[e] = pack_bf16x2_f2(gl);
+            }
           }
-        } else if (EPI == EPI_GELU_ONLY) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(gelu_erf(f[2 * e]), gelu_erf(f[2 * e + 1]));
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
         }
-        if (p.red_mode != 0) {
-          // bias gradient fused into the epilogue: sums of the (bf16-rounded) values this GEMM stores
-          float rv[16];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const bool ok = row_ok && (cols + 2 * e < p.N);
-            rv[2 * e] = ok ? bf16lo(o[e]) : 0.f;
-            rv[2 * e + 1] = ok ? bf16hi(o[e]) : 0.f;
-          }
-          if (p.red_mode == 2) {
+        if (p.red_mode == 2) {
+          // bias gradient fused into the epilogue (token mixing: bias index = output row): sum of the bf16-rounded values
+          // this thread stores (N is even, so validity is per bf16 pair).
+          if (row_ok) {
             float rs = 0.f;
+            const int nv = min(8, max(0, (p.N - cols) >> 1));
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rs += rv[j];
-            if (row_ok) red_add_f32(p.red_out + grow, rs);          // token mixing: bias index = output row
-          } else {
-            // channel mixing: bias index = output column.  Butterfly transpose-reduce over the warp's 32 rows:
-            // after the 4 halving steps lane l holds column ((l >> 1) & 15)'s sum over 16 rows, one more step pairs them.
-#pragma unroll
-            for (int w = 8; w >= 1; w >>= 1) {
-              const bool upper = (lane & (w * 2)) != 0;
-#pragma unroll
-              for (int j = 0; j < w; ++j) {
-                const float send = upper ? rv[j] : rv[j + w];
-                const float keep = upper ? rv[j + w] : rv[j];
-                rv[j] = keep + __shfl_xor_sync(0xffffffffu, send, w * 2);
-              }
-            }
-            rv[0] += __shfl_xor_sync(0xffffffffu, rv[0], 1);
-            // lane bits (4,3,2,1) select which column survived: bit set => upper half at that step
-            const int cidx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-            if ((lane & 1) == 0 && cols + cidx < p.N) red_add_f32(p.red_out + cols + cidx, rv[0]);
+            for (int e = 0; e < 8; ++e)
+              if (e < nv) rs += bf16lo(o[e]) + bf16hi(o[e]);
+            red_add_f32(p.red_out + grow, rs);
           }
         }
         // staging tile = [32 rows][64 B]; 16-byte chunk c of row r lives at c ^ ((r >> 1) & 3) (matches SWIZZLE_64B)
@@ -515,6 +511,37 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // TMA_AUX: the OTHER buffer's store is the previous bulk group -> once it is drained, refill it with the aux
             // operand of this warp's next sub-chunk (second half of this chunk, or first half of the next live tile)
             if (TMA_AUX) tma_store_wait_read<1>();
+          }
+          if (p.red_mode == 1) {
+            // bias gradient fused into the epilogue (channel mixing: bias index = output column).  The finished 32 x 32
+            // sub-chunk sits in the staging buffer: lane l sums column pair (l & 15) over 16 rows -- one conflict-free
+            // LDS.32 + 2 unpacks + 2 adds per row, ~3 instructions per element where the register butterfly this
+            // replaces (31 SHFL + 62 FSEL per 16 columns) cost ~10 and made the DGELU GEMMs issue-bound.
+            const int pr = lane & 15, hh = lane >> 4;
+            const int kq = pr >> 2;
+            // row r = hh * 16 + (i ^ hh): the upper half-warp walks rows of the opposite parity, i.e. the other 16 banks
+            const uint32_t base_even = smem_u32(bufp) + hh * 1024 + hh * 64 + (pr & 3) * 4;
+            const uint32_t base_odd = smem_u32(bufp) + hh * 1024 - hh * 64 + (pr & 3) * 4;
+            const uint32_t kx[4] = {uint32_t(kq) * 16, uint32_t(kq ^ 1) * 16, uint32_t(kq ^ 2) * 16, uint32_t(kq ^ 3) * 16};
+            const int nrows = min(32, p.M - (tc.m0 + q * 32));      // > 0: the work item is live
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t addr = ((i & 1) ? base_odd : base_even) + i * 64 + kx[(i >> 1) & 3];
+              uint32_t w;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr) : "memory");
+              if (nrows == 32 || hh * 16 + (i ^ hh) < nrows) {
+                s0 += bf16lo(w);
+                s1 += bf16hi(w);
+              }
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            const int colp = col0 + (st >> 1) * 32 + 2 * pr;
+            if (hh == 0 && colp < p.N) {
+              red_add_f32(p.red_out + colp, s0);
+              red_add_f32(p.red_out + colp + 1, s1);
+            }
           }
           if (TMA_AUX) {
             if (st == 1) issue_aux(tile, 1, sub + 1);

@@ -48,21 +48,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with an explicit suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of spinning -- a spinning epilogue warp costs the math warps of its scheduler their issue slots
+// (ncu: 22 % of all executed instructions of the GELU GEMM were try_wait spins before this).
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok;
 }
 // Bounded wait: a protocol bug must trap (CUDA error on the host) instead of
-// hanging the GPU box.  ~2^31 cycles is > 1 s at any B200 clock.
+// hanging the GPU box.  2^32 cycles is > 2 s at any B200 clock.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
@@ -281,6 +284,69 @@ __device__ __forceinline__ float dgelu_erf(float z) {
   return d;
 }
 
+
+// ----------------------------------------------------------------------------- packed fp32x2 math (sm_100: FFMA2 / FMUL2 / FADD2)
+// Two fp32 lanes per instruction: the GELU epilogues are issue-bound (ncu: 68 % issue-active, 23 thread instructions
+// per element), so every packed op is an issue slot saved.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_erf_t for a pair of pre-activations (same formula, same constants): the Horner steps, the products and the
+// final gelu / gelu' combine run packed; |z|, the two MUFUs and the z < 0 select stay per element.
+// 23 instructions per pair (11 packed + 4 MUFU + 8 scalar) against 36 scalar ones.
+template <bool WITH_GRAD>
+__device__ __forceinline__ void gelu_erf_pair(f32x2 z, f32x2& gelu, f32x2& dgelu) {
+  float z0, z1;
+  unpack2(z, z0, z1);
+  const float t0 = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z0), 1.0f));
+  const float t1 = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z1), 1.0f));
+  const f32x2 t = pack2(t0, t1);
+  f32x2 p = fma2(pack2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, pack2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = fma2(p, t, pack2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = fma2(p, t, pack2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = fma2(p, t, pack2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  p = mul2(p, t);
+  // exp(-z^2/2) = 2^(-(z * s)^2), s = sqrt(log2(e) / 2)
+  const f32x2 w = mul2(z, pack2(0.84932180028801907f, 0.84932180028801907f));
+  float w0, w1;
+  unpack2(mul2(w, w), w0, w1);
+  const float e0 = ex2_approx(-w0), e1 = ex2_approx(-w1);
+  const f32x2 e = pack2(e0, e1);
+  float h0, h1;
+  unpack2(mul2(p, e), h0, h1);
+  const float c0 = (z0 < 0.f) ? h0 : 1.0f - h0;
+  const float c1 = (z1 < 0.f) ? h1 : 1.0f - h1;
+  const f32x2 cdf = pack2(c0, c1);
+  gelu = mul2(z, cdf);
+  if (WITH_GRAD) dgelu = fma2(mul2(z, pack2(0.3989422804014327f, 0.3989422804014327f)), e, cdf);   // Phi(z) + z * phi(z)
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_f2(f32x2 v) {
+  float lo, hi;
+  unpack2(v, lo, hi);
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 }  // namespace vmlp
 
 // ============================================================================= cta_group::2 (CTA pair) variants
@@ -309,13 +375,16 @@ __device__ __forceinline__ void tma_load_3d_2cta(void* smem_dst, const CUtensorM
       "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_cta_addr(smem_u32(bar))), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// arrive on the mbarrier at the same offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same offset in CTA `cta` of the cluster.  No `.release.cluster`: that form compiles to
+// MEMBAR.ALL.GPU + ERRBAR in front of the arrive (8 % of the CTA-pair GELU GEMM's stall samples).  The only thing this
+// arrive publishes is "my tcgen05.ld reads of the accumulator are done", which tcgen05.wait::ld + fence::before_thread_sync
+// already order.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n"
       ".reg .b32 ra;\n"
       "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
@@ -351,6 +420,57 @@ __device__ __forceinline__ void umma_commit_2cta_mc(uint64_t* bar) {
           smem_u32(bar)),
       "h"(mask)
       : "memory");
+}
+
+// ----------------------------------------------------------------------------- lean main-loop forms
+// Address-taking variants for the producer / MMA loops: operands are plain 32-bit shared-window addresses and
+// descriptor words that the caller advances with one integer add per stage / k-step.
+__device__ __forceinline__ void mbar_arrive_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// CG = 2: `bar` is the leader CTA's barrier (leader_cta_addr), data lands in the issuing CTA's shared memory.
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_u32(uint32_t smem_dst, uint64_t map, uint32_t bar, int c0, int c1, int c2) {
+  if (CG == 2)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(smem_dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// tcgen05.mma with the two shared-memory descriptors given as (low word, shared high word).
+template <int CG>
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
 }  // namespace vmlp
