@@ -161,7 +161,11 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   // CTA-pair kernel (cta_group::2, 256 x 256 tiles) for the large un-batched GEMMs: channel-mixing fwd/dgrad/wgrad
   const bool one_output = (g.batch == 1 || g.contract_batch);
   int cg = g.cta_group;
-  if (cg == 0) cg = (bn == 256 && one_output && (g.M % 256 == 0 || g.M >= 4096) && g.M >= 512) ? 2 : 1;
+  // ... and wherever a 256-row pair tile wastes no more rows than two 128-row tiles would (M = 196 token GEMMs: measured
+  // 88 -> 80 us dgrad, 100 -> 91 us wgrad; M = 784 is 4 x 256 = 1024 vs 7 x 128 = 896 rows and stays on single CTAs)
+  const long long pad1 = (g.M + 127) / 128 * 128, pad2 = (g.M + 255) / 256 * 256;
+  if (cg == 0)
+    cg = (bn == 256 && ((one_output && (g.M % 256 == 0 || g.M >= 4096) && g.M >= 512) || (pad1 == pad2 && g.M > 128))) ? 2 : 1;
   if (const char* e = getenv("VMLP_FORCE_CTA_GROUP")) cg = atoi(e) == 2 ? ((bn == 256) ? 2 : 1) : 1;
   if (cg != 1 && cg != 2) return fail(VMLP_EINVAL, "cta_group must be 0, 1 or 2");
   if (cg == 2 && bn != 256) return fail(VMLP_EINVAL, "cta_group 2 needs block_n 256");
@@ -301,6 +305,54 @@ vmlp_gemm_args gemm_args(int M, int N, int K, int batch, vmlp_operand A, vmlp_op
   return g;
 }
 
+// LayerNorm backward (+ residual-gradient add, + dgamma / dbeta).  add_colsum / out_rowsum (both optional, C <= 1536
+// and add != null only): the Mixer block backward folds its two output-bias gradients into this pass (rowwise.cuh).
+int layernorm_bwd_impl(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const float* mean,
+                       const float* rstd, const void* gamma, const void* add, int64_t add_ld, void* dx,
+                       int64_t dx_ld, float* dgamma, float* dbeta, int64_t rows, int32_t C, float* add_colsum,
+                       float* out_rowsum, int row_period, vmlp_stream_t stream) {
+  if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || rows <= 0 || (C % 8))
+    return fail(VMLP_EINVAL, "layernorm_bwd args");
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(gamma) || (add && !aligned16(add)) ||
+      (dy_ld % 8) || (x_ld % 8) || (dx_ld % 8) || (add_ld % 8))
+    return fail(VMLP_EALIGN, "layernorm_bwd alignment");
+  const bool extra = add_colsum != nullptr || out_rowsum != nullptr;
+  if (extra && (C > 1536 || !add || row_period <= 0)) return fail(VMLP_EINVAL, "layernorm_bwd fused sums need C <= 1536 and add");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const DeviceInfo& dv = device_info();
+  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
+  const int grid = (int)(blocks < dv.sms * 6 ? blocks : dv.sms * 6);
+  if (C <= 1536) {
+    // warp-private column partials: 8 warps x 16 (24) x NV floats (<= 96 KB) needs the dynamic-smem opt-in
+    if (extra) {
+      DISPATCH_VPL(C, {
+        auto kern = layernorm_bwd_kernel<VPL, 1, 1>;
+        const size_t sh = (size_t)RW_WARPS * 24 * VPL * 32 * sizeof(float);
+        static bool done = false;
+        if (!done) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); done = true; }
+        kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
+                                           dx_ld, dgamma, dbeta, rows, C, add_colsum, out_rowsum, row_period);
+      });
+    } else {
+      DISPATCH_VPL(C, {
+        auto kern = layernorm_bwd_kernel<VPL, 1, 0>;
+        const size_t sh = (size_t)RW_WARPS * 16 * VPL * 32 * sizeof(float);
+        static bool done = false;
+        if (!done) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); done = true; }
+        kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
+                                           dx_ld, dgamma, dbeta, rows, C, nullptr, nullptr, 1);
+      });
+    }
+  } else {
+    DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL, 0, 0><<<grid, RW_THREADS, 16 * VPL * 32 * sizeof(float), st>>>(
+                        (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
+                        dbeta, rows, C, nullptr, nullptr, 1)));
+  }
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
 }  // namespace
 
 // ============================================================================================ C ABI
@@ -338,33 +390,8 @@ int vmlp_layernorm_fwd(const void* x, int64_t x_ld, const void* gamma, const voi
 int vmlp_layernorm_bwd(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, const float* mean,
                        const float* rstd, const void* gamma, const void* add, int64_t add_ld, void* dx,
                        int64_t dx_ld, float* dgamma, float* dbeta, int64_t rows, int32_t C, vmlp_stream_t stream) {
-  if (!dy || !x || !mean || !rstd || !gamma || !dx || !dgamma || !dbeta || rows <= 0 || (C % 8))
-    return fail(VMLP_EINVAL, "layernorm_bwd args");
-  if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || !aligned16(gamma) || (add && !aligned16(add)) ||
-      (dy_ld % 8) || (x_ld % 8) || (dx_ld % 8) || (add_ld % 8))
-    return fail(VMLP_EALIGN, "layernorm_bwd alignment");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const DeviceInfo& dv = device_info();
-  long long blocks = (rows + RW_WARPS - 1) / RW_WARPS;
-  const int grid = (int)(blocks < dv.sms * 6 ? blocks : dv.sms * 6);
-  if (C <= 1536) {
-    // warp-private column partials: 8 warps x 16 x NV floats (<= 96 KB) needs the dynamic-smem opt-in
-    DISPATCH_VPL(C, {
-      auto kern = layernorm_bwd_kernel<VPL, 1>;
-      const size_t sh = (size_t)RW_WARPS * 16 * VPL * 32 * sizeof(float);
-      static bool done = false;
-      if (!done) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); done = true; }
-      kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
-                                         dx_ld, dgamma, dbeta, rows, C);
-    });
-  } else {
-    DISPATCH_VPL(C, (layernorm_bwd_kernel<VPL, 0><<<grid, RW_THREADS, 16 * VPL * 32 * sizeof(float), st>>>(
-                        (cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx, dx_ld, dgamma,
-                        dbeta, rows, C)));
-  }
-  CUDA_OK(cudaGetLastError());
-  ++g_launches;
-  return VMLP_OK;
+  return layernorm_bwd_impl(dy, dy_ld, x, x_ld, mean, rstd, gamma, add, add_ld, dx, dx_ld, dgamma, dbeta, rows, C,
+                            nullptr, nullptr, 1, stream);
 }
 
 int vmlp_affine_fwd(const void* x, const void* alpha, const void* beta, void* y, int64_t rows, int32_t C,
@@ -953,7 +980,8 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     g.out_f32 = g_w2c; g.out_ld = Dc;
     if ((rc = gemm_impl(g, st))) return rc;
   }
-  if ((rc = vmlp_colsum(dy, C, nullptr, 0, g_b2c, R, C, stream))) return rc;
+  const bool fused_sums = C <= 1536;   // db2c = colsum(dY) and db2t = per-token sums of dU ride in the LN2 backward pass
+  if (!fused_sums && (rc = vmlp_colsum(dy, C, nullptr, 0, g_b2c, R, C, stream))) return rc;
   {  // dXhat2 = dZ2 * W1c                        [R, C];  W1c [Dc, C] MN-major B
     vmlp_gemm_args g = gemm_args((int)R, C, Dc, 1, opnd(dZ, R, Dc, Dc, 0, 0), opnd(p->w1c, Dc, C, C, 0, 1), VMLP_EPI_STORE);
     g.D = dXh; g.d_ld = C;
@@ -965,7 +993,8 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     if ((rc = gemm_impl(g, st))) return rc;
   }
   // dU = dY + LN2'(dXhat2)
-  if ((rc = vmlp_layernorm_bwd(dXh, C, s->u, C, mean2, rstd2, p->ln2_w, dy, C, dU, C, g_ln2w, g_ln2b, R, C, stream))) return rc;
+  if ((rc = layernorm_bwd_impl(dXh, C, s->u, C, mean2, rstd2, p->ln2_w, dy, C, dU, C, g_ln2w, g_ln2b, R, C,
+                               fused_sums ? g_b2c : nullptr, fused_sums ? g_b2t : nullptr, N, stream))) return rc;
 
   // ================= token half:  u = x + TokenFF(LN1(x))
   {
@@ -986,7 +1015,7 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds;
     if ((rc = gemm_impl(g, st))) return rc;
   }
-  if ((rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;
+  if (!fused_sums && (rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;
   {  // dXhat1[b] [N, C] = W1t^T [N, Ds] * dZ1[b] [Ds, C];  padded W1t [Ds, Np] as MN-major A
     vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(s->w1t_pad, Ds, N, Np, 0, 1), opnd(dZ, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_STORE);
     g.D = dXh; g.d_ld = C; g.d_bs = (long long)N * C;

@@ -137,21 +137,27 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, const 
 // ([e][vector] layout => conflict-free red.shared) and are flushed with one global red.add per column.
 // PRIV = 1: every warp owns a private [2][8][NV] fp32 slice of shared memory and updates it with plain ld/add/st
 // (conflict-free, no atomic-unit serialisation); PRIV = 0 (rows longer than 1536): one slice per block, red.shared.
-template <int VPL, int PRIV>
+// EXTRA = 1 (Mixer block backward, PRIV only): the same pass also produces the two bias gradients that otherwise cost a
+// pass each -- add_colsum[c] += sum_r add[r, c] (the channel-MLP output bias: `add` is the block's dY) and
+// out_rowsum[r % row_period] += sum_c dx[r, c] (the token-MLP output bias: dx is the token half's dY).
+template <int VPL, int PRIV, int EXTRA>
 __global__ void __launch_bounds__(RW_THREADS, (VPL <= 4) ? 3 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, const __nv_bfloat16* __restrict__ x,
                      long long x_ld, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ add,
                      long long add_ld, __nv_bfloat16* __restrict__ dx, long long dx_ld,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
-  extern __shared__ float sh[];           // [PRIV ? warps : 1][2][8][NV]  (NV = VPL * 32 vectors)
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C,
+                     float* __restrict__ add_colsum, float* __restrict__ out_rowsum, int row_period) {
+  extern __shared__ float sh[];           // [PRIV ? warps : 1][2 + EXTRA][8][NV]  (NV = VPL * 32 vectors)
   constexpr int NV = VPL * 32;
   constexpr int SLICES = PRIV ? RW_WARPS : 1;
-  float* sh_g = sh + (PRIV ? (threadIdx.x >> 5) * 16 * NV : 0);
+  constexpr int SL = (2 + EXTRA) * 8 * NV;      // floats per slice
+  float* sh_g = sh + (PRIV ? (threadIdx.x >> 5) * SL : 0);
   float* sh_b = sh_g + 8 * NV;
+  float* sh_a = sh_b + 8 * NV;                  // EXTRA only
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  for (int i = threadIdx.x; i < SLICES * 16 * NV; i += RW_THREADS) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < SLICES * SL; i += RW_THREADS) sh[i] = 0.f;
   __syncthreads();
   const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * RW_WARPS;
@@ -193,6 +199,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
     }
     s1 = warp_sum(s1) / C;
     s2 = warp_sum(s2) / C;
+    float osum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int vi = i * 32 + lane;
@@ -208,22 +215,32 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
         for (int e = 0; e < 8; ++e) {
           const float xh = (xv[e] - mean) * rstd;
           o[e] = a[e] + rstd * (d[e] * gm[e] - s1 - xh * s2);
+          if (EXTRA) {
+            sh_a[e * NV + vi] += a[e];
+            osum += o[e];
+          }
         }
         *reinterpret_cast<uint4*>(dx + r * dx_ld + vi * 8) = pack8(o);
       }
+    }
+    if (EXTRA && out_rowsum != nullptr) {
+      osum = warp_sum(osum);
+      if (lane == 0) red_add_f32(out_rowsum + (int)(r % row_period), osum);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nvec * 8; i += RW_THREADS) {
     const int vi = i >> 3, e = i & 7;
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, sa = 0.f;
 #pragma unroll
     for (int w = 0; w < SLICES; ++w) {
-      sg += sh[w * 16 * NV + e * NV + vi];
-      sb += sh[w * 16 * NV + 8 * NV + e * NV + vi];
+      sg += sh[w * SL + e * NV + vi];
+      sb += sh[w * SL + 8 * NV + e * NV + vi];
+      if (EXTRA) sa += sh[w * SL + 16 * NV + e * NV + vi];
     }
     red_add_f32(dgamma + i, sg);
     red_add_f32(dbeta + i, sb);
+    if (EXTRA && add_colsum != nullptr) red_add_f32(add_colsum + i, sa);
   }
 }
 
