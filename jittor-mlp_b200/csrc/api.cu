@@ -96,7 +96,7 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t rows, int64
 
 template <int BN, int EPI, int CG>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
-                  const GemmParams& p, int grid, cudaStream_t st) {
+                  const CUtensorMap& tpf, const GemmParams& p, int grid, cudaStream_t st) {
   auto kern = gemm_bf16_sm100<BN, EPI, CG>;
   using SM = GemmSmem<BN, EPI, CG>;
   static bool attr_set[64] = {};
@@ -107,7 +107,7 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr_set[dev & 63] = true;
   }
   if (CG == 1) {
-    kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ta, tb, td, td2, p);
+    kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ta, tb, td, td2, tpf, p);
   } else {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -122,7 +122,7 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, td2, p));
+    CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, td, td2, tpf, p));
   }
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -131,17 +131,17 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
 
 template <int BN, int CG>
 int launch_gemm_bn(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td,
-                   const CUtensorMap& td2, const GemmParams& p, int grid, cudaStream_t st) {
+                   const CUtensorMap& td2, const CUtensorMap& tpf, const GemmParams& p, int grid, cudaStream_t st) {
   switch (epi) {
-    case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_DGELU: return launch_gemm_t<BN, EPI_DGELU, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_ATOMIC: return launch_gemm_t<BN, EPI_ATOMIC, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_MUL: return launch_gemm_t<BN, EPI_MUL, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_GELU_ONLY: return launch_gemm_t<BN, EPI_GELU_ONLY, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_RESID_DUAL: return launch_gemm_t<BN, EPI_RESID_DUAL, CG>(ta, tb, td, td2, p, grid, st);
-    case EPI_MUL_DUAL: return launch_gemm_t<BN, EPI_MUL_DUAL, CG>(ta, tb, td, td2, p, grid, st);
+    case EPI_STORE: return launch_gemm_t<BN, EPI_STORE, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_GELU: return launch_gemm_t<BN, EPI_GELU, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_RESID: return launch_gemm_t<BN, EPI_RESID, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_DGELU: return launch_gemm_t<BN, EPI_DGELU, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_ATOMIC: return launch_gemm_t<BN, EPI_ATOMIC, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_MUL: return launch_gemm_t<BN, EPI_MUL, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_GELU_ONLY: return launch_gemm_t<BN, EPI_GELU_ONLY, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_RESID_DUAL: return launch_gemm_t<BN, EPI_RESID_DUAL, CG>(ta, tb, td, td2, tpf, p, grid, st);
+    case EPI_MUL_DUAL: return launch_gemm_t<BN, EPI_MUL_DUAL, CG>(ta, tb, td, td2, tpf, p, grid, st);
   }
   return fail(VMLP_EINVAL, "unknown epilogue %d", epi);
 }
@@ -181,9 +181,10 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   const bool a_batched = g.A.batch_stride != 0 && g.batch > 1;
   const bool b_batched = g.B.batch_stride != 0 && g.batch > 1;
 
-  CUtensorMap ta, tb, td, td2;
+  CUtensorMap ta, tb, td, td2, tpf;
   memset(&td, 0, sizeof(td));
   memset(&td2, 0, sizeof(td2));
+  memset(&tpf, 0, sizeof(tpf));
   int rc;
   // K-major: inner = K, box (64, 128 | BN).  MN-major: inner = M/N, box (64, 64) per swizzle atom.
   rc = make_map(&ta, g.A.ptr, g.A.cols, g.A.rows, a_batched ? g.batch : 1, g.A.ld, g.A.batch_stride, 64,
@@ -248,6 +249,9 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
       // single-output aux epilogues: the aux operand is fetched by TMA (32 x 32 boxes); its map rides in the D2 slot
       rc = make_map(&td2, g.aux, g.N, g.M, (g.aux_bs != 0 ? p.batch : 1), g.aux_ld, g.aux_bs, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
+      // ... and is L2-prefetched by the producer, one [128 rows x BN cols] box per CTA tile
+      rc = make_map(&tpf, g.aux, g.N, g.M, (g.aux_bs != 0 ? p.batch : 1), g.aux_ld, g.aux_bs, bn, GEMM_BM, CU_TENSOR_MAP_SWIZZLE_NONE);
+      if (rc) return rc;
     }
     if (epi_is_dual(epi)) {
       if (!g.D2) return fail(VMLP_EINVAL, "dual-output epilogue needs D2");
@@ -263,9 +267,9 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   p.inv_batch = 1.0f / (float)p.batch;
   const long long clusters = dv.sms / cg;
   const int grid = (int)(total < clusters ? total : clusters) * cg;
-  if (cg == 2) return launch_gemm_bn<256, 2>(epi, ta, tb, td, td2, p, grid, st);
-  if (bn == 256) return launch_gemm_bn<256, 1>(epi, ta, tb, td, td2, p, grid, st);
-  return launch_gemm_bn<128, 1>(epi, ta, tb, td, td2, p, grid, st);
+  if (cg == 2) return launch_gemm_bn<256, 2>(epi, ta, tb, td, td2, tpf, p, grid, st);
+  if (bn == 256) return launch_gemm_bn<256, 1>(epi, ta, tb, td, td2, tpf, p, grid, st);
+  return launch_gemm_bn<128, 1>(epi, ta, tb, td, td2, tpf, p, grid, st);
 }
 
 int rw_grid(long long rows) {
@@ -333,6 +337,17 @@ int layernorm_bwd_impl(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
         kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
                                            dx_ld, dgamma, dbeta, rows, C, add_colsum, out_rowsum, row_period);
       });
+    } else if (C <= 128) {
+      // narrow rows: 4 (C <= 64) or 2 rows per warp; same 8 x 16 x 32 floats of warp-private partials
+      const size_t sh = (size_t)RW_WARPS * 16 * 32 * sizeof(float);
+      const long long blocks2 = (rows + RW_WARPS * (C <= 64 ? 4 : 2) - 1) / (RW_WARPS * (C <= 64 ? 4 : 2));
+      const int grid2 = (int)(blocks2 < dv.sms * 6 ? blocks2 : dv.sms * 6);
+      if (C <= 64)
+        layernorm_bwd_kernel<1, 1, 0, 8><<<grid2, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld,
+                                                                      (bf)dx, dx_ld, dgamma, dbeta, rows, C, nullptr, nullptr, 1);
+      else
+        layernorm_bwd_kernel<1, 1, 0, 16><<<grid2, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld,
+                                                                       (bf)dx, dx_ld, dgamma, dbeta, rows, C, nullptr, nullptr, 1);
     } else {
       DISPATCH_VPL(C, {
         auto kern = layernorm_bwd_kernel<VPL, 1, 0>;
@@ -380,6 +395,11 @@ int vmlp_layernorm_fwd(const void* x, int64_t x_ld, const void* gamma, const voi
   if (!aligned16(x) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || (x_ld % 8) || (y_ld % 8))
     return fail(VMLP_EALIGN, "layernorm_fwd alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (C <= 64)         // narrow rows: 4 (2) rows per warp
+    layernorm_fwd_kernel<1, 8><<<rw_grid((rows + 3) / 4), RW_THREADS, 0, st>>>((cbf)x, x_ld, (cbf)gamma, (cbf)beta, (bf)y, y_ld, mean, rstd, rows, C, eps);
+  else if (C <= 128)
+    layernorm_fwd_kernel<1, 16><<<rw_grid((rows + 1) / 2), RW_THREADS, 0, st>>>((cbf)x, x_ld, (cbf)gamma, (cbf)beta, (bf)y, y_ld, mean, rstd, rows, C, eps);
+  else
   DISPATCH_VPL(C, (layernorm_fwd_kernel<VPL><<<rw_grid(rows), RW_THREADS, 0, st>>>(
                       (cbf)x, x_ld, (cbf)gamma, (cbf)beta, (bf)y, y_ld, mean, rstd, rows, C, eps)));
   CUDA_OK(cudaGetLastError());
@@ -592,6 +612,7 @@ int vmlp_gn_bwd(const void* dy, const void* x, const float* acc, const void* gam
   const long long psv = P * (C / 8), total = psv * B;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t sh = 2 * (size_t)C * sizeof(float);
+  if (C / 8 > RW_THREADS) return fail(VMLP_EINVAL, "gn_bwd: C=%d exceeds %d channels", C, 8 * RW_THREADS);
   if (gelu) gn_bwd_reduce_kernel<1><<<gn_grid(B, psv), RW_THREADS, sh, st>>>((cbf)dy, (cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)dn, acc2, dgamma, dbeta, psv, C, eps);
   else gn_bwd_reduce_kernel<0><<<gn_grid(B, psv), RW_THREADS, sh, st>>>((cbf)dy, (cbf)x, acc, (cbf)gamma, (cbf)beta, (bf)dn, acc2, dgamma, dbeta, psv, C, eps);
   CUDA_OK(cudaGetLastError());

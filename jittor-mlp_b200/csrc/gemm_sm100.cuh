@@ -121,7 +121,7 @@ template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2,
-                const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmPf, const GemmParams p) {
   using L = GemmSmem<BN, EPI, CG>;
   const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const bool is_leader = (cta_rank == 0);
@@ -149,6 +149,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     if (EPI != EPI_ATOMIC) tma_prefetch_desc(&tmD);
     if (DUAL || TMA_AUX) tma_prefetch_desc(&tmD2);   // second output, or (TMA_AUX) the aux operand's map
+    if (TMA_AUX) tma_prefetch_desc(&tmPf);           // the aux operand again, one [128 x BN] box per CTA tile (L2 prefetch)
     if (TMA_AUX)
       for (int i = 0; i < 2 * GEMM_EPI_WARPS; ++i) mbar_init(&aux_bar_base[i], 1);
     for (int s = 0; s < STAGES; ++s) {
@@ -195,6 +196,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // running K coordinates: kin = k-block inside its group of kpb blocks, kbat = batch element the group belongs to
       int kbat = tc.b_idx, kin = kb0;
       if (p.kbatch) { kbat = kb0 / p.kpb; kin = kb0 - kbat * p.kpb; }
+      // TMA_AUX epilogues stream an aux tensor as large as the output through per-warp 2 KB TMA loads that are issued only
+      // one sub-chunk ahead (all the shared memory the staging can get), i.e. with the full HBM latency exposed.  The
+      // producer is a whole tile ahead of the epilogue: one L2 prefetch of this CTA's [128 x BN] aux box per tile turns
+      // those loads into L2 hits.
+      if (TMA_AUX && elect_one_sync()) tma_prefetch_l2_3d(&tmPf, tc.n0, tc.m0, tc.b_idx);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {

@@ -15,6 +15,13 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// sum over aligned groups of G lanes (G = 8, 16, 32): narrow rows pack 32 / G rows into one warp
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
   f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
@@ -78,46 +85,55 @@ __device__ __forceinline__ void flush_col_partials(float (&acc)[VPL][8], float* 
 // --------------------------------------------------------------------------- LayerNorm forward
 // y = (x - mean) * rstd * gamma + beta over the last axis (biased variance, eps inside sqrt):
 // torch.nn.LayerNorm semantics used by PreNormResidual (models_pytorch/mlp_mixer.py:6-13).
-template <int VPL>
+// G = lanes per row.  Rows of <= 128 channels (Hire-MLP stage 0/1: C = 64 / 128) would leave 24 / 16 lanes of a
+// one-row-per-warp layout idle (measured 121 us for 205 MB, 4x off the HBM floor), so 32 / G rows share a warp.
+template <int VPL, int G = 32>
 __global__ void __launch_bounds__(RW_THREADS)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, const __nv_bfloat16* __restrict__ gamma,
                      const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, long long y_ld,
                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int C,
                      float eps) {
+  static_assert(G == 32 || VPL == 1, "row packing needs one vector per lane");
+  constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & 31;
+  const int sl = lane & (G - 1), sub = lane / G;
   const int nvec = C >> 3;
   const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * RW_WARPS;
-  for (long long r = gw; r < rows; r += nw) {
+  for (long long r0 = gw * RPW; r0 < rows; r0 += nw * RPW) {
+    const long long r = r0 + sub;
+    const bool row_ok = r < rows;
     float v[VPL][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * 32 + sl;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+      if (row_ok && vi < nvec) {
         unpack8(ldg_nc_v4(x + r * x_ld + vi * 8), v[i]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) s += v[i][e];
       }
     }
-    const float mean = warp_sum(s) / C;
+    const float mean = group_sum<G>(s) / C;
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      if (i * 32 + lane < nvec) {
+      if (i * 32 + sl < nvec) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; ss += d * d; }
       }
     }
-    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
-    if (lane == 0) {
+    const float rstd = rsqrtf(group_sum<G>(ss) / C + eps);
+    if (sl == 0 && row_ok) {
       if (mean_out) mean_out[r] = mean;
       if (rstd_out) rstd_out[r] = rstd;
     }
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * 32 + sl;
+      if (row_ok && vi < nvec) {
         float g[8], b[8], o[8];
         unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), g);
         unpack8(*reinterpret_cast<const uint4*>(beta + vi * 8), b);
@@ -140,7 +156,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ld, const 
 // EXTRA = 1 (Mixer block backward, PRIV only): the same pass also produces the two bias gradients that otherwise cost a
 // pass each -- add_colsum[c] += sum_r add[r, c] (the channel-MLP output bias: `add` is the block's dY) and
 // out_rowsum[r % row_period] += sum_c dx[r, c] (the token-MLP output bias: dx is the token half's dY).
-template <int VPL, int PRIV, int EXTRA>
+// G < 32 (PRIV only): 32 / G narrow rows per warp, one private shared-memory slice per row slot.
+template <int VPL, int PRIV, int EXTRA, int G = 32>
 __global__ void __launch_bounds__(RW_THREADS, (VPL <= 4) ? 3 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, const __nv_bfloat16* __restrict__ x,
                      long long x_ld, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -148,26 +165,34 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
                      long long add_ld, __nv_bfloat16* __restrict__ dx, long long dx_ld,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C,
                      float* __restrict__ add_colsum, float* __restrict__ out_rowsum, int row_period) {
-  extern __shared__ float sh[];           // [PRIV ? warps : 1][2 + EXTRA][8][NV]  (NV = VPL * 32 vectors)
-  constexpr int NV = VPL * 32;
-  constexpr int SLICES = PRIV ? RW_WARPS : 1;
+  static_assert(G == 32 || (VPL == 1 && PRIV == 1 && EXTRA == 0), "row packing: one vector per lane, private slices");
+  extern __shared__ float sh[];           // [PRIV ? warps * rows-per-warp : 1][2 + EXTRA][8][NV]
+  constexpr int RPW = 32 / G;
+  constexpr int NV = (G < 32) ? G : VPL * 32;
+  constexpr int SLICES = PRIV ? RW_WARPS * RPW : 1;
   constexpr int SL = (2 + EXTRA) * 8 * NV;      // floats per slice
-  float* sh_g = sh + (PRIV ? (threadIdx.x >> 5) * SL : 0);
+  const int lane = threadIdx.x & 31;
+  const int sl = lane & (G - 1), sub = lane / G;
+  float* sh_g = sh + (PRIV ? ((threadIdx.x >> 5) * RPW + sub) * SL : 0);
   float* sh_b = sh_g + 8 * NV;
   float* sh_a = sh_b + 8 * NV;                  // EXTRA only
-  const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   for (int i = threadIdx.x; i < SLICES * SL; i += RW_THREADS) sh[i] = 0.f;
   __syncthreads();
   const long long gw = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * RW_WARPS;
-  for (long long r = gw; r < rows; r += nw) {
-    const float mean = mean_in[r], rstd = rstd_in[r];
+  for (long long r0 = gw * RPW; r0 < rows; r0 += nw * RPW) {
+    const long long r = r0 + sub;
+    const bool row_ok = r < rows;
+    float mean = 0.f, rstd = 0.f;
+    if (row_ok) { mean = mean_in[r]; rstd = rstd_in[r]; }
     uint4 rd[VPL], rx[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * 32 + sl;
+      rd[i] = make_uint4(0, 0, 0, 0);
+      rx[i] = make_uint4(0, 0, 0, 0);
+      if (row_ok && vi < nvec) {
         rd[i] = ldg_nc_v4(dy + r * dy_ld + vi * 8);
         rx[i] = ldg_nc_v4(x + r * x_ld + vi * 8);
       }
@@ -175,8 +200,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * 32 + sl;
+      if (row_ok && vi < nvec) {
         float d[8], xv[8], gm[8];
         unpack8(rd[i], d);
         unpack8(rx[i], xv);
@@ -197,13 +222,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
         }
       }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
+    s1 = group_sum<G>(s1) / C;
+    s2 = group_sum<G>(s2) / C;
     float osum = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * 32 + sl;
+      if (row_ok && vi < nvec) {
         float d[8], xv[8], gm[8], o[8], a[8];
         unpack8(rd[i], d);
         unpack8(rx[i], xv);

@@ -159,7 +159,10 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ a
 }
 // backward pass A: dn = dy (* gelu'(n)),  n = xhat * gamma + beta  (recomputed from x);
 //   per sample:  acc2[b] += (sum g, sum g * xhat),  g = dn * gamma
-//   per channel: dgamma += sum dn * xhat, dbeta += sum dn      (block-local smem partials, one red.add per column)
+//   per channel: dgamma += sum dn * xhat, dbeta += sum dn
+// Thread t of a block owns channel vector (t % nvec) of position (t / nvec) and strides over positions, so its 16
+// per-channel partial sums live in registers for the whole kernel and reach shared memory once (the first version did
+// two shared-memory atomics per ELEMENT on 2C addresses: 220 us for the 308 MB of AS-MLP-T stage 0, 21 % of the step).
 template <int GELU>
 __global__ void __launch_bounds__(RW_THREADS)
 gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
@@ -168,7 +171,7 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long per_sample_vec, int C, float eps) {
   extern __shared__ float shc[];          // [2][C] column partials
   __shared__ float shs[2][RW_WARPS];
-  const int nvec = C >> 3;
+  const int nvec = C >> 3;                // host guarantees nvec <= RW_THREADS
   for (int i = threadIdx.x; i < 2 * C; i += RW_THREADS) shc[i] = 0.f;
   __syncthreads();
   const long long b = blockIdx.y;
@@ -176,30 +179,42 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
   float mean, rstd;
   gn_mean_rstd(acc, b, n, eps, mean, rstd);
   const long long base = b * per_sample_vec;
+  const int ppb = RW_THREADS / nvec;      // positions per block iteration
+  const int cv = threadIdx.x % nvec, po = threadIdx.x / nvec;
+  const bool active = po < ppb;
+  const int c0 = cv * 8;
+  const int P = static_cast<int>(per_sample_vec / nvec);
   float s1 = 0.f, s2 = 0.f;
-  const FastDiv dv(nvec);
-  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < per_sample_vec; i += gridDim.x * RW_THREADS) {
-    int pos, cv;
-    dv.divmod(i, pos, cv);
-    const int c0 = cv * 8;
-    float d[8], v[8], g[8], bt[8], o[8];
-    unpack8(ldg_nc_v4(dy + (base + i) * 8), d);
-    unpack8(ldg_nc_v4(x + (base + i) * 8), v);
-    unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
-    if (GELU) unpack8(*reinterpret_cast<const uint4*>(beta + c0), bt);
+  float ag[8], ab[8], g[8], bt[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { ag[e] = 0.f; ab[e] = 0.f; bt[e] = 0.f; }
+  unpack8(*reinterpret_cast<const uint4*>(gamma + c0), g);
+  if (GELU) unpack8(*reinterpret_cast<const uint4*>(beta + c0), bt);
+  if (active) {
+    for (int pos = blockIdx.x * ppb + po; pos < P; pos += gridDim.x * ppb) {
+      const long long i = base + (long long)pos * nvec + cv;
+      float d[8], v[8], o[8];
+      unpack8(ldg_nc_v4(dy + i * 8), d);
+      unpack8(ldg_nc_v4(x + i * 8), v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xh = (v[e] - mean) * rstd;
+        float dv = d[e];
+        if (GELU) dv *= dgelu_erf(xh * g[e] + bt[e]);
+        o[e] = dv;
+        const float gg = dv * g[e];
+        s1 += gg;
+        s2 += gg * xh;
+        ag[e] += dv * xh;
+        ab[e] += dv;
+      }
+      *reinterpret_cast<uint4*>(dn + i * 8) = pack8(o);
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float xh = (v[e] - mean) * rstd;
-      float dv = d[e];
-      if (GELU) dv *= dgelu_erf(xh * g[e] + bt[e]);
-      o[e] = dv;
-      const float gg = dv * g[e];
-      s1 += gg;
-      s2 += gg * xh;
-      atomicAdd(&shc[c0 + e], dv * xh);
-      atomicAdd(&shc[C + c0 + e], dv);
+      atomicAdd(&shc[c0 + e], ag[e]);
+      atomicAdd(&shc[C + c0 + e], ab[e]);
     }
-    *reinterpret_cast<uint4*>(dn + (base + i) * 8) = pack8(o);
   }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
@@ -335,10 +350,11 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ sdy, const float* _
 // The shifts are never materialised: every kernel below reads t at clamp(position + offset_k(channel quarter)).
 __device__ __forceinline__ void s2_plan_offset(int k, int quarter, int& dh, int& dw) {
   // `x[:,1:] = x[:,:-1]` => out[i] = in[i-1] => offset -1 (s2_mlp_v2.py:15-29)
-  const int plan1_dh[4] = {-1, 1, 0, 0}, plan1_dw[4] = {0, 0, -1, 1};
-  if (k == 0) { dh = plan1_dh[quarter]; dw = plan1_dw[quarter]; }
-  else if (k == 1) { dh = plan1_dw[quarter]; dw = plan1_dh[quarter]; }
-  else { dh = 0; dw = 0; }
+  // plan 1: quarters (0, 1) move along h by (-1, +1), quarters (2, 3) along w; plan 2 swaps the axes; k = 2 is identity
+  const int sgn = (quarter & 1) ? 1 : -1;
+  const bool on_h = ((quarter >> 1) == 0) != (k == 1);
+  dh = (k < 2 && on_h) ? sgn : 0;
+  dw = (k < 2 && !on_h) ? sgn : 0;
 }
 // value of x_k[b, h, w, c0 .. c0+7] (forward gather, clamp) as 8 floats
 __device__ __forceinline__ void s2_gather8(const __nv_bfloat16* __restrict__ t, long long img, int h, int w, int k,
@@ -360,10 +376,29 @@ __device__ __forceinline__ void s2_gather8(const __nv_bfloat16* __restrict__ t, 
     }
   }
 }
-// adjoint gather of a [B, H, W, C] field g for branch k: sum of g over the output positions that read (h, w)
+// adjoint gather of a [B, H, W, C] field g for branch k: sum of g over the output positions that read (h, w).
+// A vector that lies inside one channel quarter (always, when C/4 is a multiple of 8) costs at most two 16-byte loads:
+// the shifted neighbour and, on the clamped edge, the position itself.
 __device__ __forceinline__ void s2_adjoint8(const __nv_bfloat16* __restrict__ g, long long img, int h, int w, int k,
                                             int c0, int H, int W, int C, float (&o)[8]) {
   const int qs = C >> 2;
+  const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
+  if (q0 == q1) {
+    int dh, dw;
+    s2_plan_offset(k, q0, dh, dw);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    const int hs = h - dh, ws = w - dw;
+    if (hs >= 0 && hs < H && ws >= 0 && ws < W) unpack8(ldg_nc_v4(g + img + ((long long)hs * W + ws) * C + c0), o);
+    const bool edge = (dh < 0 && h == 0) || (dh > 0 && h == H - 1) || (dw < 0 && w == 0) || (dw > 0 && w == W - 1);
+    if (edge) {
+      float s[8];
+      unpack8(ldg_nc_v4(g + img + ((long long)h * W + w) * C + c0), s);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += s[e];
+    }
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     int dh, dw;
@@ -519,11 +554,20 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = bar[k][e] * gv[e];
       } else {
+        const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
+        if (k == 2 || q0 == q1) {
+          int dh = 0, dw = 0;
+          if (k < 2) s2_plan_offset(k, q0, dh, dw);
+          const float cnt = (k < 2) ? s2_read_count(h, w, H, W, dh, dw) : 1.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          int dh, dw;
-          s2_plan_offset(k, min((c0 + e) / qs, 3), dh, dw);
-          o[e] = dav[e] * (k < 2 ? s2_read_count(h, w, H, W, dh, dw) : 1.f);
+          for (int e = 0; e < 8; ++e) o[e] = dav[e] * cnt;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            int dh, dw;
+            s2_plan_offset(k, min((c0 + e) / qs, 3), dh, dw);
+            o[e] = dav[e] * s2_read_count(h, w, H, W, dh, dw);
+          }
         }
       }
       *reinterpret_cast<uint4*>(dt + (b * H * W + (long long)h * W + w) * 3 * C + k * C + c0) = pack8(o);

@@ -1,7 +1,7 @@
 #!/bin/bash
-# quick iteration loop: GEMM + Mixer parity, A/B of one block against the baseline build, per-kernel bench table
+# quick iteration loop: GEMM + Mixer parity, A/B of one block against a previous build, per-kernel bench table
 mkdir -p gpurun_out
-python -m pytest tests/test_gemm_gpu.py tests/test_mixer_gpu.py -x -q 2>&1 | tail -3
+python -m pytest tests/test_gemm_gpu.py tests/test_mixer_gpu.py tests/test_resmlp_gmlp_gpu.py -x -q 2>&1 | tail -3
 bash tools/ab_block.sh
 python bench.py --no-cpu-baseline --steps 10 > gpurun_out/bench_quick.log 2>/dev/null
 python - <<'PY'
