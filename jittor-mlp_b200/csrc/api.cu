@@ -450,6 +450,17 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
   if (!aligned16(a) || (a_ld % 8) || (b && (!aligned16(b) || (b_ld % 8)))) return fail(VMLP_EALIGN, "colsum alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo& dv = device_info();
+  if (a_ld == C && (!b || b_ld == C) && C <= 8 * RW_THREADS) {
+    const int rpb = RW_THREADS / (C / 8);
+    long long gx = (rows + 4LL * rpb - 1) / (4LL * rpb);
+    const long long cap = (long long)dv.sms * 8;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    colsum_flat_kernel<<<(unsigned)gx, RW_THREADS, (size_t)C * sizeof(float), st>>>((cbf)a, (cbf)b, out, rows, C);
+    CUDA_OK(cudaGetLastError());
+    ++g_launches;
+    return VMLP_OK;
+  }
   const int slabs = (C + 255) / 256;
   long long gx = (rows + RW_WARPS - 1) / RW_WARPS;
   const long long cap = (long long)(dv.sms * 8 + slabs - 1) / slabs;
@@ -676,7 +687,7 @@ static int s2v2_check(const void* a, const void* b, int B, int H, int W, int C) 
 static dim3 s2v2_reduce_grid(int B, int H, int W, int C) {
   const int plane = RW_THREADS / (C / 8);
   long long gx = ((long long)H * W + plane - 1) / plane;
-  const long long cap = ((long long)device_info().sms * 4 + B - 1) / B;
+  const long long cap = ((long long)device_info().sms * 8 + B - 1) / B;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)B);
@@ -695,7 +706,7 @@ int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int3
   int rc = s2v2_check(t, out, B, H, W, C);
   if (rc) return rc;
   if (!hat || !aligned16(hat)) return fail(VMLP_EALIGN, "s2v2 hat");
-  s2v2_combine_kernel<<<sample_grid((long long)H * W * (C / 8), B), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  s2v2_combine_kernel<<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)t, (cbf)hat, (bf)out, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -715,7 +726,7 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
   s2v2_softmax_bwd_kernel<<<(int)((nv + 127) / 128), 128, 0, st>>>((cbf)hat, dbar_f32, (bf)dhat, B, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
-  s2v2_dt_kernel<0><<<sample_grid((long long)H * W * (C / 8), B), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, (bf)dt, B, H, W, C);
+  s2v2_dt_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, (bf)dt, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -723,7 +734,7 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
 int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
   int rc = s2v2_check(da, dt, B, H, W, C);
   if (rc) return rc;
-  s2v2_dt_kernel<1><<<sample_grid((long long)H * W * (C / 8), B), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  s2v2_dt_kernel<1><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       (cbf)da, nullptr, (bf)dt, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;

@@ -371,6 +371,64 @@ colsum_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bf
   }
 }
 
+// Contiguous rows (ld == C, C <= 2048): thread t owns channel vector (t % nvec) of row slot (t / nvec), so a block streams
+// whole rows fully coalesced whatever C is (the slab kernel above keeps 20 of 32 lanes idle at C = 96) and keeps four
+// 16-byte loads per operand in flight.
+__global__ void __launch_bounds__(RW_THREADS)
+colsum_flat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float* __restrict__ out,
+                   long long rows, int C) {
+  extern __shared__ float shc[];          // [C]
+  const int nvec = C >> 3;
+  for (int i = threadIdx.x; i < C; i += RW_THREADS) shc[i] = 0.f;
+  __syncthreads();
+  const int rpb = RW_THREADS / nvec;      // rows per block iteration
+  const int cv = threadIdx.x % nvec, ro = threadIdx.x / nvec;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (ro < rpb) {
+    const long long step = (long long)gridDim.x * rpb;
+    long long r = (long long)blockIdx.x * rpb + ro;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      uint4 va[4], vb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        va[u] = ldg_nc_v4(a + ((r + u * step) * nvec + cv) * 8);
+        if (b) vb[u] = ldg_nc_v4(b + ((r + u * step) * nvec + cv) * 8);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float d[8];
+        unpack8(va[u], d);
+        if (b) {
+          float m[8];
+          unpack8(vb[u], m);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] *= m[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += d[e];
+      }
+    }
+    for (; r < rows; r += step) {
+      float d[8];
+      unpack8(ldg_nc_v4(a + (r * nvec + cv) * 8), d);
+      if (b) {
+        float m[8];
+        unpack8(ldg_nc_v4(b + (r * nvec + cv) * 8), m);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] *= m[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += d[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&shc[cv * 8 + e], acc[e]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += RW_THREADS) red_add_f32(out + i, shc[i]);
+}
+
 // --------------------------------------------------------------------------- batched row sums
 // out[m] += sum_{b, c} a[b, m, c]   (token-mixing bias gradients: reductions over B*C)
 __global__ void __launch_bounds__(RW_THREADS)

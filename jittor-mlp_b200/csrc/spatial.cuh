@@ -50,45 +50,93 @@ __device__ __forceinline__ float shift_fetch(const __nv_bfloat16* __restrict__ i
   }
 }
 
+// One source vector of channel group g for output position (h, w): MODE 0 zero-fills outside, MODE 1 clamps,
+// MODE 2 is the clamp adjoint (shifted neighbour, plus the position itself on the clamped edge).
+template <int MODE>
+__device__ __forceinline__ void shift_vec8(const __nv_bfloat16* __restrict__ in, long long img, int h, int w, int c0,
+                                           int H, int W, int C, int dh, int dw, float (&o)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.f;
+  if (MODE == 0) {
+    const int hs = h + dh, ws = w + dw;
+    // L1-allocating load: neighbouring positions re-read the other half of each 32-byte sector (group width 40 B)
+    if (hs >= 0 && hs < H && ws >= 0 && ws < W) unpack8(ldg_v4(in + img + ((long long)hs * W + ws) * C + c0), o);
+  } else if (MODE == 1) {
+    const int hs = min(max(h + dh, 0), H - 1), ws = min(max(w + dw, 0), W - 1);
+    unpack8(ldg_v4(in + img + ((long long)hs * W + ws) * C + c0), o);
+  } else {
+    const int hs = h - dh, ws = w - dw;
+    if (hs >= 0 && hs < H && ws >= 0 && ws < W) unpack8(ldg_v4(in + img + ((long long)hs * W + ws) * C + c0), o);
+    const bool edge = (dh < 0 && h == 0) || (dh > 0 && h == H - 1) || (dw < 0 && w == 0) || (dw > 0 && w == W - 1);
+    if (edge) {
+      float s[8];
+      unpack8(ldg_v4(in + img + ((long long)h * W + w) * C + c0), s);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] += s[e];
+    }
+  }
+}
+
+// A 16-byte vector inside one channel group moves as a whole; a vector straddling two ADJACENT groups (AS-MLP: groups of
+// ceil(C / 5) = 20 channels, 2 of every 12 vectors) is stitched from the two groups' source vectors.  The per-element
+// path (8 scalar loads + 8 group searches, ~200 instructions, taken by every warp) made the first version
+// instruction-bound at 3.6x the HBM floor; it is left for vectors that span three or more groups.
 template <int MODE>
 __global__ void __launch_bounds__(RW_THREADS)
 shift_nhwc_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                   const ShiftTable tab) {
+  __shared__ int s_start[9], s_dh[8], s_dw[8];
+  if (threadIdx.x < 9) s_start[threadIdx.x] = tab.start[threadIdx.x];
+  if (threadIdx.x < 8) { s_dh[threadIdx.x] = tab.dh[threadIdx.x]; s_dw[threadIdx.x] = tab.dw[threadIdx.x]; }
+  __syncthreads();
+  const int ng = tab.ngroups;
+  auto group_of = [&](int c) {
+    int g = 0;
+    for (int i = 1; i < ng; ++i)
+      if (c >= s_start[i]) g = i;
+    return g;
+  };
   const int nvec = C >> 3;
   const FastDiv dv(nvec), dw_(W);
   const long long b = blockIdx.y;
   const long long img = b * (long long)H * W * C;
   const int per_img = H * W * nvec;
+  (void)B;
   for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < per_img; i += gridDim.x * RW_THREADS) {
     int pos, cv, h, w;
     dv.divmod(i, pos, cv);
     dw_.divmod(pos, h, w);
     const int c0 = cv * 8;
-    const int g0 = shift_group(tab, c0), g1 = shift_group(tab, c0 + 7);
+    const int g0 = group_of(c0), g1 = group_of(c0 + 7);
+    __nv_bfloat16* dst = out + img + ((long long)h * W + w) * C + c0;
     float o[8];
-    bool done = false;
-    if (g0 == g1 && MODE != 2) {
-      // whole vector moves together: one 16-byte load at the shifted position
-      int hs = h + tab.dh[g0], ws = w + tab.dw[g0];
-      bool inside = true;
-      if (MODE == 0) inside = (hs >= 0 && hs < H && ws >= 0 && ws < W);
-      else { hs = min(max(hs, 0), H - 1); ws = min(max(ws, 0), W - 1); }
-      if (inside) {
-        // L1-allocating load: neighbouring positions re-read the other half of each 32-byte sector (group width 40 B)
-        *reinterpret_cast<uint4*>(out + img + ((long long)h * W + w) * C + c0) =
-            ldg_v4(in + img + ((long long)hs * W + ws) * C + c0);
+    if (g0 == g1) {
+      if (MODE == 0 || MODE == 1) {
+        // pure copy: no unpack / repack
+        int hs = h + s_dh[g0], ws = w + s_dw[g0];
+        bool inside = true;
+        if (MODE == 0) inside = (hs >= 0 && hs < H && ws >= 0 && ws < W);
+        else { hs = min(max(hs, 0), H - 1); ws = min(max(ws, 0), W - 1); }
+        *reinterpret_cast<uint4*>(dst) = inside ? ldg_v4(in + img + ((long long)hs * W + ws) * C + c0) : make_uint4(0, 0, 0, 0);
       } else {
-        *reinterpret_cast<uint4*>(out + img + ((long long)h * W + w) * C + c0) = make_uint4(0, 0, 0, 0);
+        shift_vec8<MODE>(in, img, h, w, c0, H, W, C, s_dh[g0], s_dw[g0], o);
+        *reinterpret_cast<uint4*>(dst) = pack8(o);
       }
-      done = true;
-    }
-    if (!done) {
+    } else if (g1 == g0 + 1) {
+      float o1[8];
+      shift_vec8<MODE>(in, img, h, w, c0, H, W, C, s_dh[g0], s_dw[g0], o);
+      shift_vec8<MODE>(in, img, h, w, c0, H, W, C, s_dh[g1], s_dw[g1], o1);
+      const int split = s_start[g1] - c0;     // first element of the vector that belongs to group g1 (1..7)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = (e < split) ? o[e] : o1[e];
+      *reinterpret_cast<uint4*>(dst) = pack8(o);
+    } else {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int g = (g0 == g1) ? g0 : shift_group(tab, c0 + e);
-        o[e] = shift_fetch<MODE>(in, img, h, w, c0 + e, H, W, C, tab.dh[g], tab.dw[g]);
+        const int g = group_of(c0 + e);
+        o[e] = shift_fetch<MODE>(in, img, h, w, c0 + e, H, W, C, s_dh[g], s_dw[g]);
       }
-      *reinterpret_cast<uint4*>(out + img + ((long long)h * W + w) * C + c0) = pack8(o);
+      *reinterpret_cast<uint4*>(dst) = pack8(o);
     }
   }
 }
@@ -434,8 +482,11 @@ s2v2_reduce_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __r
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
   if (pl < plane) {
+    const FastDiv dw_(W);
+#pragma unroll 2
     for (int pos = blockIdx.x * plane + pl; pos < H * W; pos += gridDim.x * plane) {
-      const int h = pos / W, w = pos % W;
+      int h, w;
+      dw_.divmod(pos, h, w);
       float gv[8];
       if (MODE) unpack8(ldg_nc_v4(g + gimg + (long long)pos * C + v * 8), gv);
 #pragma unroll
@@ -478,30 +529,37 @@ __device__ __forceinline__ void s2_softmax3(const __nv_bfloat16* __restrict__ ha
   }
 }
 // out[b, pos, c] = sum_k softmax_k(hat[b, :, c]) * x_k[b, pos, c]      (s2_mlp_v2.py:45-51)
+// Thread t owns channel vector (t % nvec) and walks positions (t / nvec) + k * plane: the softmax over k of its 8
+// channels (24 exp) is evaluated once per thread, not once per position.
 __global__ void __launch_bounds__(RW_THREADS)
 s2v2_combine_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ hat,
                     __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
   const int nvec = C >> 3;
-  const FastDiv dv(nvec), dw_(W);
+  const int plane = RW_THREADS / nvec;
+  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  const FastDiv dw_(W);
   const long long b = blockIdx.y;
   (void)B;
-  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < H * W * nvec; i += gridDim.x * RW_THREADS) {
-    int pos, cv, h, w;
-    dv.divmod(i, pos, cv);
+  if (pl >= plane) return;
+  const int c0 = v * 8;
+  float bar[3][8];
+  s2_softmax3(hat, b, c0, C, bar);
+  const long long img = b * H * W * 3 * C;
+#pragma unroll 2
+  for (int pos = blockIdx.x * plane + pl; pos < H * W; pos += gridDim.x * plane) {
+    int h, w;
     dw_.divmod(pos, h, w);
-    const int c0 = cv * 8;
-    float bar[3][8], o[8];
-    s2_softmax3(hat, b, c0, C, bar);
+    float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float xv[8];
-      s2_gather8(t, b * H * W * 3 * C, h, w, k, c0, H, W, C, xv);
+      s2_gather8(t, img, h, w, k, c0, H, W, C, xv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] += bar[k][e] * xv[e];
     }
-    *reinterpret_cast<uint4*>(out + (b * H * W + (long long)h * W + w) * C + c0) = pack8(o);
+    *reinterpret_cast<uint4*>(out + (b * H * W + pos) * C + c0) = pack8(o);
   }
 }
 // dhat[b, k, c] = bar_k * (dbar_k - sum_j bar_j dbar_j)                 (softmax over k backward)
@@ -532,29 +590,33 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
                __nv_bfloat16* __restrict__ dt, int B, int H, int W, int C) {
   const int nvec = C >> 3;
   const int qs = C >> 2;
-  const FastDiv dv(nvec), dw_(W);
+  const int plane = RW_THREADS / nvec;
+  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  const FastDiv dw_(W);
   const long long b = blockIdx.y;
   (void)B;
-  for (int i = blockIdx.x * RW_THREADS + threadIdx.x; i < H * W * nvec; i += gridDim.x * RW_THREADS) {
-    int pos, cv, h, w;
-    dv.divmod(i, pos, cv);
+  if (pl >= plane) return;
+  const int c0 = v * 8;
+  const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
+  float bar[3][8];
+  if (MODE == 0) s2_softmax3(hat, b, c0, C, bar);
+  float dav[8];
+  if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(src + b * C + c0), dav);
+  const long long simg = b * H * W * C;
+#pragma unroll 2
+  for (int pos = blockIdx.x * plane + pl; pos < H * W; pos += gridDim.x * plane) {
+    int h, w;
     dw_.divmod(pos, h, w);
-    const int c0 = cv * 8;
-    float bar[3][8];
-    if (MODE == 0) s2_softmax3(hat, b, c0, C, bar);
-    float dav[8];
-    if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(src + b * C + c0), dav);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float o[8];
       if (MODE == 0) {
         float gv[8];
-        if (k < 2) s2_adjoint8(src, b * H * W * C, h, w, k, c0, H, W, C, gv);
-        else unpack8(ldg_nc_v4(src + (b * H * W + (long long)h * W + w) * C + c0), gv);
+        if (k < 2) s2_adjoint8(src, simg, h, w, k, c0, H, W, C, gv);
+        else unpack8(ldg_nc_v4(src + simg + (long long)pos * C + c0), gv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = bar[k][e] * gv[e];
       } else {
-        const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
         if (k == 2 || q0 == q1) {
           int dh = 0, dw = 0;
           if (k < 2) s2_plan_offset(k, q0, dh, dw);
@@ -570,7 +632,7 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
           }
         }
       }
-      *reinterpret_cast<uint4*>(dt + (b * H * W + (long long)h * W + w) * 3 * C + k * C + c0) = pack8(o);
+      *reinterpret_cast<uint4*>(dt + (b * H * W + pos) * 3 * C + k * C + c0) = pack8(o);
     }
   }
 }
