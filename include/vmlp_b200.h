@@ -114,6 +114,11 @@ int vmlp_affine_bwd(const void* dy, const void* x, const void* alpha, const void
 /* out[c] += sum_r a[r, c] * (b ? b[r, c] : 1) */
 int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float* out, int64_t rows, int32_t C,
                 vmlp_stream_t stream);
+/* one pass, contiguous [rows, C] tensors (C <= 2048): out_a[c] += sum_r a[r, c];  out_ab[c] += sum_r a[r, c] * b[r, c]
+   (b may alias a).  The two batch statistics of nn.BatchNorm2d in training mode (conv_mixer.py:20,27,31) and of its
+   backward in one read of each tensor. */
+int vmlp_colsum2(const void* a, const void* b, float* out_a, float* out_ab, int64_t rows, int32_t C,
+                 vmlp_stream_t stream);
 /* out[m] += sum_{b, c} a[b, m, c] */
 int vmlp_rowsum_batched(const void* a, float* out, int64_t batch, int32_t rows_per_batch, int32_t C,
                         vmlp_stream_t stream);
@@ -176,6 +181,10 @@ int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int3
 int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, float* dbar_f32, void* dhat, void* dt,
                           int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
 int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
+/* the whole split-attention backward w.r.t. t in one write: dt = softmax_k(hat) * adjoint_k(dout) + da * read_count_k.
+   Pair with vmlp_s2v2_combine_bwd(..., dt = NULL, ...), which then only produces dbar / dhat. */
+int vmlp_s2v2_dt_fused(const void* dout, const void* hat, const void* da, void* dt, int32_t B, int32_t H, int32_t W,
+                       int32_t C, vmlp_stream_t stream);
 
 /* Hire-MLP region rearrangement (hire_mlp.py:44-152) as load-time index arithmetic on channels-last tensors.
  * Padding is circular with Hp = H + (h - H % h), Wp = W + (w - W % w); step = cross_region_step or 0.

@@ -101,6 +101,7 @@ SYMBOLS = [
     ("vmlp_affine_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int32, c_void_p]),
     ("vmlp_colsum", c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p]),
+    ("vmlp_colsum2", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     ("vmlp_rowsum_batched", c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     ("vmlp_cast_f32_to_bf16", c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     ("vmlp_pad_rows", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
@@ -127,6 +128,7 @@ SYMBOLS = [
     ("vmlp_s2v2_combine_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                         c_int32, c_int32, c_void_p]),
     ("vmlp_s2v2_sum_bwd", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_dt_fused", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_hire_build", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
     ("vmlp_hire_build_adj", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
     ("vmlp_hire_combine", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),

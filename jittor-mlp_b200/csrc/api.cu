@@ -94,6 +94,22 @@ int make_map(CUtensorMap* m, const void* ptr, int64_t inner, int64_t rows, int64
   return VMLP_OK;
 }
 
+// 4-D bf16 tensor map over a channels-last image tensor [B, H, W, C]: dims (C, W, H, B), no swizzle, zero OOB fill.
+int make_map_nhwc(CUtensorMap* m, const void* ptr, int B, int H, int W, int C, int box_c, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(VMLP_ELAUNCH, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!aligned16(ptr) || (C % 8) != 0) return fail(VMLP_EALIGN, "image tensor %p C=%d must be 16-byte aligned rows", ptr, C);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VMLP_EINVAL, "cuTensorMapEncodeTiled (NHWC) failed (%d): B %d H %d W %d C %d", (int)r, B, H, W, C);
+  return VMLP_OK;
+}
+
 template <int BN, int EPI, int CG>
 int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& td2,
                   const CUtensorMap& tpf, const GemmParams& p, int grid, cudaStream_t st) {
@@ -456,7 +472,7 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
     const long long cap = (long long)dv.sms * 8;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    colsum_flat_kernel<<<(unsigned)gx, RW_THREADS, (size_t)C * sizeof(float), st>>>((cbf)a, (cbf)b, out, rows, C);
+    colsum_flat_kernel<0><<<(unsigned)gx, RW_THREADS, (size_t)C * sizeof(float), st>>>((cbf)a, (cbf)b, out, nullptr, rows, C);
     CUDA_OK(cudaGetLastError());
     ++g_launches;
     return VMLP_OK;
@@ -467,6 +483,22 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   colsum_kernel<<<dim3((unsigned)gx, (unsigned)slabs), RW_THREADS, 0, st>>>((cbf)a, a_ld, (cbf)b, b_ld, out, rows, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+int vmlp_colsum2(const void* a, const void* b, float* out_a, float* out_ab, int64_t rows, int32_t C,
+                 vmlp_stream_t stream) {
+  if (!a || !b || !out_a || !out_ab || rows <= 0 || (C % 8) || C > 8 * RW_THREADS) return fail(VMLP_EINVAL, "colsum2 args");
+  if (!aligned16(a) || !aligned16(b)) return fail(VMLP_EALIGN, "colsum2 alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rpb = RW_THREADS / (C / 8);
+  long long gx = (rows + 4LL * rpb - 1) / (4LL * rpb);
+  const long long cap = (long long)device_info().sms * 8;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  colsum_flat_kernel<1><<<(unsigned)gx, RW_THREADS, 2 * (size_t)C * sizeof(float), st>>>((cbf)a, (cbf)b, out_a, out_ab, rows, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -714,9 +746,10 @@ int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int3
 }
 int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, float* dbar_f32, void* dhat, void* dt,
                           int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
-  int rc = s2v2_check(t, dt, B, H, W, C);
+  int rc = s2v2_check(t, dhat, B, H, W, C);
   if (rc) return rc;
-  if (!hat || !dout || !dbar_f32 || !dhat || !aligned16(hat) || !aligned16(dout) || !aligned16(dhat)) return fail(VMLP_EALIGN, "s2v2 bwd");
+  if (!hat || !dout || !dbar_f32 || !dhat || !aligned16(hat) || !aligned16(dout) || !aligned16(dhat) || (dt && !aligned16(dt)))
+    return fail(VMLP_EALIGN, "s2v2 bwd");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   s2v2_reduce_kernel<1><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, RW_THREADS * 24 * sizeof(float), st>>>(
       (cbf)t, (cbf)dout, dbar_f32, H, W, C);
@@ -726,16 +759,29 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
   s2v2_softmax_bwd_kernel<<<(int)((nv + 127) / 128), 128, 0, st>>>((cbf)hat, dbar_f32, (bf)dhat, B, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
-  s2v2_dt_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, (bf)dt, B, H, W, C);
-  CUDA_OK(cudaGetLastError());
-  ++g_launches;
+  if (dt) {     // dt == NULL: the caller finishes with vmlp_s2v2_dt_fused once d(a) is known
+    s2v2_dt_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, nullptr, (bf)dt, B, H, W, C);
+    CUDA_OK(cudaGetLastError());
+    ++g_launches;
+  }
   return VMLP_OK;
 }
 int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
   int rc = s2v2_check(da, dt, B, H, W, C);
   if (rc) return rc;
   s2v2_dt_kernel<1><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      (cbf)da, nullptr, (bf)dt, B, H, W, C);
+      nullptr, nullptr, (cbf)da, (bf)dt, B, H, W, C);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_s2v2_dt_fused(const void* dout, const void* hat, const void* da, void* dt, int32_t B, int32_t H, int32_t W,
+                       int32_t C, vmlp_stream_t stream) {
+  int rc = s2v2_check(dout, dt, B, H, W, C);
+  if (rc) return rc;
+  if (!hat || !da || !aligned16(hat) || !aligned16(da)) return fail(VMLP_EALIGN, "s2v2 dt_fused");
+  s2v2_dt_kernel<2><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      (cbf)dout, (cbf)hat, (cbf)da, (bf)dt, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -814,11 +860,24 @@ static int dwconv_launch(const void* x, const void* w, const void* bias, void* o
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
     attr_done = true;
   }
-  const long long tiles = (long long)B * ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
+  const long long tiles = (long long)B * ((H + DW_TH - 1) / DW_TH) * ((W + DW_TW - 1) / DW_TW);
+  if (tiles >= (1 << 22)) return fail(VMLP_EINVAL, "dwconv: too many tiles");
   const int cb = (C + DW_CH - 1) / DW_CH;
-  long long gx = ((long long)device_info().sms * 3 + cb - 1) / cb;
+  // persistent blocks: the grid must not exceed the resident capacity (asked from the runtime: registers, shared memory
+  // and the L1 carve-out decide), or the few blocks of a second wave double the kernel time
+  static int occ = 0;
+  if (occ == 0) {
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DW_THREADS, DwSmem<K>::BYTES));
+    if (occ < 1) occ = 1;
+    if (getenv("VMLP_DEBUG")) fprintf(stderr, "vmlp: dwconv<%d,%d,%d> %d blocks/SM\n", K, FLIP, EPI, occ);
+  }
+  long long gx = ((long long)device_info().sms * occ) / cb;
+  if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
-  kern<<<dim3((unsigned)gx, (unsigned)cb), 256, DwSmem<K>::BYTES, st>>>((cbf)x, (cbf)w, (cbf)bias, (bf)o1, (bf)o2, B, H, W, C);
+  CUtensorMap tmx;
+  int rc = make_map_nhwc(&tmx, x, B, H, W, C, DW_CH, DwSmem<K>::IN_W, DwSmem<K>::IN_H);
+  if (rc) return rc;
+  kern<<<dim3((unsigned)gx, (unsigned)cb), DW_THREADS, DwSmem<K>::BYTES, st>>>(tmx, (cbf)w, (cbf)bias, (bf)o1, (bf)o2, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -828,14 +887,27 @@ static int dwconv_wgrad_launch(const void* x, const void* dz, float* dw, int B, 
   auto kern = dwconv_wgrad_kernel<K>;
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES_WGRAD));
     attr_done = true;
   }
-  const long long tiles = (long long)B * ((H + DW_TILE - 1) / DW_TILE) * ((W + DW_TILE - 1) / DW_TILE);
+  const long long tiles = (long long)B * ((H + DW_TH - 1) / DW_TH) * ((W + DW_TW - 1) / DW_TW);
+  if (tiles >= (1 << 22)) return fail(VMLP_EINVAL, "dwconv: too many tiles");
   const int cb = (C + DW_CH - 1) / DW_CH;
-  long long gx = ((long long)device_info().sms * 3 + cb - 1) / cb;
+  static int occ = 0;
+  if (occ == 0) {
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * K, DwSmem<K>::BYTES_WGRAD));
+    if (occ < 1) occ = 1;
+    if (getenv("VMLP_DEBUG")) fprintf(stderr, "vmlp: dwconv_wgrad<%d> %d blocks/SM\n", K, occ);
+  }
+  long long gx = ((long long)device_info().sms * occ) / cb;
+  if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
-  kern<<<dim3((unsigned)gx, (unsigned)cb), 256, DwSmem<K>::BYTES, st>>>((cbf)x, (cbf)dz, dw, B, H, W, C);
+  CUtensorMap tmx, tmdz;
+  int rc = make_map_nhwc(&tmx, x, B, H, W, C, DW_CH, DwSmem<K>::IN_W, DwSmem<K>::IN_H);
+  if (rc) return rc;
+  rc = make_map_nhwc(&tmdz, dz, B, H, W, C, DW_CH, DW_TW, DW_TH);
+  if (rc) return rc;
+  kern<<<dim3((unsigned)gx, (unsigned)cb), 32 * K, DwSmem<K>::BYTES_WGRAD, st>>>(tmx, tmdz, dw, B, H, W, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

@@ -15,6 +15,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// 128-bit shared-memory read-modify-write of four fp32 partial sums
+__device__ __forceinline__ void add_f4(float* p, float a, float b, float c, float d) {
+  float4 v = *reinterpret_cast<float4*>(p);
+  v.x += a; v.y += b; v.z += c; v.w += d;
+  *reinterpret_cast<float4*>(p) = v;
+}
 // sum over aligned groups of G lanes (G = 8, 16, 32): narrow rows pack 32 / G rows into one warp
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -202,7 +208,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
     for (int i = 0; i < VPL; ++i) {
       const int vi = i * 32 + sl;
       if (row_ok && vi < nvec) {
-        float d[8], xv[8], gm[8];
+        float d[8], xv[8], gm[8], pg[8];
         unpack8(rd[i], d);
         unpack8(rx[i], xv);
         unpack8(*reinterpret_cast<const uint4*>(gamma + vi * 8), gm);
@@ -213,12 +219,19 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
           s1 += g;
           s2 += g * xh;
           if (PRIV) {
-            sh_g[e * NV + vi] += d[e] * xh;
-            sh_b[e * NV + vi] += d[e];
+            pg[e] = d[e] * xh;
           } else {
             atomicAdd(&sh_g[e * NV + vi], d[e] * xh);
             atomicAdd(&sh_b[e * NV + vi], d[e]);
           }
+        }
+        if (PRIV) {
+          // warp-private slice, [half][vector][4] layout: 128-bit read-modify-writes (conflict-free: lane l touches the
+          // 16 bytes at l * 16), 8 shared-memory instructions per 8 elements where scalar updates needed 32
+          add_f4(sh_g + vi * 4, pg[0], pg[1], pg[2], pg[3]);
+          add_f4(sh_g + (NV + vi) * 4, pg[4], pg[5], pg[6], pg[7]);
+          add_f4(sh_b + vi * 4, d[0], d[1], d[2], d[3]);
+          add_f4(sh_b + (NV + vi) * 4, d[4], d[5], d[6], d[7]);
         }
       }
     }
@@ -240,10 +253,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
         for (int e = 0; e < 8; ++e) {
           const float xh = (xv[e] - mean) * rstd;
           o[e] = a[e] + rstd * (d[e] * gm[e] - s1 - xh * s2);
-          if (EXTRA) {
-            sh_a[e * NV + vi] += a[e];
-            osum += o[e];
-          }
+          if (EXTRA) osum += o[e];
+        }
+        if (EXTRA) {
+          add_f4(sh_a + vi * 4, a[0], a[1], a[2], a[3]);
+          add_f4(sh_a + (NV + vi) * 4, a[4], a[5], a[6], a[7]);
         }
         *reinterpret_cast<uint4*>(dx + r * dx_ld + vi * 8) = pack8(o);
       }
@@ -257,11 +271,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dy_ld, cons
   for (int i = threadIdx.x; i < nvec * 8; i += RW_THREADS) {
     const int vi = i >> 3, e = i & 7;
     float sg = 0.f, sb = 0.f, sa = 0.f;
+    // PRIV slices use the [half][vector][4] layout, the shared (atomic) slice the [e][vector] one
+    const int off = PRIV ? (((e >> 2) * NV + vi) * 4 + (e & 3)) : (e * NV + vi);
 #pragma unroll
     for (int w = 0; w < SLICES; ++w) {
-      sg += sh[w * SL + e * NV + vi];
-      sb += sh[w * SL + 8 * NV + e * NV + vi];
-      if (EXTRA) sa += sh[w * SL + 16 * NV + e * NV + vi];
+      sg += sh[w * SL + off];
+      sb += sh[w * SL + 8 * NV + off];
+      if (EXTRA) sa += sh[w * SL + 16 * NV + off];
     }
     red_add_f32(dgamma + i, sg);
     red_add_f32(dbeta + i, sb);
@@ -374,18 +390,32 @@ colsum_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bf
 // Contiguous rows (ld == C, C <= 2048): thread t owns channel vector (t % nvec) of row slot (t / nvec), so a block streams
 // whole rows fully coalesced whatever C is (the slab kernel above keeps 20 of 32 lanes idle at C = 96) and keeps four
 // 16-byte loads per operand in flight.
+// DUAL = 1: out[c] += sum_r a[r, c] AND out2[c] += sum_r a[r, c] * b[r, c] in the same pass -- the two BatchNorm
+// statistics (sum, sum of squares with b == a; sum dy, sum dy * a in backward) read each tensor once instead of twice.
+template <int DUAL>
 __global__ void __launch_bounds__(RW_THREADS)
 colsum_flat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float* __restrict__ out,
-                   long long rows, int C) {
-  extern __shared__ float shc[];          // [C]
+                   float* __restrict__ out2, long long rows, int C) {
+  extern __shared__ float shc[];          // [(1 + DUAL) * C]
   const int nvec = C >> 3;
-  for (int i = threadIdx.x; i < C; i += RW_THREADS) shc[i] = 0.f;
+  for (int i = threadIdx.x; i < (1 + DUAL) * C; i += RW_THREADS) shc[i] = 0.f;
   __syncthreads();
   const int rpb = RW_THREADS / nvec;      // rows per block iteration
   const int cv = threadIdx.x % nvec, ro = threadIdx.x / nvec;
-  float acc[8];
+  const bool same = DUAL && (a == b);
+  float acc[8], acc2[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int e = 0; e < 8; ++e) { acc[e] = 0.f; acc2[e] = 0.f; }
+  auto accumulate = [&](const uint4& va, const uint4& vb) {
+    float d[8], m[8];
+    unpack8(va, d);
+    if (b) unpack8(vb, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (DUAL) { acc[e] += d[e]; acc2[e] += d[e] * m[e]; }
+      else acc[e] += b ? d[e] * m[e] : d[e];
+    }
+  };
   if (ro < rpb) {
     const long long step = (long long)gridDim.x * rpb;
     long long r = (long long)blockIdx.x * rpb + ro;
@@ -394,39 +424,29 @@ colsum_flat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __r
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         va[u] = ldg_nc_v4(a + ((r + u * step) * nvec + cv) * 8);
-        if (b) vb[u] = ldg_nc_v4(b + ((r + u * step) * nvec + cv) * 8);
+        vb[u] = va[u];
+        if (b && !same) vb[u] = ldg_nc_v4(b + ((r + u * step) * nvec + cv) * 8);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float d[8];
-        unpack8(va[u], d);
-        if (b) {
-          float m[8];
-          unpack8(vb[u], m);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d[e] *= m[e];
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += d[e];
-      }
+      for (int u = 0; u < 4; ++u) accumulate(va[u], vb[u]);
     }
     for (; r < rows; r += step) {
-      float d[8];
-      unpack8(ldg_nc_v4(a + (r * nvec + cv) * 8), d);
-      if (b) {
-        float m[8];
-        unpack8(ldg_nc_v4(b + (r * nvec + cv) * 8), m);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] *= m[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] += d[e];
+      const uint4 va = ldg_nc_v4(a + (r * nvec + cv) * 8);
+      uint4 vb = va;
+      if (b && !same) vb = ldg_nc_v4(b + (r * nvec + cv) * 8);
+      accumulate(va, vb);
     }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&shc[cv * 8 + e], acc[e]);
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&shc[cv * 8 + e], acc[e]);
+      if (DUAL) atomicAdd(&shc[C + cv * 8 + e], acc2[e]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += RW_THREADS) red_add_f32(out + i, shc[i]);
+  for (int i = threadIdx.x; i < C; i += RW_THREADS) {
+    red_add_f32(out + i, shc[i]);
+    if (DUAL) red_add_f32(out2 + i, shc[C + i]);
+  }
 }
 
 // --------------------------------------------------------------------------- batched row sums

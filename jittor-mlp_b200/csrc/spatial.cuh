@@ -584,10 +584,12 @@ __global__ void s2v2_softmax_bwd_kernel(const __nv_bfloat16* __restrict__ hat, c
 }
 // dt[b, pos, kC + c] = bar_k[b, c] * adjoint_k(dout)[pos, c]   (MODE 0: combine backward, hat given)
 //                    = da[b, c] * read_count_k(pos, c)         (MODE 1: sum backward, da given as bf16 [B, C])
+//                    = both terms added                        (MODE 2: the whole split-attention backward in one write;
+//                      as two autograd nodes it cost a second 3C-wide write plus a 3-tensor add pass)
 template <int MODE>
 __global__ void __launch_bounds__(RW_THREADS)
 s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ hat,
-               __nv_bfloat16* __restrict__ dt, int B, int H, int W, int C) {
+               const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dt, int B, int H, int W, int C) {
   const int nvec = C >> 3;
   const int qs = C >> 2;
   const int plane = RW_THREADS / nvec;
@@ -599,9 +601,9 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
   const int c0 = v * 8;
   const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
   float bar[3][8];
-  if (MODE == 0) s2_softmax3(hat, b, c0, C, bar);
+  if (MODE != 1) s2_softmax3(hat, b, c0, C, bar);
   float dav[8];
-  if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(src + b * C + c0), dav);
+  if (MODE != 0) unpack8(*reinterpret_cast<const uint4*>(da + b * C + c0), dav);
   const long long simg = b * H * W * C;
 #pragma unroll 2
   for (int pos = blockIdx.x * plane + pl; pos < H * W; pos += gridDim.x * plane) {
@@ -610,25 +612,28 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float o[8];
-      if (MODE == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+      if (MODE != 1) {
         float gv[8];
         if (k < 2) s2_adjoint8(src, simg, h, w, k, c0, H, W, C, gv);
         else unpack8(ldg_nc_v4(src + simg + (long long)pos * C + c0), gv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = bar[k][e] * gv[e];
-      } else {
+      }
+      if (MODE != 0) {
         if (k == 2 || q0 == q1) {
           int dh = 0, dw = 0;
           if (k < 2) s2_plan_offset(k, q0, dh, dw);
           const float cnt = (k < 2) ? s2_read_count(h, w, H, W, dh, dw) : 1.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = dav[e] * cnt;
+          for (int e = 0; e < 8; ++e) o[e] += dav[e] * cnt;
         } else {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             int dh, dw;
             s2_plan_offset(k, min((c0 + e) / qs, 3), dh, dw);
-            o[e] = dav[e] * s2_read_count(h, w, H, W, dh, dw);
+            o[e] += dav[e] * s2_read_count(h, w, H, W, dh, dw);
           }
         }
       }

@@ -133,96 +133,132 @@ hire_restore_adj_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* _
 
 // ============================================================================================ ConvMixer depthwise conv
 // nn.Conv2d(dim, dim, k, groups=dim, padding="same") on [B, H, W, C] (conv_mixer.py:24): a shared-memory stencil.
-// Block = 8x8 output pixels x 64 channels; thread = (channel, 2 output rows); each tap row is slid over a register
-// window so every shared-memory load feeds K FMAs.  FLIP = 1 evaluates the same stencil with the kernel rotated by
-// 180 degrees, which is the input gradient.  EPI = 1 adds the bias and writes gelu'(z) (for backward) and gelu(z).
-constexpr int DW_TILE = 8;
-constexpr int DW_CH = 64;
+// Block = 16 x 8 output pixels x 64 channels, 128 threads: lane = channel PAIR (one 32-bit shared-memory word holds
+// both bf16 channels, all arithmetic is packed fp32x2: FFMA2), warp = four output rows.  The warp slides over its
+// 4 + K - 1 input rows once; each input row is loaded into a register window (TW + K - 1 pairs) and feeds the up to
+// four output rows it overlaps, so one window load serves up to 4 * K * 8 packed FMAs.  FLIP = 1 evaluates the same
+// stencil with the kernel rotated by 180 degrees, which is the input gradient.  EPI = 1 adds the bias and writes
+// gelu'(z) (for backward) and gelu(z).
+// (Round-1 version: scalar bf16 loads, one channel per thread, 2 output rows: 15.8 TFLOP/s fp32, 1.25 ms per layer.)
+constexpr int DW_TH = 16;                 // tile rows
+constexpr int DW_TW = 8;                  // tile columns
+constexpr int DW_CH = 64;                 // channels per block (32 pairs = one warp's lanes)
+constexpr int DW_ROWS = 4;                // output rows per warp
+constexpr int DW_THREADS = 32 * (DW_TH / DW_ROWS);
 template <int K>
 struct DwSmem {
-  static constexpr int IN_W = DW_TILE + K - 1;
-  static constexpr int IN_ELEMS = IN_W * IN_W * DW_CH;          // bf16
-  static constexpr int W_ELEMS = K * K * DW_CH;                 // float
-  static constexpr int BYTES = IN_ELEMS * 2 + W_ELEMS * 4 + DW_TILE * DW_TILE * DW_CH * 2;
+  static constexpr int IN_H = DW_TH + K - 1;
+  static constexpr int IN_W = DW_TW + K - 1;
+  static constexpr int IN_ELEMS = IN_H * IN_W * DW_CH;          // bf16
+  static constexpr int W_ELEMS = K * K * DW_CH;                 // float ([tap][pair] float2)
+  static constexpr int DZ_ELEMS = DW_TH * DW_TW * DW_CH;        // bf16 (wgrad only)
+  static constexpr int BYTES = 2 * IN_ELEMS * 2 + W_ELEMS * 4 + 128 + 16;              // two input buffers + weights + align + barriers
+  static constexpr int BYTES_WGRAD = 2 * (IN_ELEMS * 2 + DZ_ELEMS * 2) + 128 + 16;    // two (x, dz) buffer pairs
 };
 
-template <int K>
-__device__ __forceinline__ void dw_load_tile(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* s_in, long long b, int h0,
-                                             int w0, int c0, int H, int W, int C) {
-  constexpr int IN_W = DW_TILE + K - 1, P = K / 2;
-  for (int v = threadIdx.x; v < IN_W * IN_W * (DW_CH / 8); v += blockDim.x) {
-    const int cv = v % (DW_CH / 8), pos = v / (DW_CH / 8);
-    const int hh = h0 - P + pos / IN_W, ww = w0 - P + pos % IN_W;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W && c0 + cv * 8 < C)
-      val = ldg_nc_v4(x + ((b * H + hh) * W + ww) * C + c0 + cv * 8);
-    *reinterpret_cast<uint4*>(s_in + pos * DW_CH + cv * 8) = val;
-  }
+// Tile loads are single TMA instructions: a 4-D map (C, W, H, B) with box (64, COLS + K - 1, ROWS + K - 1, 1) lands the
+// halo tile as [row][col][64 channels] in shared memory; coordinates outside the image (the "same" padding) and
+// channels past C are zero-filled by the engine.  One elected thread issues the load of the NEXT tile into the other
+// buffer before the block computes the current one.  (Per-thread 16-byte loads with their address arithmetic were 20 %
+// of all executed instructions and, before double buffering, 40 % of the warp time as long-scoreboard stalls.)
+__device__ __forceinline__ f32x2 dw_lds_pair(const __nv_bfloat16* p) {     // two adjacent bf16 channels -> packed fp32x2
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+  return pack2(bf16lo(w), bf16hi(w));
 }
 
 template <int K, int FLIP, int EPI>
-__global__ void __launch_bounds__(256)
-dwconv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ wgt,
+__global__ void __launch_bounds__(DW_THREADS)
+dwconv_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ wgt,
               const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out2,
               int B, int H, int W, int C) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  constexpr int IN_W = DW_TILE + K - 1;
-  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(dw_smem);
-  float* s_w = reinterpret_cast<float*>(dw_smem + DwSmem<K>::IN_ELEMS * 2);
-  const int tiles_w = (W + DW_TILE - 1) / DW_TILE, tiles_h = (H + DW_TILE - 1) / DW_TILE;
-  const int c0 = blockIdx.y * DW_CH;
-  const int tx = threadIdx.x % DW_CH, ty = threadIdx.x / DW_CH;
-  const int c = c0 + tx;
-  for (int i = threadIdx.x; i < K * K * DW_CH; i += blockDim.x) {
-    const int cc = i % DW_CH, tap = i / DW_CH;
-    const int src = FLIP ? (K * K - 1 - tap) : tap;
-    s_w[i] = (c0 + cc < C) ? __bfloat162float(wgt[(long long)(c0 + cc) * K * K + src]) : 0.f;
+  extern __shared__ uint8_t dw_smem_raw[];
+  uint8_t* dw_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int IN_W = DwSmem<K>::IN_W, P = K / 2;
+  __nv_bfloat16* s_buf = reinterpret_cast<__nv_bfloat16*>(dw_smem);               // 2 x IN_ELEMS
+  f32x2* s_w = reinterpret_cast<f32x2*>(dw_smem + 2 * DwSmem<K>::IN_ELEMS * 2);    // [tap][pair]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_smem + 2 * DwSmem<K>::IN_ELEMS * 2 + DwSmem<K>::W_ELEMS * 4);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
   }
-  const float bv = (EPI && c < C) ? __bfloat162float(bias[c]) : 0.f;
-  for (long long tile = blockIdx.x; tile < (long long)B * tiles_h * tiles_w; tile += gridDim.x) {
-    const long long b = tile / (tiles_h * tiles_w);
-    const int h0 = static_cast<int>((tile / tiles_w) % tiles_h) * DW_TILE, w0 = static_cast<int>(tile % tiles_w) * DW_TILE;
-    __syncthreads();
-    dw_load_tile<K>(x, s_in, b, h0, w0, c0, H, W, C);
-    __syncthreads();
-    float acc[2][DW_TILE];
+  __syncthreads();
+  const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
+  const int c0 = blockIdx.y * DW_CH;
+  const int pr = threadIdx.x & 31, rg = threadIdx.x >> 5;      // channel pair, row group (warp-uniform)
+  const int c = c0 + 2 * pr;
+  for (int i = threadIdx.x; i < K * K * (DW_CH / 2); i += blockDim.x) {
+    const int pp = i % (DW_CH / 2), tap = i / (DW_CH / 2);
+    const int src = FLIP ? (K * K - 1 - tap) : tap;
+    const int cc = c0 + 2 * pp;
+    const float wa = (cc < C) ? __bfloat162float(wgt[(long long)cc * K * K + src]) : 0.f;
+    const float wb = (cc + 1 < C) ? __bfloat162float(wgt[(long long)(cc + 1) * K * K + src]) : 0.f;
+    s_w[i] = pack2(wa, wb);
+  }
+  f32x2 bv = pack2(0.f, 0.f);
+  if (EPI && c < C) bv = pack2(__bfloat162float(bias[c]), __bfloat162float(bias[c + 1]));
+  const FastDiv dtw(tiles_w), dth(tiles_h);
+  const int ntiles = B * tiles_h * tiles_w;
+  auto issue = [&](int tile, int buf) {                    // one thread: TMA load of a halo tile into buffer `buf`
+    int t1, tw_i, b, th_i;
+    dtw.divmod(tile, t1, tw_i);
+    dth.divmod(t1, b, th_i);
+    mbar_arrive_expect_tx(&bars[buf], DwSmem<K>::IN_ELEMS * 2);
+    tma_load_4d(s_buf + buf * DwSmem<K>::IN_ELEMS, &tmX, &bars[buf], c0, tw_i * DW_TW - P, th_i * DW_TH - P, b);
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    int t1, tw_i, b, th_i;
+    dtw.divmod(tile, t1, tw_i);
+    dth.divmod(t1, b, th_i);
+    const int h0 = th_i * DW_TH, w0 = tw_i * DW_TW;
+    const __nv_bfloat16* s_in = s_buf + (it & 1) * DwSmem<K>::IN_ELEMS;
+    __syncthreads();                 // every warp is done with the other buffer (previous tile) and with s_w setup
+    if (threadIdx.x == 0 && tile + static_cast<int>(gridDim.x) < ntiles) issue(tile + gridDim.x, (it + 1) & 1);
+    mbar_wait(&bars[it & 1], (it >> 1) & 1);     // this tile has landed
+    f32x2 acc[DW_ROWS][DW_TW];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < DW_ROWS; ++r)
 #pragma unroll
-      for (int q = 0; q < DW_TILE; ++q) acc[r][q] = bv;
+      for (int q = 0; q < DW_TW; ++q) acc[r][q] = bv;
+    const __nv_bfloat16* rowp = s_in + (rg * DW_ROWS) * IN_W * DW_CH + 2 * pr;
+#pragma unroll 1
+    for (int ir = 0; ir < DW_ROWS + K - 1; ++ir) {
+      f32x2 win[IN_W];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int orow = ty * 2 + r;
+      for (int q = 0; q < IN_W; ++q) win[q] = dw_lds_pair(rowp + (ir * IN_W + q) * DW_CH);
 #pragma unroll
-      for (int i = 0; i < K; ++i) {
-        float win[IN_W];
+      for (int r = 0; r < DW_ROWS; ++r) {
+        const int i = ir - r;                  // tap row of output row r that reads input row ir (warp-uniform)
+        if (i >= 0 && i < K) {
 #pragma unroll
-        for (int q = 0; q < IN_W; ++q) win[q] = __bfloat162float(s_in[((orow + i) * IN_W + q) * DW_CH + tx]);
+          for (int j = 0; j < K; ++j) {
+            const f32x2 wv = s_w[(i * K + j) * (DW_CH / 2) + pr];
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const float wv = s_w[(i * K + j) * DW_CH + tx];
-#pragma unroll
-          for (int q = 0; q < DW_TILE; ++q) acc[r][q] = fmaf(wv, win[q + j], acc[r][q]);
+            for (int q = 0; q < DW_TW; ++q) acc[r][q] = fma2(wv, win[q + j], acc[r][q]);
+          }
         }
       }
     }
     if (c < C) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int hh = h0 + ty * 2 + r;
+      for (int r = 0; r < DW_ROWS; ++r) {
+        const int hh = h0 + rg * DW_ROWS + r;
         if (hh >= H) continue;
+        const long long orow = (((long long)b * H + hh) * W + w0) * C + c;
 #pragma unroll
-        for (int q = 0; q < DW_TILE; ++q) {
-          const int ww = w0 + q;
-          if (ww >= W) continue;
-          const long long o = ((b * H + hh) * W + ww) * C + c;
+        for (int q = 0; q < DW_TW; ++q) {
+          if (w0 + q >= W) continue;
+          const long long o = orow + (long long)q * C;
           if (EPI) {            // out = gelu'(z) (kept for backward), out2 = gelu(z)
-            float d;
-            const float gz = gelu_erf_t<true>(acc[r][q], d);
-            out[o] = __float2bfloat16(d);
-            out2[o] = __float2bfloat16(gz);
+            f32x2 gl, dg;
+            gelu_erf_pair<true>(acc[r][q], gl, dg);
+            *reinterpret_cast<uint32_t*>(out + o) = pack_bf16x2_f2(dg);
+            *reinterpret_cast<uint32_t*>(out2 + o) = pack_bf16x2_f2(gl);
           } else {
-            out[o] = __float2bfloat16(acc[r][q]);
+            *reinterpret_cast<uint32_t*>(out + o) = pack_bf16x2_f2(acc[r][q]);
           }
         }
       }
@@ -231,63 +267,71 @@ dwconv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 }
 
 // dW[c][i][j] += sum_{b,h,w} dz[b,h,w,c] * x[b, h+i-P, w+j-P, c]   (fp32 atomics once per block)
-// thread = (channel, tap rows i == ty mod 4): up to ceil(K/4) x K accumulators live in registers across all tiles.
+// K warps: warp = tap row i, lane = channel pair; K packed accumulators per thread live in registers across all tiles
+// of the block.  Per output row the warp reads the dz row (8 pairs) and the x row it pairs with (8 + K - 1 pairs).
 template <int K>
-__global__ void __launch_bounds__(256)
-dwconv_wgrad_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dz, float* __restrict__ dw,
-                    int B, int H, int W, int C) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  constexpr int IN_W = DW_TILE + K - 1, TR = (K + 3) / 4;
-  __nv_bfloat16* s_in = reinterpret_cast<__nv_bfloat16*>(dw_smem);
-  __nv_bfloat16* s_dz = reinterpret_cast<__nv_bfloat16*>(dw_smem + DwSmem<K>::IN_ELEMS * 2 + DwSmem<K>::W_ELEMS * 4);
-  const int tiles_w = (W + DW_TILE - 1) / DW_TILE, tiles_h = (H + DW_TILE - 1) / DW_TILE;
+__global__ void __launch_bounds__(32 * K)
+dwconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDz,
+                    float* __restrict__ dw, int B, int H, int W, int C) {
+  extern __shared__ uint8_t dw_smem_raw[];
+  uint8_t* dw_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dw_smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int IN_W = DwSmem<K>::IN_W, P = K / 2;
+  constexpr int STAGE = DwSmem<K>::IN_ELEMS + DwSmem<K>::DZ_ELEMS;            // bf16 elements per (x, dz) buffer pair
+  __nv_bfloat16* s_buf = reinterpret_cast<__nv_bfloat16*>(dw_smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dw_smem + 2 * STAGE * 2);
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDz);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int tiles_w = (W + DW_TW - 1) / DW_TW, tiles_h = (H + DW_TH - 1) / DW_TH;
   const int c0 = blockIdx.y * DW_CH;
-  const int tx = threadIdx.x % DW_CH, ty = threadIdx.x / DW_CH;
-  float acc[TR][K];
+  const int pr = threadIdx.x & 31, ti = threadIdx.x >> 5;      // channel pair, tap row (warp-uniform)
+  f32x2 acc[K];
 #pragma unroll
-  for (int a = 0; a < TR; ++a)
-#pragma unroll
-    for (int j = 0; j < K; ++j) acc[a][j] = 0.f;
-  for (long long tile = blockIdx.x; tile < (long long)B * tiles_h * tiles_w; tile += gridDim.x) {
-    const long long b = tile / (tiles_h * tiles_w);
-    const int h0 = static_cast<int>((tile / tiles_w) % tiles_h) * DW_TILE, w0 = static_cast<int>(tile % tiles_w) * DW_TILE;
+  for (int j = 0; j < K; ++j) acc[j] = pack2(0.f, 0.f);
+  const FastDiv dtw(tiles_w), dth(tiles_h);
+  const int ntiles = B * tiles_h * tiles_w;
+  auto issue = [&](int tile, int buf) {                    // one thread: x halo tile + dz tile of the same origin
+    int t1, tw_i, b, th_i;
+    dtw.divmod(tile, t1, tw_i);
+    dth.divmod(t1, b, th_i);
+    mbar_arrive_expect_tx(&bars[buf], STAGE * 2);
+    tma_load_4d(s_buf + buf * STAGE, &tmX, &bars[buf], c0, tw_i * DW_TW - P, th_i * DW_TH - P, b);
+    tma_load_4d(s_buf + buf * STAGE + DwSmem<K>::IN_ELEMS, &tmDz, &bars[buf], c0, tw_i * DW_TW, th_i * DW_TH, b);
+  };
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < ntiles) issue(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const __nv_bfloat16* s_in = s_buf + (it & 1) * STAGE;
+    const __nv_bfloat16* s_dz = s_in + DwSmem<K>::IN_ELEMS;
     __syncthreads();
-    dw_load_tile<K>(x, s_in, b, h0, w0, c0, H, W, C);
-    for (int v = threadIdx.x; v < DW_TILE * DW_TILE * (DW_CH / 8); v += blockDim.x) {
-      const int cv = v % (DW_CH / 8), pos = v / (DW_CH / 8);
-      const int hh = h0 + pos / DW_TILE, ww = w0 + pos % DW_TILE;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (hh < H && ww < W && c0 + cv * 8 < C) val = ldg_nc_v4(dz + ((b * H + hh) * W + ww) * C + c0 + cv * 8);
-      *reinterpret_cast<uint4*>(s_dz + pos * DW_CH + cv * 8) = val;
-    }
-    __syncthreads();
+    if (threadIdx.x == 0 && tile + static_cast<int>(gridDim.x) < ntiles) issue(tile + gridDim.x, (it + 1) & 1);
+    mbar_wait(&bars[it & 1], (it >> 1) & 1);
+#pragma unroll 2
+    for (int r = 0; r < DW_TH; ++r) {
+      f32x2 g[DW_TW], win[IN_W];
 #pragma unroll
-    for (int a = 0; a < TR; ++a) {
-      const int i = ty + 4 * a;
-      if (i < K) {
+      for (int q = 0; q < DW_TW; ++q) g[q] = dw_lds_pair(s_dz + (r * DW_TW + q) * DW_CH + 2 * pr);
 #pragma unroll
-        for (int r = 0; r < DW_TILE; ++r) {
-          float g[DW_TILE], win[IN_W];
+      for (int q = 0; q < IN_W; ++q) win[q] = dw_lds_pair(s_in + ((r + ti) * IN_W + q) * DW_CH + 2 * pr);
 #pragma unroll
-          for (int q = 0; q < DW_TILE; ++q) g[q] = __bfloat162float(s_dz[(r * DW_TILE + q) * DW_CH + tx]);
+      for (int j = 0; j < K; ++j)
 #pragma unroll
-          for (int q = 0; q < IN_W; ++q) win[q] = __bfloat162float(s_in[((r + i) * IN_W + q) * DW_CH + tx]);
-#pragma unroll
-          for (int j = 0; j < K; ++j)
-#pragma unroll
-            for (int q = 0; q < DW_TILE; ++q) acc[a][j] = fmaf(g[q], win[q + j], acc[a][j]);
-        }
-      }
+        for (int q = 0; q < DW_TW; ++q) acc[j] = fma2(g[q], win[q + j], acc[j]);
     }
   }
-  if (c0 + tx < C) {
+  const int c = c0 + 2 * pr;
+  if (c < C) {
 #pragma unroll
-    for (int a = 0; a < TR; ++a) {
-      const int i = ty + 4 * a;
-      if (i < K) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) red_add_f32(dw + (long long)(c0 + tx) * K * K + i * K + j, acc[a][j]);
-      }
+    for (int j = 0; j < K; ++j) {
+      float a0, a1;
+      unpack2(acc[j], a0, a1);
+      red_add_f32(dw + (long long)c * K * K + ti * K + j, a0);
+      red_add_f32(dw + (long long)(c + 1) * K * K + ti * K + j, a1);
     }
   }
 }

@@ -124,9 +124,7 @@ class S2Attention(nn.Module):
         """mlp2(split_attention(shifts(mlp1(xn)))) + res  (s2_mlp_v2.py:60-69)."""
         sa = self.split_attention
         t = fn.linear(xn, self.mlp1.weight, self.mlp1.bias)                       # [B, H, W, 3C]
-        a = fn_s2.S2v2SumFn.apply(t)                                              # [B, C]
-        hat = fn.linear(fn.linear_gelu(a, sa.mlp1.weight, None), sa.mlp2.weight, None)   # [B, 3C]
-        s = fn_s2.S2v2CombineFn.apply(t, hat)
+        s = fn_s2.S2v2SplitAttentionFn.apply(t, sa.mlp1.weight, sa.mlp2.weight)    # sum -> tiny MLP -> softmax-combine
         return fn.linear(s, self.mlp2.weight, self.mlp2.bias, res)
 
 

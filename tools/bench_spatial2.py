@@ -68,10 +68,20 @@ rec("s2v2 sum bwd (dt write)", bwd_time(lambda: fn_s2.S2v2SumFn.apply(t), t), nt
 rec("s2v2 combine fwd", timeit(lambda: fn_s2.S2v2CombineFn.apply(t.detach(), hat.detach())), nt + nt // 3)
 rec("s2v2 combine bwd (reduce + dt)", bwd_time(lambda: fn_s2.S2v2CombineFn.apply(t, hat), t), nt + nt // 3 + nt // 3 + nt)
 # Hire-MLP-T stage 0 LayerNorm [802816, 64], stage 1 [200704, 128]
-for rows, Cc in ((B * 56 * 56, 64), (B * 28 * 28, 128), (B * 14 * 14, 320)):
+for rows, Cc in ((B * 56 * 56, 64), (B * 28 * 28, 128), (B * 14 * 14, 320), (B * 196, 768)):
     xm = bf(rows, Cc); nm = xm.numel() * 2
     g, be = bf(Cc), bf(Cc)
     rec(f"layernorm fwd [{rows}, {Cc}]", timeit(lambda: ops.layernorm_fwd(xm, g, be)), 2 * nm)
     y, mean, rstd = ops.layernorm_fwd(xm, g, be)
     dy = bf(rows, Cc)
     rec(f"layernorm bwd [{rows}, {Cc}] (+add)", timeit(lambda: ops.layernorm_bwd(dy, xm, mean, rstd, g, add=dy)), 4 * nm)
+# ConvMixer-768/32 (k = 7): depthwise stencil fwd (+bias+GELU, 2 outputs), dgrad + wgrad
+xc = bf(B, 32, 32, 768).requires_grad_(True); nc = xc.numel() * 2
+wd = (bf(768, 1, 7, 7) * 0.1).requires_grad_(True)
+bd = bf(768).requires_grad_(True)
+tdw = timeit(lambda: fn_spatial.DwConvGeluFn.apply(xc.detach(), wd.detach(), bd.detach()), iters=10)
+rec(f"convmixer dwconv 7x7+bias+GELU fwd ({2 * xc.numel() * 49 / tdw / 1e12:.1f} TFLOP/s fp32)", tdw, 3 * nc)
+yc = fn_spatial.DwConvGeluFn.apply(xc, wd, bd)
+dyc = torch.randn_like(yc)
+tbw = timeit(lambda: torch.autograd.grad(yc, (xc, wd, bd), dyc, retain_graph=True), iters=10)
+rec(f"convmixer dwconv bwd (dgelu + dgrad + wgrad + dbias) ({4 * xc.numel() * 49 / tbw / 1e12:.1f} TFLOP/s fp32)", tbw, 6 * nc)
