@@ -38,9 +38,10 @@ PRESETS = {
 }
 METRIC = "images/sec fwd+bwd MLP-Mixer-B/16 224px"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` of tools/one_block.py (B/16 shapes, batch 256):
-# profiles/r01_ncu_full_mixer_block_gemms_v3_summary.csv.  Algorithmic bytes of the wgrad: 77.1 + 308.3 MB in, 9.4 MB out.
-NCU_TRAFFIC_BYTES = {"chan_wgrad": 398.7e6, "chan_dgrad1": 376.2e6, "chan_fc2_resid": 460.6e6, "chan_fc1_gelu": 640.5e6,
-                     "chan_dgrad2_dgelu": 663.9e6}
+# profiles/r01_ncu_full_mixer_block_v11_summary.csv.  Algorithmic bytes of the channel wgrad: 77.1 + 308.3 MB in, 9.4 MB out.
+NCU_TRAFFIC_BYTES = {"chan_wgrad": 402.7e6, "chan_dgrad1": 376.4e6, "chan_fc2_resid": 465.0e6, "chan_fc1_gelu": 644.8e6,
+                     "chan_dgrad2_dgelu": 669.1e6, "tok_fc1_gelu": 639.7e6, "tok_fc2_resid": 443.5e6,
+                     "tok_dgrad2_dgelu": 681.2e6, "tok_dgrad1": 365.9e6, "tok_wgrad": 392.1e6}
 
 
 def peaks():
@@ -367,9 +368,9 @@ def main():
         except Exception as e:
             line["eager_torch_bf16"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ips, secs = cpu_port_images_per_s(args.model, 16, 2)
+        ips, secs = cpu_port_images_per_s(args.model, 32, 4)
         line["cpu_baseline"] = {"value": round(ips, 3), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"2 timed fwd+bwd steps of batch 16 (1 warm-up), oracle/restate.py fp32, {secs:.1f} s"}
+                                "sample": f"4 timed fwd+bwd steps of batch 32 (1 warm-up), oracle/restate.py fp32, {secs:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -173,7 +173,9 @@ class PatchEmbed(nn.Module):
         B, C, H, W = x.shape
         assert H == self.img_size[0] and W == self.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.img_size[0]}*{self.img_size[1]})."
-        x = self.proj(x).permute(0, 2, 3, 1).contiguous()   # stem conv stays on cuDNN; rows from here on
+        # stem conv stays on cuDNN, fed channels-last so that it runs its NHWC kernel directly and the permute below is a
+        # view (an NCHW input costs cuDNN's own nchwToNhwc pass plus a strided copy of the [B, C, H/4, W/4] output)
+        x = self.proj(x.contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1).contiguous()
         if self.norm is not None:
             x = _gn(self.norm, x)
         return x

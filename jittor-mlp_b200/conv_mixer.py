@@ -51,7 +51,7 @@ class ConvMixer(nn.Module):
 
     def forward(self, x):
         self._bn_buffers_fp32()
-        x = self.embedding(x)                               # stem: cuDNN conv + GELU + BatchNorm (torch)
+        x = self.embedding(x.contiguous(memory_format=torch.channels_last))   # stem: cuDNN conv + GELU + BatchNorm (torch), NHWC
         x = x.permute(0, 2, 3, 1).contiguous()              # channels-last rows from here on
         for blk in self.blocks:
             dw, bn1 = blk[0].fn[0], blk[0].fn[2]

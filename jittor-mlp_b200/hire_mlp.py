@@ -5,6 +5,7 @@ keys).  Quirks preserved: a FULL extra region is padded when H is
 the region gather is strided (hire_mlp.py:58,69), the last stage builds an unused ``patch_merge`` (hire_mlp.py:159-163).
 """
 from einops.layers.torch import Rearrange, Reduce
+import torch
 from torch import nn
 
 from . import fn, fn_spatial
@@ -130,7 +131,7 @@ class HireMLP(nn.Module):
                                       nn.Linear(d_model[-1], num_classes))
 
     def forward(self, x):
-        embedding = self.patcher(x)
+        embedding = self.patcher(x.contiguous(memory_format=torch.channels_last))   # cuDNN NHWC kernel, no layout passes
         embedding = embedding.permute(0, 2, 3, 1)
         for layer in self.layers:
             embedding = layer(embedding)

@@ -6,6 +6,7 @@ in-place overlapping slice copies (s2_mlp_v1.py:21-24, s2_mlp_v2.py:17-28) are u
 repeatable; its autograd backward and its Jittor twin both define the clone semantics used here.
 """
 from einops.layers.torch import Reduce
+import torch
 from torch import nn
 
 from . import fn, fn_s2
@@ -84,7 +85,8 @@ class S2MLPv1(nn.Module):
         self.mlp_head = nn.Sequential(Reduce('b c h w -> b c', 'mean'), nn.Linear(d_model[-1], num_classes))
 
     def forward(self, x):
-        return self.mlp_head(self.stages(x))
+        # channels-last input: the stage convs (cuDNN) run their NHWC kernels and the block-side permutes are views
+        return self.mlp_head(self.stages(x.contiguous(memory_format=torch.channels_last)))
 
 
 def S2MLPv1_deep(num_classes: int = 1000, **kwargs):
@@ -173,4 +175,5 @@ class S2MLPv2(nn.Module):
         self.mlp_head = nn.Sequential(Reduce('b c h w -> b c', 'mean'), nn.Linear(d_model[-1], num_classes))
 
     def forward(self, x):
-        return self.mlp_head(self.stages(x))
+        # channels-last input: the stage convs (cuDNN) run their NHWC kernels and the block-side permutes are views
+        return self.mlp_head(self.stages(x.contiguous(memory_format=torch.channels_last)))
