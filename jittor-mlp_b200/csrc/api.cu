@@ -466,13 +466,15 @@ int vmlp_colsum(const void* a, int64_t a_ld, const void* b, int64_t b_ld, float*
   if (!aligned16(a) || (a_ld % 8) || (b && (!aligned16(b) || (b_ld % 8)))) return fail(VMLP_EALIGN, "colsum alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const DeviceInfo& dv = device_info();
-  if (a_ld == C && (!b || b_ld == C) && C <= 8 * RW_THREADS) {
+  if (C <= 8 * RW_THREADS) {
     const int rpb = RW_THREADS / (C / 8);
-    long long gx = (rows + 4LL * rpb - 1) / (4LL * rpb);
-    const long long cap = (long long)dv.sms * 8;
+    // >= 16 rows per thread, so that the block's setup and its C global atomics stay small next to its streaming work
+    long long gx = (rows + 16LL * rpb - 1) / (16LL * rpb);
+    const long long cap = (long long)dv.sms * 6;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    colsum_flat_kernel<0><<<(unsigned)gx, RW_THREADS, (size_t)C * sizeof(float), st>>>((cbf)a, (cbf)b, out, nullptr, rows, C);
+    colsum_flat_kernel<0><<<(unsigned)gx, RW_THREADS, (size_t)rpb * C * sizeof(float), st>>>((cbf)a, a_ld, (cbf)b, b_ld, out,
+                                                                                          nullptr, rows, C);
     CUDA_OK(cudaGetLastError());
     ++g_launches;
     return VMLP_OK;
@@ -494,11 +496,12 @@ int vmlp_colsum2(const void* a, const void* b, float* out_a, float* out_ab, int6
   if (!aligned16(a) || !aligned16(b)) return fail(VMLP_EALIGN, "colsum2 alignment");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rpb = RW_THREADS / (C / 8);
-  long long gx = (rows + 4LL * rpb - 1) / (4LL * rpb);
-  const long long cap = (long long)device_info().sms * 8;
+  long long gx = (rows + 16LL * rpb - 1) / (16LL * rpb);
+  const long long cap = (long long)device_info().sms * 6;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  colsum_flat_kernel<1><<<(unsigned)gx, RW_THREADS, 2 * (size_t)C * sizeof(float), st>>>((cbf)a, (cbf)b, out_a, out_ab, rows, C);
+  colsum_flat_kernel<1><<<(unsigned)gx, RW_THREADS, 2 * (size_t)rpb * C * sizeof(float), st>>>((cbf)a, C, (cbf)b, C, out_a, out_ab,
+                                                                                               rows, C);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

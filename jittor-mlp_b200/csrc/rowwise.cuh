@@ -387,19 +387,18 @@ colsum_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bf
   }
 }
 
-// Contiguous rows (ld == C, C <= 2048): thread t owns channel vector (t % nvec) of row slot (t / nvec), so a block streams
-// whole rows fully coalesced whatever C is (the slab kernel above keeps 20 of 32 lanes idle at C = 96) and keeps four
-// 16-byte loads per operand in flight.
+// Rows of C <= 2048 channels (any row stride): thread t owns channel vector (t % nvec) of row slot (t / nvec), so a
+// block streams whole rows fully coalesced whatever C is (the slab kernel above keeps 20 of 32 lanes idle at C = 96) and
+// keeps four 16-byte loads per operand in flight.  Block reduction: per-slot partials in shared memory, summed by one
+// thread per column (shared-memory float atomics serialise; with ~10 us of work per block they dominated).
 // DUAL = 1: out[c] += sum_r a[r, c] AND out2[c] += sum_r a[r, c] * b[r, c] in the same pass -- the two BatchNorm
 // statistics (sum, sum of squares with b == a; sum dy, sum dy * a in backward) read each tensor once instead of twice.
 template <int DUAL>
 __global__ void __launch_bounds__(RW_THREADS)
-colsum_flat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, float* __restrict__ out,
-                   float* __restrict__ out2, long long rows, int C) {
-  extern __shared__ float shc[];          // [(1 + DUAL) * C]
+colsum_flat_kernel(const __nv_bfloat16* __restrict__ a, long long a_ld, const __nv_bfloat16* __restrict__ b,
+                   long long b_ld, float* __restrict__ out, float* __restrict__ out2, long long rows, int C) {
+  extern __shared__ float shc[];          // [(1 + DUAL)][rpb][C]
   const int nvec = C >> 3;
-  for (int i = threadIdx.x; i < (1 + DUAL) * C; i += RW_THREADS) shc[i] = 0.f;
-  __syncthreads();
   const int rpb = RW_THREADS / nvec;      // rows per block iteration
   const int cv = threadIdx.x % nvec, ro = threadIdx.x / nvec;
   const bool same = DUAL && (a == b);
@@ -419,33 +418,40 @@ colsum_flat_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __r
   if (ro < rpb) {
     const long long step = (long long)gridDim.x * rpb;
     long long r = (long long)blockIdx.x * rpb + ro;
+    const __nv_bfloat16* pa = a + cv * 8;
+    const __nv_bfloat16* pb = b ? b + cv * 8 : nullptr;
     for (; r + 3 * step < rows; r += 4 * step) {
       uint4 va[4], vb[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        va[u] = ldg_nc_v4(a + ((r + u * step) * nvec + cv) * 8);
+        va[u] = ldg_nc_v4(pa + (r + u * step) * a_ld);
         vb[u] = va[u];
-        if (b && !same) vb[u] = ldg_nc_v4(b + ((r + u * step) * nvec + cv) * 8);
+        if (b && !same) vb[u] = ldg_nc_v4(pb + (r + u * step) * b_ld);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) accumulate(va[u], vb[u]);
     }
     for (; r < rows; r += step) {
-      const uint4 va = ldg_nc_v4(a + (r * nvec + cv) * 8);
+      const uint4 va = ldg_nc_v4(pa + r * a_ld);
       uint4 vb = va;
-      if (b && !same) vb = ldg_nc_v4(b + (r * nvec + cv) * 8);
+      if (b && !same) vb = ldg_nc_v4(pb + r * b_ld);
       accumulate(va, vb);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&shc[cv * 8 + e], acc[e]);
-      if (DUAL) atomicAdd(&shc[C + cv * 8 + e], acc2[e]);
+      shc[ro * C + cv * 8 + e] = acc[e];
+      if (DUAL) shc[(rpb + ro) * C + cv * 8 + e] = acc2[e];
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += RW_THREADS) {
-    red_add_f32(out + i, shc[i]);
-    if (DUAL) red_add_f32(out2 + i, shc[C + i]);
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < rpb; ++k) {
+      s1 += shc[k * C + i];
+      if (DUAL) s2 += shc[(rpb + k) * C + i];
+    }
+    red_add_f32(out + i, s1);
+    if (DUAL) red_add_f32(out2 + i, s2);
   }
 }
 

@@ -11,23 +11,33 @@ import torch
 
 
 class GraphedStep:
-    """loss = loss_fn(model(x)); loss.backward() as one CUDA graph.  Gradients land in ``p.grad`` (static tensors)."""
+    """loss = loss_fn(model(x)); loss.backward() as one CUDA graph.  Gradients land in ``p.grad`` (static tensors).
 
-    def __init__(self, model, example_x, loss_fn, warmup=3):
+    ``step_fn(x) -> loss`` replaces the default body; the data-parallel step (``dp.DataParallel.step_fwd_bwd``: the same
+    fwd+bwd with the per-block NCCL gradient all-reduces enqueued from inside backward) is captured this way, so an
+    N-GPU step is one graph launch per rank too.  NCCL's watchdog thread touches CUDA while we capture, hence the
+    thread-local capture mode.
+    """
+
+    def __init__(self, model, example_x, loss_fn, warmup=3, step_fn=None):
         self.model, self.loss_fn = model, loss_fn
         self.static_x = example_x.clone()
+        if step_fn is None:
+            def step_fn(x):
+                loss = loss_fn(model(x))
+                loss.backward()
+                return loss
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                      # warm-up off the default stream (allocator, lazy inits)
             for _ in range(warmup):
                 model.zero_grad(set_to_none=True)
-                loss_fn(model(self.static_x)).backward()
+                step_fn(self.static_x)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         model.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.static_loss = loss_fn(model(self.static_x))
-            self.static_loss.backward()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.static_loss = step_fn(self.static_x)
 
     def run(self, x=None, non_blocking=True):
         if x is not None:
