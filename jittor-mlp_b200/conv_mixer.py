@@ -17,13 +17,13 @@ class Residual(nn.Module):
         self.fn = fn_
 
 
-def _bn(a, bn, res=None):
+def _bn(a, bn, res=None, link=None):
     if bn.training:
         if bn.track_running_stats:
             bn.num_batches_tracked += 1
         mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
         return fn_spatial.BatchNormFn.apply(a, bn.weight, bn.bias, bn.running_mean if bn.track_running_stats else None,
-                                            bn.running_var if bn.track_running_stats else None, mom, bn.eps, res)
+                                            bn.running_var if bn.track_running_stats else None, mom, bn.eps, res, link)
     return fn_spatial.batch_norm_eval(a, bn, res)
 
 
@@ -55,8 +55,10 @@ class ConvMixer(nn.Module):
         x = x.permute(0, 2, 3, 1).contiguous()              # channels-last rows from here on
         for blk in self.blocks:
             dw, bn1 = blk[0].fn[0], blk[0].fn[2]
-            a = fn_spatial.DwConvGeluFn.apply(x, dw.weight, dw.bias)
-            x = _bn(a, bn1, x)                              # BN(GELU(dwconv(x))) + x   (conv_mixer.py:23-26)
-            a = fn.linear_gelu(x, blk[1].weight, blk[1].bias)
-            x = _bn(a, blk[3])                              # BN(GELU(conv1x1(x)))      (conv_mixer.py:28-31)
+            # each GELU output feeds exactly one BatchNorm: its backward also applies gelu' (fn.GeluLink)
+            l1, l2 = fn.GeluLink(), fn.GeluLink()
+            a = fn_spatial.DwConvGeluFn.apply(x, dw.weight, dw.bias, l1)
+            x = _bn(a, bn1, x, l1)                          # BN(GELU(dwconv(x))) + x   (conv_mixer.py:23-26)
+            a = fn.linear_gelu(x, blk[1].weight, blk[1].bias, l2)
+            x = _bn(a, blk[3], None, l2)                    # BN(GELU(conv1x1(x)))      (conv_mixer.py:28-31)
         return self.classifier[2](x.mean(dim=(1, 2)))

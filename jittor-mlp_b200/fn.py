@@ -63,11 +63,22 @@ class LinearFn(torch.autograd.Function):
         return dx, gw, gb, (dy if ctx.has_res else None)
 
 
+class GeluLink:
+    """Hand-shake between a (conv, GELU) producer and the BatchNorm that is its ONLY consumer (conv_mixer.py:23-32).
+    The producer publishes its saved gelu'(z); a BatchNorm that accepts the link multiplies it into its own backward
+    pass (``vmlp_chan_lin`` with the z operand), so the gradient the producer receives is already d(pre-activation)
+    and the separate read-multiply-write pass over the activation disappears."""
+    __slots__ = ("gp", "fused")
+
+    def __init__(self):
+        self.gp, self.fused = None, False
+
+
 class LinearGeluFn(torch.autograd.Function):
     """y = gelu(x W^T + b); the pre-activation is kept for backward."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, link=None):
         _chk(x, "x"); _chk(w, "w"); _chk(b, "b")
         x2, w2 = _rows(x), _w2d(w)
         R, Ci, Co = x2.shape[0], x2.shape[1], w2.shape[0]
@@ -76,6 +87,9 @@ class LinearGeluFn(torch.autograd.Function):
         gemm(R, Co, Ci, operand(x2, 0), operand(w2, 0), L.EPI_GELU, D=z, D2=_rows(y), bias=b, bias_mode=1)
         ctx.save_for_backward(x, w, z)
         ctx.has_b = b is not None
+        ctx.link = link
+        if link is not None:
+            link.gp = z                     # z holds gelu'(pre-activation)
         return y
 
     @staticmethod
@@ -84,12 +98,15 @@ class LinearGeluFn(torch.autograd.Function):
         dy = dy.contiguous()
         x2, w2, dy2 = _rows(x), _w2d(w), _rows(dy)
         R, Ci, Co = x2.shape[0], x2.shape[1], w2.shape[0]
-        dz = _new(R, Co, like=x)
-        L.check(L.lib().vmlp_dgelu_mul(dy2.data_ptr(), Co, z.data_ptr(), Co, dz.data_ptr(), Co, R, Co, L.stream_ptr()))
+        if ctx.link is not None and ctx.link.fused:
+            dz = dy2                        # the consumer's backward already multiplied by gelu'
+        else:
+            dz = _new(R, Co, like=x)
+            L.check(L.lib().vmlp_dgelu_mul(dy2.data_ptr(), Co, z.data_ptr(), Co, dz.data_ptr(), Co, R, Co, L.stream_ptr()))
         dx = torch.empty_like(x)
         gemm(R, Ci, Co, operand(dz, 0), operand(w2, 1), L.EPI_STORE, D=_rows(dx))
         gw, gb = _param_grads(dz, x2, w, w.new_empty(Co) if ctx.has_b else None)
-        return dx, gw, gb
+        return dx, gw, gb, None
 
 
 class MlpFn(torch.autograd.Function):
@@ -228,8 +245,8 @@ def linear(x, w, b=None, res=None):
     return LinearFn.apply(x, w, b, res)
 
 
-def linear_gelu(x, w, b=None):
-    return LinearGeluFn.apply(x, w, b)
+def linear_gelu(x, w, b=None, link=None):
+    return LinearGeluFn.apply(x, w, b, link)
 
 
 def mlp(x, w1, b1, w2, b2, res=None):

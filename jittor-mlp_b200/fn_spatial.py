@@ -64,7 +64,7 @@ class DwConvGeluFn(torch.autograd.Function):
     """a = gelu(depthwise_conv_kxk(x) + bias), padding "same" (conv_mixer.py:24-25); x: [B, H, W, C]."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, link=None):
         _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias")
         B, H, W, C = x.shape
         K = weight.shape[-1]
@@ -72,6 +72,9 @@ class DwConvGeluFn(torch.autograd.Function):
         L.check(L.lib().vmlp_dwconv_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), z.data_ptr(), a.data_ptr(), B, H, W,
                                         C, K, L.stream_ptr()))
         ctx.save_for_backward(x, weight, z)
+        ctx.link = link
+        if link is not None:
+            link.gp = z                     # z holds gelu'(pre-activation), see fn.GeluLink
         return a
 
     @staticmethod
@@ -81,15 +84,18 @@ class DwConvGeluFn(torch.autograd.Function):
         K = weight.shape[-1]
         da = da.contiguous()
         lib = L.lib()
-        dz = torch.empty_like(x)
-        L.check(lib.vmlp_dgelu_mul(da.data_ptr(), C, z.data_ptr(), C, dz.data_ptr(), C, B * H * W, C, L.stream_ptr()))
+        if ctx.link is not None and ctx.link.fused:
+            dz = da                         # the BatchNorm backward already multiplied by gelu'
+        else:
+            dz = torch.empty_like(x)
+            L.check(lib.vmlp_dgelu_mul(da.data_ptr(), C, z.data_ptr(), C, dz.data_ptr(), C, B * H * W, C, L.stream_ptr()))
         dx = torch.empty_like(x)
         L.check(lib.vmlp_dwconv_dgrad(dz.data_ptr(), weight.data_ptr(), dx.data_ptr(), B, H, W, C, K, L.stream_ptr()))
         g = _f32(C * K * K + C, x.device)
         L.check(lib.vmlp_dwconv_wgrad(x.data_ptr(), dz.data_ptr(), g.data_ptr(), B, H, W, C, K, L.stream_ptr()))
         colsum_into(g[C * K * K:], dz.view(-1, C))
         gb = cast_f32_to_bf16(g)
-        return dx, gb[:C * K * K].view(weight.shape), gb[C * K * K:]
+        return dx, gb[:C * K * K].view(weight.shape), gb[C * K * K:], None
 
 
 def _colsum2(out_a, out_ab, a2d, b2d):
@@ -108,7 +114,7 @@ class BatchNormFn(torch.autograd.Function):
     running-stat update with momentum and the unbiased variance (conv_mixer.py:20,27,31)."""
 
     @staticmethod
-    def forward(ctx, a, gamma, beta, running_mean, running_var, momentum, eps, res):
+    def forward(ctx, a, gamma, beta, running_mean, running_var, momentum, eps, res, link=None):
         _chk(a, "a"); _chk(gamma, "gamma"); _chk(beta, "beta"); _chk(res, "res")
         C = a.shape[-1]
         R = a.numel() // C
@@ -129,13 +135,18 @@ class BatchNormFn(torch.autograd.Function):
         L.check(lib.vmlp_chan_lin(a.data_ptr(), res.data_ptr() if res is not None else 0, 0, A.data_ptr(),
                                   ones.data_ptr() if ones is not None else 0, Cc.data_ptr(), y.data_ptr(), R, C,
                                   L.stream_ptr()))
-        ctx.save_for_backward(a, gamma, mean, rstd)
+        gp = None
+        if link is not None and link.gp is not None and link.gp.shape == a.shape:
+            gp = link.gp                    # `a` is gelu(z) of the linked producer and feeds only this BatchNorm
+            link.fused = True
+        ctx.save_for_backward(a, gamma, mean, rstd, *([gp] if gp is not None else []))
         ctx.has_res = res is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        a, gamma, mean, rstd = ctx.saved_tensors
+        a, gamma, mean, rstd = ctx.saved_tensors[:4]
+        gp = ctx.saved_tensors[4] if len(ctx.saved_tensors) > 4 else None
         C = a.shape[-1]
         R = a.numel() // C
         dy = dy.contiguous()
@@ -147,10 +158,11 @@ class BatchNormFn(torch.autograd.Function):
                                      A.data_ptr(), Bq.data_ptr(), Cc.data_ptr(), dg.data_ptr(), db.data_ptr(), R, C,
                                      L.stream_ptr()))
         da = torch.empty_like(a)
-        L.check(lib.vmlp_chan_lin(dy.data_ptr(), a.data_ptr(), 0, A.data_ptr(), Bq.data_ptr(), Cc.data_ptr(),
-                                  da.data_ptr(), R, C, L.stream_ptr()))
+        # linked producer: da * gelu'(z) in the same pass, i.e. the gradient w.r.t. the producer's pre-activation
+        L.check(lib.vmlp_chan_lin(dy.data_ptr(), a.data_ptr(), gp.data_ptr() if gp is not None else 0, A.data_ptr(),
+                                  Bq.data_ptr(), Cc.data_ptr(), da.data_ptr(), R, C, L.stream_ptr()))
         g = cast_f32_to_bf16(st[5 * C:])
-        return da, g[:C], g[C:], None, None, None, None, (dy if ctx.has_res else None)
+        return da, g[:C], g[C:], None, None, None, None, (dy if ctx.has_res else None), None
 
 
 def batch_norm_eval(a, bn, res=None):
