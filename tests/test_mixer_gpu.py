@@ -35,15 +35,17 @@ def test_against_reference_golden(golden, name):
         assert err < 3 * TOL or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * float(fx["dx"].abs().max() + 1), (k, err)
 
 
-def test_block_against_oracle_b16_shapes():
-    """One block at the Mixer-B/16 shapes (N 196, C 768, Ds 784, Dc 3072), batch 4; fwd and all gradients."""
+@pytest.mark.parametrize("C,batch", [(768, 4), (1024, 2)])
+def test_block_against_oracle_b16_shapes(C, batch):
+    """One block at the Mixer-B/16 (N 196, C 768, Ds 784, Dc 3072) and L/16 (C 1024, Dc 4096) shapes; fwd and all
+    gradients (the output-bias gradients come out of the fused LayerNorm-backward pass)."""
     torch.manual_seed(0)
-    m = J.MLPMixer(196, 768, 1)
+    m = J.MLPMixer(196, C, 1)
     with torch.no_grad():
         for p in m.parameters():
             p.add_(0.05 * torch.randn_like(p))
     sd = {k: v.detach().clone().bfloat16().float().requires_grad_(True) for k, v in m.state_dict().items()}
-    x = torch.randn(4, 196, 768, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    x = torch.randn(batch, 196, C, generator=torch.Generator().manual_seed(1)).bfloat16().float()
     xr = x.clone().requires_grad_(True)
     ref = restate.mixer_block(sd, "model.0.", xr)
     dy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2)).bfloat16().float()
