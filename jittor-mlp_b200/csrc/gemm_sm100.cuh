@@ -1,6 +1,6 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:
-//   TMA (128B-swizzled tiles) -> mbarrier ring -> tcgen05.mma (cta_group::1, 128xBNx16)
-//   -> double-buffered TMEM accumulators -> fused epilogue -> per-warp TMA store / fp32 red.add.
+//   TMA (128B-swizzled tiles) -> mbarrier ring -> tcgen05.mma (cta_group::1: 128 x BN x 16, or cta_group::2: a CTA pair
+//   on a 256 x 256 tile) -> double-buffered TMEM accumulators -> fused epilogue -> per-warp TMA store / fp32 red.add.
 //
 //   D[b][m, n] = epilogue( sum_k A[b][m, k] * B[b][n, k] )
 //
@@ -9,13 +9,13 @@
 // directly as MN-major operands, so no permute/transposed copy is ever materialised
 // (reference: the Conv1d(k=1)-over-tokens trick, models_pytorch/mlp_mixer.py:34,37).
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM owner + MMA issuer
-// (one lane), warps 2..9 = epilogue.  A warp may only read the TMEM lane quarter (warp_idx % 4),
-// so two warps share each 32-row quarter and split the 64-column chunks between them
-// (even / odd chunks).  Every epilogue warp is an independent pipeline: it owns two 4 KB staging
-// buffers, issues its own TMA stores (box 64 cols x 32 rows) and prefetches the auxiliary
-// operand (residual / saved pre-activation / gate) of its NEXT work item into registers before
-// doing the math of the current one -- no block-level barrier anywhere in the steady state.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (both run warp-convergent loops of a
+// few dozen instructions per k-block and issue under elect.sync), warps 2..17 = epilogue.  A warp may only read the TMEM
+// lane quarter (warp_idx % 4), so four warps share each 32-row quarter and own one 64-column chunk of the tile each.
+// Every epilogue warp is an independent pipeline: it owns one or two 2 KB staging buffers (32 rows x 32 columns,
+// SWIZZLE_64B), issues its own TMA stores, and fetches the auxiliary operand (residual: register prefetch one step ahead;
+// saved gelu' / gate: per-warp TMA into the idle staging buffer, L2-prefetched by the producer one tile ahead) -- no
+// block-level barrier anywhere in the steady state.  DESIGN.md section 4.1 has the measurements behind each choice.
 #pragma once
 #include "ptx.cuh"
 

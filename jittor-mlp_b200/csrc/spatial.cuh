@@ -15,13 +15,6 @@ struct ShiftTable {
   int dh[8];
   int dw[8];
 };
-__device__ __forceinline__ int shift_group(const ShiftTable& t, int c) {
-  int g = 0;
-#pragma unroll
-  for (int i = 1; i < 8; ++i)
-    if (i < t.ngroups && c >= t.start[i]) g = i;
-  return g;
-}
 
 // MODE 0: zero padding  out[h, w] = in[h + dh, w + dw] (0 outside)        -- AS-MLP Shift (shift_cuda.py:44-72);
 //                        its adjoint is the same gather with negated offsets (shift_cuda.py:75-103).
