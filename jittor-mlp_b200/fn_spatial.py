@@ -4,7 +4,7 @@ import ctypes
 import torch
 
 from . import _lib as L
-from .ops import BF16, _chk, _f32, _new, cast_f32_to_bf16, colsum_into
+from .ops import BF16, _chk, _f32, _new, cast_f32_to_bf16, colsum2_into, colsum_into
 
 
 def _hire_dims(x, h, w, step_h, step_w):
@@ -98,17 +98,6 @@ class DwConvGeluFn(torch.autograd.Function):
         return dx, gb[:C * K * K].view(weight.shape), gb[C * K * K:], None
 
 
-def _colsum2(out_a, out_ab, a2d, b2d):
-    """out_a += column sums of a, out_ab += column sums of a * b (one read of each tensor)."""
-    R, C = a2d.shape
-    if C <= 2048 and a2d.is_contiguous() and b2d.is_contiguous():
-        L.check(L.lib().vmlp_colsum2(a2d.data_ptr(), b2d.data_ptr(), out_a.data_ptr(), out_ab.data_ptr(), R, C,
-                                     L.stream_ptr()))
-    else:
-        colsum_into(out_a, a2d)
-        colsum_into(out_ab, a2d, b2d)
-
-
 class BatchNormFn(torch.autograd.Function):
     """nn.BatchNorm2d in training mode on channels-last rows (+ optional residual): batch statistics over all rows,
     running-stat update with momentum and the unbiased variance (conv_mixer.py:20,27,31)."""
@@ -122,7 +111,7 @@ class BatchNormFn(torch.autograd.Function):
         st = _f32(6 * C, a.device)                 # s1, s2, A, Cc, mean, rstd
         s1, s2, A, Cc, mean, rstd = (st[i * C:(i + 1) * C] for i in range(6))
         a2 = a.view(R, C)
-        _colsum2(s1, s2, a2, a2)                   # sum a, sum a^2 in one pass
+        colsum2_into(s1, s2, a2, a2)                   # sum a, sum a^2 in one pass
         L.check(lib.vmlp_bn_fwd_coef(s1.data_ptr(), s2.data_ptr(), gamma.data_ptr(), beta.data_ptr(), A.data_ptr(),
                                      Cc.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                      running_mean.data_ptr() if running_mean is not None else 0,
@@ -153,7 +142,7 @@ class BatchNormFn(torch.autograd.Function):
         lib = L.lib()
         st = _f32(7 * C, a.device)                 # sdy, sdya, A, Bq, Cc, dgamma, dbeta
         sdy, sdya, A, Bq, Cc, dg, db = (st[i * C:(i + 1) * C] for i in range(7))
-        _colsum2(sdy, sdya, dy.view(R, C), a.view(R, C))   # sum dy, sum dy * a in one pass
+        colsum2_into(sdy, sdya, dy.view(R, C), a.view(R, C))   # sum dy, sum dy * a in one pass
         L.check(lib.vmlp_bn_bwd_coef(sdy.data_ptr(), sdya.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                      A.data_ptr(), Bq.data_ptr(), Cc.data_ptr(), dg.data_ptr(), db.data_ptr(), R, C,
                                      L.stream_ptr()))

@@ -225,6 +225,17 @@ def colsum_into(out, a2d, b2d=None):
                                 out.data_ptr(), rows, C, L.stream_ptr()))
 
 
+def colsum2_into(out_a, out_ab, a2d, b2d):
+    """out_a += column sums of a, out_ab += column sums of a * b, one read of each tensor (vmlp_colsum2)."""
+    R, C = a2d.shape
+    if C <= 2048 and a2d.is_contiguous() and b2d.is_contiguous():
+        L.check(L.lib().vmlp_colsum2(a2d.data_ptr(), b2d.data_ptr(), out_a.data_ptr(), out_ab.data_ptr(), R, C,
+                                     L.stream_ptr()))
+    else:
+        colsum_into(out_a, a2d)
+        colsum_into(out_ab, a2d, b2d)
+
+
 def rowsum_batched_into(out, a3d):
     Bn, M, C = a3d.shape
     L.check(L.lib().vmlp_rowsum_batched(a3d.data_ptr(), out.data_ptr(), Bn, M, C, L.stream_ptr()))
@@ -311,16 +322,17 @@ class ResMLPBlockFn(torch.autograd.Function):
         flat, (g_a1, g_b1a, g_wt, g_bt, g_w1, g_b1, g_w2, g_b2, g_a2, g_b2a, g_g1, g_g2) = _grad_views(params, x.device)
         dy2 = dy.view(R, C)
         # ---- channel half: y = u + gamma_2 * (h W2^T + b2)
-        colsum_into(g_g2, dy2, f2)
+        s_dy = _f32(C, x.device)
+        colsum2_into(s_dy, g_g2, dy2, f2)                  # sum dy (-> d b2 = gamma_2 * sum dy) and d gamma_2 in one pass
+        g_b2.copy_(gamma2.float() * s_dy)
         dF2 = mul_colvec(dy2, gamma2)
         dZ = _new(R, D, like=x)
-        gemm(R, D, C, operand(dF2, 0), operand(w2, 1), L.EPI_DGELU, D=dZ, aux=z)
+        gemm(R, D, C, operand(dF2, 0), operand(w2, 1), L.EPI_DGELU, D=dZ, aux=z,
+             red_out=g_b1, red_mode=1)                      # d b1 = column sums of dZ, fused into the epilogue
         gemm(C, D, R, operand(dF2, 1), operand(h, 1), L.EPI_ATOMIC, out_f32=g_w2.view(C, D))
-        colsum_into(g_b2, dF2)
         du = _new(R, C, like=x)
         gemm(R, C, D, operand(dZ, 0), operand(w1, 1), L.EPI_RESID, D=du, aux=dy2)        # du = dZ W1 + dy
         gemm(D, C, R, operand(dZ, 1), operand(u.view(R, C), 1), L.EPI_ATOMIC, out_f32=g_w1.view(D, C))
-        colsum_into(g_b1, dZ)
         dt = affine_bwd(du, t.view(R, C), alpha2, g_a2, g_b2a)                            # u = t * alpha2 + beta2
         # ---- token half: t = a + gamma_1 * (Wt a + bt)
         colsum_into(g_g1, dt, f1.view(R, C))
