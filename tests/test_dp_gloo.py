@@ -18,8 +18,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _worker(rank, world, port, q, mode):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      VMLP_DP_MODE=mode)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import jittor_mlp_b200 as J
     from jittor_mlp_b200 import dp
@@ -44,11 +45,14 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_gradient_average_matches_single_process_big_batch():
+@pytest.mark.parametrize("mode", ["overlap", "end"])
+def test_two_rank_gradient_average_matches_single_process_big_batch(mode):
+    """Both bucket schedules of dp.DataParallel: reduce each block's bucket as soon as its backward is enqueued
+    ("overlap"), or all buckets back to back after the backward ("end")."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
