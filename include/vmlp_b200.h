@@ -39,8 +39,13 @@ enum {
   VMLP_EWORKSPACE = -5   /* caller-provided workspace too small                     */
 };
 
-/* Library / device introspection. */
+/* Library / device introspection.  VMLP_ABI_VERSION changes whenever a struct or a signature below changes; a binding
+ * checks it together with vmlp_abi_struct_bytes (0 operand, 1 gemm_args, 2 mixer_params, 3 mixer_saved, 4 hire_dims)
+ * before the first call.  vmlp_source_hash: digest of the sources the library was built from (stale-build detection). */
+#define VMLP_ABI_VERSION 2
 int vmlp_abi_version(void);
+const char* vmlp_source_hash(void);
+int vmlp_abi_struct_bytes(int32_t which);
 const char* vmlp_last_error(void);          /* thread-local message for the last failing call */
 int vmlp_device_check(void);                /* VMLP_OK iff current device is compute capability 10.x */
 int vmlp_sm_count(void);
@@ -222,6 +227,28 @@ int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H,
                   vmlp_stream_t stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Fused token-mixing MLP (models_pytorch/mlp_mixer.py:16-27,34,37 -- FeedForward with Conv1d(k=1) over the token axis):
+ *     forward :  u[b]   = x[b] + W2 gelu_erf(W1 xhat[b] + b1) + b2        xhat, x, u : [B, N, C];  W1 [Ds, N], W2 [N, Ds]
+ *     backward:  dxhat[b] = W1^T ((W2^T du[b]) .* gelu_erf'(W1 xhat[b] + b1))
+ * One kernel each: the hidden tensor [B, Ds, C] stays in TMEM / shared memory between the two contractions (forward)
+ * and is recomputed on chip in backward.  Saved / produced for the weight gradients, TRANSPOSED ([B, C, Ds], the layout
+ * the epilogue holds them in):  hT = gelu(..)^T (forward, optional), dzT = d(pre-activation)^T (backward).
+ * Weight operands are K-major copies made by vmlp_tokmix_prepare (w [rows, cols] -> pad [rows, ld] zero-padded and / or
+ * tr [cols, ldt] transposed, zero-padded; either may be NULL):
+ *     w1_pad  = pad(W1)  [Ds, Np]      w2T_pad = tr(W2) [Ds, Np]      w1T = tr(W1) [N, Ds]        Np = ceil8(N)
+ * db1 (fp32 [Ds], optional) += sum over (b, c) of dz.  vmlp_tokmix_supported: N <= 256, Ds <= 1024, C % 8 == Ds % 8 == 0
+ * and the tiles of that shape fit in shared memory; otherwise the caller composes vmlp_gemm_bf16 calls.
+ * ------------------------------------------------------------------------------------------ */
+int vmlp_tokmix_supported(int32_t B, int32_t N, int32_t C, int32_t Ds, int32_t backward);
+int vmlp_tokmix_prepare(const void* w, int32_t rows, int32_t cols, void* pad, int32_t ld, void* tr, int32_t ldt,
+                        vmlp_stream_t stream);
+int vmlp_tokmix_fwd(const void* xhat, const void* x, const void* w1_pad, int32_t Np, const void* w2, const void* b1,
+                    const void* b2, void* u, void* hT, int32_t B, int32_t N, int32_t C, int32_t Ds, vmlp_stream_t stream);
+int vmlp_tokmix_bwd(const void* xhat, const void* du, const void* w1_pad, const void* w2T_pad, int32_t Np,
+                    const void* w1T, const void* b1, void* dxhat, void* dzT, float* db1, int32_t B, int32_t N, int32_t C,
+                    int32_t Ds, vmlp_stream_t stream);
+
+/* --------------------------------------------------------------------------------------------
  * MLP-Mixer block: models_pytorch/mlp_mixer.py:35-40
  *     u = x + TokenFF(LN1(x))   (FeedForward with Conv1d(k=1) over tokens, :16-27,:37)
  *     y = u + ChanFF(LN2(u))    (FeedForward with Linear over channels,    :38)
@@ -238,6 +265,8 @@ typedef struct {
 
 /* Activations the forward pass keeps for backward (caller-allocated, bf16 unless noted):
  *   xhat1 [B,N,C]  z1,h1 [B,Ds,C]  u [B,N,C]  xhat2 [B,N,C]  z2,h2 [B*N,Dc]
+ *   When vmlp_mixer_token_fused(p) != 0 the token half runs as vmlp_tokmix_fwd/_bwd: z1 is not used (may be NULL) and
+ *   h1 holds the transposed hidden activation [B, C, Ds] (same element count).
  *   stats: fp32 [4][B*N] = mean1, rstd1, mean2, rstd2
  *   w1t_pad: bf16 [Ds, ceil8(N)] scratch for the 16-byte-pitch copy of W1t */
 typedef struct {
@@ -246,6 +275,7 @@ typedef struct {
   void* w1t_pad;
 } vmlp_mixer_saved;
 
+int vmlp_mixer_token_fused(const vmlp_mixer_params* p);
 int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, const vmlp_mixer_saved* s,
                          vmlp_stream_t stream);
 

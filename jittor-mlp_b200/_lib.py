@@ -28,12 +28,34 @@ def _sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
 
 
+ABI_VERSION = 2          # == VMLP_ABI_VERSION in include/vmlp_b200.h
+
+
+def source_hash():
+    """Digest of every file the library is built from; baked into the .so (vmlp_source_hash) so that a stale or foreign
+    build is recognised by content -- file times do not survive the copy onto the GPU box."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    for d in deps + [os.path.join(INCLUDE, "vmlp_b200.h")]:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def _built_hash(path):
+    """vmlp_source_hash() of an existing library without binding anything else (None if it cannot be read)."""
+    try:
+        fn = ctypes.CDLL(path).vmlp_source_hash
+        fn.restype = ctypes.c_char_p
+        return fn().decode()
+    except (OSError, AttributeError):
+        return None
+
+
 def _stale():
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "vmlp_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return not os.path.exists(LIB_PATH) or _built_hash(LIB_PATH) != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -42,10 +64,12 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-o", LIB_PATH] + _sources()
+    tmp = LIB_PATH + ".tmp%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, '-DVMLP_SRC_HASH="%s"' % source_hash(), "-o", tmp] + _sources()
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True)
+    os.replace(tmp, LIB_PATH)            # atomic: concurrent ranks never load a half-written library
     return LIB_PATH
 
 
@@ -88,6 +112,8 @@ EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_ATOMIC, EPI_MUL, EPI_GELU_ONLY, E
 _P = ctypes.POINTER
 SYMBOLS = [
     ("vmlp_abi_version", c_int32, []),
+    ("vmlp_source_hash", ctypes.c_char_p, []),
+    ("vmlp_abi_struct_bytes", c_int32, [c_int32]),
     ("vmlp_last_error", ctypes.c_char_p, []),
     ("vmlp_device_check", c_int32, []),
     ("vmlp_sm_count", c_int32, []),
@@ -138,6 +164,13 @@ SYMBOLS = [
     ("vmlp_dwconv_dgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_dwconv_wgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_patchify", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_tokmix_supported", c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32]),
+    ("vmlp_tokmix_prepare", c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
+    ("vmlp_tokmix_fwd", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_tokmix_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_mixer_token_fused", c_int32, [_P(MixerParams)]),
     ("vmlp_mixer_block_fwd", c_int32, [_P(MixerParams), c_void_p, c_void_p, _P(MixerSaved), c_void_p]),
     ("vmlp_mixer_grad_elems", c_int64, [_P(MixerParams)]),
     ("vmlp_mixer_bwd_workspace_elems", c_int64, [_P(MixerParams)]),
@@ -153,20 +186,28 @@ class VmlpError(RuntimeError):
 
 
 def lib():
-    """Load the shared library (building it if the sources are newer).  Raises if unavailable."""
+    """Load the shared library, (re)building it when it is missing or was built from other sources.  Raises if
+    unavailable or if its ABI does not match this binding -- never a fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    explicit = bool(os.environ.get("VMLP_LIB_PATH"))
+    if not explicit and _stale():
         try:
             build()
-        except Exception as e:  # no nvcc on the box and no prebuilt .so: hard error, never a fallback
-            raise VmlpError(f"libvmlp_b200.so is missing and could not be built: {e}") from e
+        except Exception as e:  # no nvcc on the box and no matching prebuilt .so: hard error
+            raise VmlpError(f"libvmlp_b200.so is missing or stale and could not be built: {e}") from e
     handle = ctypes.CDLL(LIB_PATH)
     for name, restype, argtypes in SYMBOLS:
         fn = getattr(handle, name)  # AttributeError if the header and the library disagree
         fn.restype = restype
         fn.argtypes = argtypes
+    if handle.vmlp_abi_version() != ABI_VERSION:
+        raise VmlpError(f"{LIB_PATH}: ABI version {handle.vmlp_abi_version()} != binding {ABI_VERSION}")
+    for which, struct in enumerate((Operand, GemmArgs, MixerParams, MixerSaved, HireDims)):
+        if handle.vmlp_abi_struct_bytes(which) != ctypes.sizeof(struct):
+            raise VmlpError(f"{LIB_PATH}: sizeof({struct.__name__}) = {ctypes.sizeof(struct)} here, "
+                            f"{handle.vmlp_abi_struct_bytes(which)} in the library")
     _lib = handle
     return handle
 

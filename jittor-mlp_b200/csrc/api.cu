@@ -5,6 +5,7 @@
 #include "rowwise.cuh"
 #include "spatial.cuh"
 #include "spatial2.cuh"
+#include "tokmix_sm100.cuh"
 
 #include <cstdarg>
 #include <cstdlib>
@@ -60,14 +61,62 @@ const DeviceInfo& device_info() {
     static DeviceInfo bad;
     return bad;
   }
+  static std::once_flag once[64];
   DeviceInfo& d = info[dev];
-  if (!d.ok) {
+  std::call_once(once[dev], [&] {
     cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
     d.ok = d.sms > 0;
-  }
+  });
   return d;
+}
+
+// ---- process-wide knobs, read once (getenv is not cheap and not re-entrant against setenv)
+struct EnvKnobs {
+  int force_cta_group = 0;   // VMLP_FORCE_CTA_GROUP = 1 | 2 (A/B measurements)
+  bool debug = false;        // VMLP_DEBUG
+  bool tokmix = true;        // VMLP_TOKMIX = 0 keeps the unfused token-mixing GEMM sequence
+};
+const EnvKnobs& env_knobs() {
+  static const EnvKnobs k = [] {
+    EnvKnobs e;
+    if (const char* v = getenv("VMLP_FORCE_CTA_GROUP")) e.force_cta_group = atoi(v) == 2 ? 2 : 1;
+    e.debug = getenv("VMLP_DEBUG") != nullptr;
+    if (const char* v = getenv("VMLP_TOKMIX")) e.tokmix = atoi(v) != 0;
+    return e;
+  }();
+  return k;
+}
+
+// Per-device one-time opt-in to > 48 KB of dynamic shared memory (cudaFuncSetAttribute applies to the CURRENT device
+// only, so the flag is kept per device; atomics make concurrent first calls from several host threads benign -- at
+// worst the attribute is set twice to the same value).
+template <typename K>
+int smem_optin(K kern, int bytes, std::atomic<int>* done_bytes /* [64], zero-initialised */) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (done_bytes[dev].load(std::memory_order_acquire) < bytes) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done_bytes[dev].store(bytes, std::memory_order_release);
+  }
+  return VMLP_OK;
+}
+// Resident blocks per SM of a persistent kernel, cached per device.
+template <typename K>
+int occupancy_cached(K kern, int threads, int smem, std::atomic<int>* occ /* [64] */, int* out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  int v = occ[dev].load(std::memory_order_acquire);
+  if (v == 0) {
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, threads, smem));
+    if (v < 1) v = 1;
+    occ[dev].store(v, std::memory_order_release);
+  }
+  *out = v;
+  return VMLP_OK;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -115,13 +164,8 @@ int launch_gemm_t(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
                   const CUtensorMap& tpf, const GemmParams& p, int grid, cudaStream_t st) {
   auto kern = gemm_bf16_sm100<BN, EPI, CG>;
   using SM = GemmSmem<BN, EPI, CG>;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr_set[dev & 63] = true;
-  }
+  static std::atomic<int> optin[64];
+  if (int rc = smem_optin(kern, SM::TOTAL, optin)) return rc;
   if (CG == 1) {
     kern<<<grid, GEMM_THREADS, SM::TOTAL, st>>>(ta, tb, td, td2, tpf, p);
   } else {
@@ -182,7 +226,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   const long long pad1 = (g.M + 127) / 128 * 128, pad2 = (g.M + 255) / 256 * 256;
   if (cg == 0)
     cg = (bn == 256 && ((one_output && (g.M % 256 == 0 || g.M >= 4096) && g.M >= 512) || (pad1 == pad2 && g.M > 128))) ? 2 : 1;
-  if (const char* e = getenv("VMLP_FORCE_CTA_GROUP")) cg = atoi(e) == 2 ? ((bn == 256) ? 2 : 1) : 1;
+  if (const int f = env_knobs().force_cta_group) cg = (f == 2 && bn == 256) ? 2 : 1;
   if (cg != 1 && cg != 2) return fail(VMLP_EINVAL, "cta_group must be 0, 1 or 2");
   if (cg == 2 && bn != 256) return fail(VMLP_EINVAL, "cta_group 2 needs block_n 256");
 
@@ -348,8 +392,8 @@ int layernorm_bwd_impl(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
       DISPATCH_VPL(C, {
         auto kern = layernorm_bwd_kernel<VPL, 1, 1>;
         const size_t sh = (size_t)RW_WARPS * 24 * VPL * 32 * sizeof(float);
-        static bool done = false;
-        if (!done) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); done = true; }
+        static std::atomic<int> optin[64];
+        if (int rc2 = smem_optin(kern, (int)sh, optin)) return rc2;
         kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
                                            dx_ld, dgamma, dbeta, rows, C, add_colsum, out_rowsum, row_period);
       });
@@ -368,8 +412,8 @@ int layernorm_bwd_impl(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
       DISPATCH_VPL(C, {
         auto kern = layernorm_bwd_kernel<VPL, 1, 0>;
         const size_t sh = (size_t)RW_WARPS * 16 * VPL * 32 * sizeof(float);
-        static bool done = false;
-        if (!done) { CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); done = true; }
+        static std::atomic<int> optin[64];
+        if (int rc2 = smem_optin(kern, (int)sh, optin)) return rc2;
         kern<<<grid, RW_THREADS, sh, st>>>((cbf)dy, dy_ld, (cbf)x, x_ld, mean, rstd, (cbf)gamma, (cbf)add, add_ld, (bf)dx,
                                            dx_ld, dgamma, dbeta, rows, C, nullptr, nullptr, 1);
       });
@@ -384,12 +428,151 @@ int layernorm_bwd_impl(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
   return VMLP_OK;
 }
 
+// ------------------------------------------------------------------------------------------- fused token-mixing MLP
+constexpr int TM_SMEM_MAX = 227 * 1024;
+
+// Fills the shape-derived fields; returns the dynamic shared memory the kernel needs (0 = shape not supported).
+int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
+  memset(&p, 0, sizeof(p));
+  if (B <= 0 || N <= 0 || C <= 0 || Ds <= 0 || (C % 8) || (Ds % 8) || N > 256 || Ds > TM_MAX_DS) return 0;
+  p.B = B; p.N = N; p.C = C; p.Ds = Ds;
+  p.NT = (N + 15) & ~15;
+  p.tiles_c = (C + 127) / 128;
+  p.n_tiles = B * p.tiles_c;
+  p.n_pairs = (p.n_tiles + 1) / 2;
+  p.n_chunks = (Ds + TM_CH - 1) / TM_CH;
+  p.last_n1 = (Ds - (p.n_chunks - 1) * TM_CH + 15) & ~15;
+  p.kf = p.NT / 64;
+  p.tail = p.NT % 64;
+  p.wa_stage = p.kf * 4096 + (p.tail == 16 ? 1024 : p.tail ? 4096 : 0);
+  p.wb_stage = p.NT * 64;
+  p.inv_tiles_c = 1.0f / (float)p.tiles_c;
+  if ((long long)p.n_tiles >= (1ll << 22)) return 0;
+  const int fixed = TM_BAR_BYTES + 1024 /* alignment slack */ + 2 * TM_HTILE + p.NT * 256 * (backward ? 2 : 1) +
+                    p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
+  for (int depth = 4; depth >= 2; --depth) {
+    const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
+    if (fixed + rings <= TM_SMEM_MAX) {
+      p.s_wa = p.s_wb = depth;
+      // never less than half an SM's shared memory: one CTA per SM, so the 512-column TMEM allocation of a CTA pair can
+      // never wait for a co-resident CTA of another pair (allocation order across two SMs could deadlock)
+      return fixed + rings > 120 * 1024 ? fixed + rings : 120 * 1024;
+    }
+  }
+  return 0;
+}
+
+int tokmix_launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const TokParams& p, int smem, cudaStream_t st) {
+  const DeviceInfo& dv = device_info();
+  memset(&cfg, 0, sizeof(cfg));
+  const int clusters = p.n_pairs < dv.sms / 2 ? p.n_pairs : dv.sms / 2;
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(TM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return VMLP_OK;
+}
+
+int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np, const void* w2, const void* b1,
+                    const void* b2, void* u, void* hT, int B, int N, int C, int Ds, cudaStream_t st) {
+  const DeviceInfo& dv = device_info();
+  if (!dv.ok || dv.cc_major != 10) return fail(VMLP_EARCH, "device is not sm_100 (no fallback)");
+  TokParams p;
+  const int smem = tokmix_plan(p, B, N, C, Ds, false);
+  if (!smem) return fail(VMLP_EINVAL, "tokmix_fwd: unsupported shape B %d N %d C %d Ds %d", B, N, C, Ds);
+  if (!xhat || !x || !w1_pad || !w2 || !b1 || !b2 || !u) return fail(VMLP_EINVAL, "tokmix_fwd null pointer");
+  if (Np < N || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_fwd: padded weight pitch %d", Np);
+  p.b1 = (cbf)b1; p.b2 = (cbf)b2; p.resid = (cbf)x; p.out = (bf)u;
+  CUtensorMap tX, tW1, tW1t, tW2, tH, tR;
+  int rc;
+  if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
+  if ((rc = make_map(&tW1, w1_pad, N, Ds, 1, Np, 0, 64, 32))) return rc;
+  if ((rc = make_map(&tW1t, w1_pad, N, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tW2, w2, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
+  if (hT) { if ((rc = make_map(&tH, hT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc; }
+  else tH = tW2;
+  if ((rc = make_map(&tR, x, C, N, B, C, (long long)N * C, C < 128 ? C : 128, p.NT, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  static std::atomic<int> optin[64];
+  if ((rc = smem_optin(tokmix_fwd_sm100, smem, optin))) return rc;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  tokmix_launch_cfg(cfg, attr, p, smem, st);
+  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_fwd_sm100, tX, tW1, tW1t, tW2, tH, tR, p, hT ? 1 : 0));
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const void* w2T_pad, int Np, const void* w1T,
+                    const void* b1, void* dxhat, void* dzT, float* db1, int B, int N, int C, int Ds, cudaStream_t st) {
+  const DeviceInfo& dv = device_info();
+  if (!dv.ok || dv.cc_major != 10) return fail(VMLP_EARCH, "device is not sm_100 (no fallback)");
+  TokParams p;
+  const int smem = tokmix_plan(p, B, N, C, Ds, true);
+  if (!smem) return fail(VMLP_EINVAL, "tokmix_bwd: unsupported shape B %d N %d C %d Ds %d", B, N, C, Ds);
+  if (!xhat || !du || !w1_pad || !w2T_pad || !w1T || !b1 || !dxhat || !dzT) return fail(VMLP_EINVAL, "tokmix_bwd null pointer");
+  if (Np < N || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_bwd: padded weight pitch %d", Np);
+  p.b1 = (cbf)b1; p.out = (bf)dxhat; p.db1 = db1;
+  CUtensorMap tX, tDU, tW1, tW1t, tW2T, tW2Tt, tW1T, tDZ;
+  int rc;
+  if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
+  if ((rc = make_map(&tDU, du, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
+  if ((rc = make_map(&tW1, w1_pad, N, Ds, 1, Np, 0, 64, 32))) return rc;
+  if ((rc = make_map(&tW1t, w1_pad, N, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tW2T, w2T_pad, N, Ds, 1, Np, 0, 64, 32))) return rc;
+  if ((rc = make_map(&tW2Tt, w2T_pad, N, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tW1T, w1T, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
+  if ((rc = make_map(&tDZ, dzT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc;
+  static std::atomic<int> optin[64];
+  if ((rc = smem_optin(tokmix_bwd_sm100, smem, optin))) return rc;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  tokmix_launch_cfg(cfg, attr, p, smem, st);
+  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_bwd_sm100, tX, tDU, tW1, tW1t, tW2T, tW2Tt, tW1T, tDZ, p));
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+// w [rows, cols] -> pad [rows, ld] and / or tr [cols, ldt] (either may be null)
+int tokmix_prepare_impl(const void* w, int rows, int cols, void* pad, int ld, void* tr, int ldt, cudaStream_t st) {
+  if (!w || rows <= 0 || cols <= 0 || (pad && ld < cols) || (tr && ldt < rows)) return fail(VMLP_EINVAL, "tokmix_prepare args");
+  const long long n = (pad ? (long long)rows * ld : 0) + (tr ? (long long)cols * ldt : 0);
+  if (n == 0) return VMLP_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  tokmix_prepare_kernel<<<(int)blocks, 256, 0, st>>>((cbf)w, rows, cols, (bf)pad, ld, (bf)tr, ldt);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
 }  // namespace
 
 // ============================================================================================ C ABI
 extern "C" {
 
-int vmlp_abi_version(void) { return 1; }
+int vmlp_abi_version(void) { return VMLP_ABI_VERSION; }
+#ifndef VMLP_SRC_HASH
+#define VMLP_SRC_HASH "unknown"
+#endif
+const char* vmlp_source_hash(void) { return VMLP_SRC_HASH; }
+int vmlp_abi_struct_bytes(int32_t which) {
+  switch (which) {
+    case 0: return (int)sizeof(vmlp_operand);
+    case 1: return (int)sizeof(vmlp_gemm_args);
+    case 2: return (int)sizeof(vmlp_mixer_params);
+    case 3: return (int)sizeof(vmlp_mixer_saved);
+    case 4: return (int)sizeof(vmlp_hire_dims);
+  }
+  return -1;
+}
 const char* vmlp_last_error(void) { return g_err; }
 int vmlp_device_check(void) {
   const DeviceInfo& dv = device_info();
@@ -858,22 +1041,17 @@ template <int K, int FLIP, int EPI>
 static int dwconv_launch(const void* x, const void* w, const void* bias, void* o1, void* o2, int B, int H, int W, int C,
                          cudaStream_t st) {
   auto kern = dwconv_kernel<K, FLIP, EPI>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES));
-    attr_done = true;
-  }
+  static std::atomic<int> optin[64];
+  if (int rc0 = smem_optin(kern, DwSmem<K>::BYTES, optin)) return rc0;
   const long long tiles = (long long)B * ((H + DW_TH - 1) / DW_TH) * ((W + DW_TW - 1) / DW_TW);
   if (tiles >= (1 << 22)) return fail(VMLP_EINVAL, "dwconv: too many tiles");
   const int cb = (C + DW_CH - 1) / DW_CH;
   // persistent blocks: the grid must not exceed the resident capacity (asked from the runtime: registers, shared memory
   // and the L1 carve-out decide), or the few blocks of a second wave double the kernel time
-  static int occ = 0;
-  if (occ == 0) {
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DW_THREADS, DwSmem<K>::BYTES));
-    if (occ < 1) occ = 1;
-    if (getenv("VMLP_DEBUG")) fprintf(stderr, "vmlp: dwconv<%d,%d,%d> %d blocks/SM\n", K, FLIP, EPI, occ);
-  }
+  static std::atomic<int> occ_cache[64];
+  int occ = 1;
+  if (int rc0 = occupancy_cached(kern, DW_THREADS, DwSmem<K>::BYTES, occ_cache, &occ)) return rc0;
+  if (env_knobs().debug) fprintf(stderr, "vmlp: dwconv<%d,%d,%d> %d blocks/SM\n", K, FLIP, EPI, occ);
   long long gx = ((long long)device_info().sms * occ) / cb;
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
@@ -888,20 +1066,15 @@ static int dwconv_launch(const void* x, const void* w, const void* bias, void* o
 template <int K>
 static int dwconv_wgrad_launch(const void* x, const void* dz, float* dw, int B, int H, int W, int C, cudaStream_t st) {
   auto kern = dwconv_wgrad_kernel<K>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DwSmem<K>::BYTES_WGRAD));
-    attr_done = true;
-  }
+  static std::atomic<int> optin[64];
+  if (int rc0 = smem_optin(kern, DwSmem<K>::BYTES_WGRAD, optin)) return rc0;
   const long long tiles = (long long)B * ((H + DW_TH - 1) / DW_TH) * ((W + DW_TW - 1) / DW_TW);
   if (tiles >= (1 << 22)) return fail(VMLP_EINVAL, "dwconv: too many tiles");
   const int cb = (C + DW_CH - 1) / DW_CH;
-  static int occ = 0;
-  if (occ == 0) {
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * K, DwSmem<K>::BYTES_WGRAD));
-    if (occ < 1) occ = 1;
-    if (getenv("VMLP_DEBUG")) fprintf(stderr, "vmlp: dwconv_wgrad<%d> %d blocks/SM\n", K, occ);
-  }
+  static std::atomic<int> occ_cache[64];
+  int occ = 1;
+  if (int rc0 = occupancy_cached(kern, 32 * K, DwSmem<K>::BYTES_WGRAD, occ_cache, &occ)) return rc0;
+  if (env_knobs().debug) fprintf(stderr, "vmlp: dwconv_wgrad<%d> %d blocks/SM\n", K, occ);
   long long gx = ((long long)device_info().sms * occ) / cb;
   if (gx < 1) gx = 1;
   if (gx > tiles) gx = tiles;
@@ -968,6 +1141,26 @@ int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H,
   return VMLP_OK;
 }
 
+// ============================================================================================ fused token-mixing MLP
+int vmlp_tokmix_supported(int32_t B, int32_t N, int32_t C, int32_t Ds, int32_t backward) {
+  TokParams p;
+  return tokmix_plan(p, B, N, C, Ds, backward != 0) ? 1 : 0;
+}
+int vmlp_tokmix_prepare(const void* w, int32_t rows, int32_t cols, void* pad, int32_t ld, void* tr, int32_t ldt,
+                        vmlp_stream_t stream) {
+  return tokmix_prepare_impl(w, rows, cols, pad, ld, tr, ldt, static_cast<cudaStream_t>(stream));
+}
+int vmlp_tokmix_fwd(const void* xhat, const void* x, const void* w1_pad, int32_t Np, const void* w2, const void* b1,
+                    const void* b2, void* u, void* hT, int32_t B, int32_t N, int32_t C, int32_t Ds, vmlp_stream_t stream) {
+  return tokmix_fwd_impl(xhat, x, w1_pad, Np, w2, b1, b2, u, hT, B, N, C, Ds, static_cast<cudaStream_t>(stream));
+}
+int vmlp_tokmix_bwd(const void* xhat, const void* du, const void* w1_pad, const void* w2T_pad, int32_t Np,
+                    const void* w1T, const void* b1, void* dxhat, void* dzT, float* db1, int32_t B, int32_t N, int32_t C,
+                    int32_t Ds, vmlp_stream_t stream) {
+  return tokmix_bwd_impl(xhat, du, w1_pad, w2T_pad, Np, w1T, b1, dxhat, dzT, db1, B, N, C, Ds,
+                         static_cast<cudaStream_t>(stream));
+}
+
 // ============================================================================================ MLP-Mixer block
 static int mixer_check(const vmlp_mixer_params* p) {
   if (!p) return fail(VMLP_EINVAL, "null params");
@@ -976,6 +1169,14 @@ static int mixer_check(const vmlp_mixer_params* p) {
   return VMLP_OK;
 }
 static inline int pad8(int n) { return (n + 7) & ~7; }
+// The token-mixing half runs as the fused on-chip kernels (tokmix_sm100.cuh) whenever both directions support the
+// shape; VMLP_TOKMIX=0 (read once) keeps the unfused GEMM sequence for A/B measurements.
+static bool mixer_token_fused(const vmlp_mixer_params* p) {
+  if (!env_knobs().tokmix) return false;
+  TokParams t;
+  return tokmix_plan(t, p->B, p->N, p->C, p->Ds, false) && tokmix_plan(t, p->B, p->N, p->C, p->Ds, true);
+}
+int vmlp_mixer_token_fused(const vmlp_mixer_params* p) { return (p && mixer_check(p) == VMLP_OK && mixer_token_fused(p)) ? 1 : 0; }
 
 int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, const vmlp_mixer_saved* s,
                          vmlp_stream_t stream) {
@@ -997,23 +1198,30 @@ int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, con
     CUDA_OK(cudaGetLastError());
     ++g_launches;
   }
-  {  // Z1[b] [Ds, C] = W1t [Ds, N] * Xhat1[b] [N, C] ; H1 = gelu(Z1)
-    vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(s->w1t_pad, Ds, N, Np, 0, 0),
-                                 opnd(s->xhat1, N, C, C, (long long)N * C, 1), VMLP_EPI_GELU);
-    g.D = s->z1; g.d_ld = C; g.d_bs = (long long)Ds * C;
-    g.D2 = s->h1; g.d2_ld = C; g.d2_bs = (long long)Ds * C;
-    g.bias = p->b1t; g.bias_mode = 2;
-    rc = gemm_impl(g, st);
+  if (mixer_token_fused(p)) {
+    // one kernel: U = X + W2t gelu(W1t Xhat1 + b1t) + b2t; the hidden tensor stays on chip, H^T [B, C, Ds] is saved
+    if (!s->h1) return fail(VMLP_EINVAL, "mixer fwd: h1 buffer missing");
+    rc = tokmix_fwd_impl(s->xhat1, x, s->w1t_pad, Np, p->w2t, p->b1t, p->b2t, s->u, s->h1, B, N, C, Ds, st);
     if (rc) return rc;
-  }
-  {  // U[b] [N, C] = W2t [N, Ds] * H1[b] [Ds, C] + b2t[n] + X[b]
-    vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(p->w2t, N, Ds, Ds, 0, 0),
-                                 opnd(s->h1, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_RESID);
-    g.D = s->u; g.d_ld = C; g.d_bs = (long long)N * C;
-    g.bias = p->b2t; g.bias_mode = 2;
-    g.aux = x; g.aux_ld = C; g.aux_bs = (long long)N * C;
-    rc = gemm_impl(g, st);
-    if (rc) return rc;
+  } else {
+    {  // Z1[b] [Ds, C] = W1t [Ds, N] * Xhat1[b] [N, C] ; H1 = gelu(Z1)
+      vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(s->w1t_pad, Ds, N, Np, 0, 0),
+                                   opnd(s->xhat1, N, C, C, (long long)N * C, 1), VMLP_EPI_GELU);
+      g.D = s->z1; g.d_ld = C; g.d_bs = (long long)Ds * C;
+      g.D2 = s->h1; g.d2_ld = C; g.d2_bs = (long long)Ds * C;
+      g.bias = p->b1t; g.bias_mode = 2;
+      rc = gemm_impl(g, st);
+      if (rc) return rc;
+    }
+    {  // U[b] [N, C] = W2t [N, Ds] * H1[b] [Ds, C] + b2t[n] + X[b]
+      vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(p->w2t, N, Ds, Ds, 0, 0),
+                                   opnd(s->h1, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_RESID);
+      g.D = s->u; g.d_ld = C; g.d_bs = (long long)N * C;
+      g.bias = p->b2t; g.bias_mode = 2;
+      g.aux = x; g.aux_ld = C; g.aux_bs = (long long)N * C;
+      rc = gemm_impl(g, st);
+      if (rc) return rc;
+    }
   }
   // ---- channel mixing: y = u + gelu(LN2(u) W1c^T + b1c) W2c^T + b2c   (rows = B*N tokens)
   rc = vmlp_layernorm_fwd(s->u, C, p->ln2_w, p->ln2_b, s->xhat2, C, mean2, rstd2, R, C, p->eps, stream);
@@ -1048,7 +1256,8 @@ int64_t vmlp_mixer_bwd_workspace_elems(const vmlp_mixer_params* p) {
   const int64_t R = (int64_t)p->B * p->N, C = p->C;
   const int64_t tok = (int64_t)p->Ds * C, chn = (int64_t)p->N * p->Dc;
   const int64_t hid = (int64_t)p->B * (tok > chn ? tok : chn);
-  return hid + 2 * R * C;   // dZ (max of both halves) + dXhat + dU
+  // dZ (max of both halves) + dXhat + dU + the transposed token weights of the fused backward (W2t^T [Ds, Np], W1t^T [N, Ds])
+  return hid + 2 * R * C + (int64_t)p->Ds * pad8(p->N) + (int64_t)pad8(p->N) * p->Ds;
 }
 
 int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* dy, void* dx,
@@ -1072,8 +1281,9 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
   float* g_w2c = g_b1c + Dc;        float* g_b2c = g_w2c + (long long)C * Dc;
   // bf16 workspace
   bf ws = (bf)workspace;
-  const long long hid = vmlp_mixer_bwd_workspace_elems(p) - 2 * R * C;
-  bf dZ = ws; bf dXh = ws + hid; bf dU = dXh + R * C;
+  const long long wtr = (long long)Ds * Np;
+  const long long hid = vmlp_mixer_bwd_workspace_elems(p) - 2 * R * C - 2 * wtr;
+  bf dZ = ws; bf dXh = ws + hid; bf dU = dXh + R * C; bf w2T_pad = dU + R * C; bf w1T = w2T_pad + wtr;
 
   // ================= channel half:  y = u + FF(LN2(u))
   {  // dZ2 = (dY * W2c) .* gelu'(Z2)            [R, Dc];  W2c [C, Dc] is the MN-major B operand
@@ -1103,35 +1313,48 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
   if ((rc = layernorm_bwd_impl(dXh, C, s->u, C, mean2, rstd2, p->ln2_w, dy, C, dU, C, g_ln2w, g_ln2b, R, C,
                                fused_sums ? g_b2c : nullptr, fused_sums ? g_b2t : nullptr, N, stream))) return rc;
 
-  // ================= token half:  u = x + TokenFF(LN1(x))
-  {
-    const long long n = (long long)Ds * Np;
-    pad_rows_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((cbf)p->w1t, (bf)s->w1t_pad, Ds, N, Np);
-    CUDA_OK(cudaGetLastError());
-    ++g_launches;
-  }
-  {  // dZ1[b] [Ds, C] = (W2t^T [Ds, N] * dU[b] [N, C]) .* gelu'(Z1[b]);  W2t [N, Ds] is the MN-major A operand
-    vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(p->w2t, N, Ds, Ds, 0, 1), opnd(dU, N, C, C, (long long)N * C, 1), VMLP_EPI_DGELU);
-    g.D = dZ; g.d_ld = C; g.d_bs = (long long)Ds * C;
-    g.aux = s->z1; g.aux_ld = C; g.aux_bs = (long long)Ds * C;
-    g.red_out = g_b1t; g.red_mode = 2;            // db1t[m] = sum over (batch, channels) of dZ1: per output row
-    if ((rc = gemm_impl(g, st))) return rc;
-  }
-  {  // dW2t [N, Ds] += sum_b dU[b] [N, C] * H1[b]^T [C, Ds]    (contraction over batch and channels)
-    vmlp_gemm_args g = gemm_args(N, Ds, C, B, opnd(dU, N, C, C, (long long)N * C, 0), opnd(s->h1, Ds, C, C, (long long)Ds * C, 0), VMLP_EPI_ATOMIC);
-    g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds;
-    if ((rc = gemm_impl(g, st))) return rc;
-  }
-  if (!fused_sums && (rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;
-  {  // dXhat1[b] [N, C] = W1t^T [N, Ds] * dZ1[b] [Ds, C];  padded W1t [Ds, Np] as MN-major A
-    vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(s->w1t_pad, Ds, N, Np, 0, 1), opnd(dZ, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_STORE);
-    g.D = dXh; g.d_ld = C; g.d_bs = (long long)N * C;
-    if ((rc = gemm_impl(g, st))) return rc;
-  }
-  {  // dW1t [Ds, N] += sum_b dZ1[b] [Ds, C] * Xhat1[b]^T [C, N]
-    vmlp_gemm_args g = gemm_args(Ds, N, C, B, opnd(dZ, Ds, C, C, (long long)Ds * C, 0), opnd(s->xhat1, N, C, C, (long long)N * C, 0), VMLP_EPI_ATOMIC);
-    g.contract_batch = 1; g.out_f32 = g_w1t; g.out_ld = N;
-    if ((rc = gemm_impl(g, st))) return rc;
+  // ================= token half:  u = x + TokenFF(LN1(x))      (the padded W1t copy of the forward pass is reused)
+  if (mixer_token_fused(p)) {
+    // K-major transposed weight copies, then ONE kernel for the data-gradient chain (Z recomputed on chip):
+    // dXhat1 = W1t^T ((W2t^T dU) .* gelu'(W1t Xhat1 + b1t)), dZ^T [B, C, Ds] saved for dW1t, db1t accumulated on the way
+    if ((rc = tokmix_prepare_impl(p->w2t, N, Ds, nullptr, 0, w2T_pad, Np, st))) return rc;
+    if ((rc = tokmix_prepare_impl(p->w1t, Ds, N, nullptr, 0, w1T, Ds, st))) return rc;
+    if ((rc = tokmix_bwd_impl(s->xhat1, dU, s->w1t_pad, w2T_pad, Np, w1T, p->b1t, dXh, dZ, g_b1t, B, N, C, Ds, st))) return rc;
+    {  // dW2t [N, Ds] += sum_b dU[b] [N, C] * H^T[b] [C, Ds]        (B operand MN-major: rows = contraction index c)
+      vmlp_gemm_args g = gemm_args(N, Ds, C, B, opnd(dU, N, C, C, (long long)N * C, 0), opnd(s->h1, C, Ds, Ds, (long long)C * Ds, 1), VMLP_EPI_ATOMIC);
+      g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds;
+      if ((rc = gemm_impl(g, st))) return rc;
+    }
+    if (!fused_sums && (rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;
+    {  // dW1t [Ds, N] += sum_b dZ^T[b]^T [Ds, C] * Xhat1[b]^T [C, N] (A operand MN-major)
+      vmlp_gemm_args g = gemm_args(Ds, N, C, B, opnd(dZ, C, Ds, Ds, (long long)C * Ds, 1), opnd(s->xhat1, N, C, C, (long long)N * C, 0), VMLP_EPI_ATOMIC);
+      g.contract_batch = 1; g.out_f32 = g_w1t; g.out_ld = N;
+      if ((rc = gemm_impl(g, st))) return rc;
+    }
+  } else {
+    {  // dZ1[b] [Ds, C] = (W2t^T [Ds, N] * dU[b] [N, C]) .* gelu'(Z1[b]);  W2t [N, Ds] is the MN-major A operand
+      vmlp_gemm_args g = gemm_args(Ds, C, N, B, opnd(p->w2t, N, Ds, Ds, 0, 1), opnd(dU, N, C, C, (long long)N * C, 1), VMLP_EPI_DGELU);
+      g.D = dZ; g.d_ld = C; g.d_bs = (long long)Ds * C;
+      g.aux = s->z1; g.aux_ld = C; g.aux_bs = (long long)Ds * C;
+      g.red_out = g_b1t; g.red_mode = 2;            // db1t[m] = sum over (batch, channels) of dZ1: per output row
+      if ((rc = gemm_impl(g, st))) return rc;
+    }
+    {  // dW2t [N, Ds] += sum_b dU[b] [N, C] * H1[b]^T [C, Ds]    (contraction over batch and channels)
+      vmlp_gemm_args g = gemm_args(N, Ds, C, B, opnd(dU, N, C, C, (long long)N * C, 0), opnd(s->h1, Ds, C, C, (long long)Ds * C, 0), VMLP_EPI_ATOMIC);
+      g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds;
+      if ((rc = gemm_impl(g, st))) return rc;
+    }
+    if (!fused_sums && (rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;
+    {  // dXhat1[b] [N, C] = W1t^T [N, Ds] * dZ1[b] [Ds, C];  padded W1t [Ds, Np] as MN-major A
+      vmlp_gemm_args g = gemm_args(N, C, Ds, B, opnd(s->w1t_pad, Ds, N, Np, 0, 1), opnd(dZ, Ds, C, C, (long long)Ds * C, 1), VMLP_EPI_STORE);
+      g.D = dXh; g.d_ld = C; g.d_bs = (long long)N * C;
+      if ((rc = gemm_impl(g, st))) return rc;
+    }
+    {  // dW1t [Ds, N] += sum_b dZ1[b] [Ds, C] * Xhat1[b]^T [C, N]
+      vmlp_gemm_args g = gemm_args(Ds, N, C, B, opnd(dZ, Ds, C, C, (long long)Ds * C, 0), opnd(s->xhat1, N, C, C, (long long)N * C, 0), VMLP_EPI_ATOMIC);
+      g.contract_batch = 1; g.out_f32 = g_w1t; g.out_ld = N;
+      if ((rc = gemm_impl(g, st))) return rc;
+    }
   }
   // dX = dU + LN1'(dXhat1)
   if ((rc = vmlp_layernorm_bwd(dXh, C, x, C, mean1, rstd1, p->ln1_w, dU, C, dx, C, g_ln1w, g_ln1b, R, C, stream))) return rc;

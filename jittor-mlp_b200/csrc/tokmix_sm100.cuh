@@ -1,0 +1,772 @@
+// Fused token-mixing MLP of the MLP-Mixer block for sm_100a (reference: models_pytorch/mlp_mixer.py:16-27,34,37 --
+// FeedForward(num_patches, 4 * num_patches, dense = Conv1d(k=1)) applied along the token axis of [B, N, C]).
+//
+//   forward :  U[b]  = X[b] + W2 * gelu(W1 * Xh[b] + b1) + b2          Xh = LN1(X) [B, N, C],  W1 [Ds, N],  W2 [N, Ds]
+//   backward:  dXh[b] = W1^T * ( (W2^T * dU[b]) .* gelu'(W1 * Xh[b] + b1) )     (+ dZ^T saved for the weight gradient)
+//
+// The hidden tensor Z/H [B, Ds, C] never makes an HBM round trip between the two GEMMs.  Work item of one CTA = one image
+// and 128 channels ("tile"); a CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256) shares every weight chunk: each
+// CTA loads half of the chunk's rows, so the L2 -> SMEM weight traffic per SM is half of what two independent CTAs need.
+// Everything is computed TRANSPOSED (channels = M = TMEM lanes):
+//
+//   G1:  Z^T[c, m]   = sum_n Xh^T[c, n] * W1[m, n]       A = the [N, 128c] activation tile as it lies in memory (MN-major),
+//                                                         B = 64 rows of W1 (K-major), accumulator 64 TMEM columns
+//   epi: H^T[c, m]   = gelu(Z^T + b1[m])  -> bf16 -> SMEM tile [128c x 64m] (K-major A operand of G2) (+ TMA store, fwd)
+//   G2:  U^T[c, n]  += sum_m H^T[c, m] * W2[n, m]         B = [N rows x 64 m] of W2 (K-major), accumulator NT columns
+//
+// and in backward  G1 (Z recomputed), G2: dH^T = dU^T * W2 chunk, epi: dZ^T = dH^T .* gelu'(Z^T), G3: dXh^T += dZ^T * W1 chunk.
+// Hidden chunks of 64 divide Ds = 784 with 16 left over (UMMA N = 16 for the tail chunk): no padded MMA work along Ds;
+// the token axis N = 196 is padded to NT = 208 by TMA zero fill (13 k-steps of 16).
+//
+// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM owner, warp 2 = TMA store of
+// the saved hidden tile, warp 3 idle, warps 4..19 = epilogue (TMEM lane quarter = warp % 4, 16 of the chunk's 64 columns
+// each).  The MMA warp issues G1 two chunks ahead of G2 so that the tensor pipe works on Z(g+1), Z(g+2) while the
+// epilogue warps run GELU on Z(g); all hand-offs are mbarriers (multicast tcgen05.commit towards both CTAs, remote
+// arrives towards the leader), no block-wide barrier in the steady state.
+#pragma once
+#include "ptx.cuh"
+
+namespace vmlp {
+
+constexpr int TM_CH = 64;                              // hidden chunk (UMMA N of G1, K of G2 per chunk)
+constexpr int TM_EPI_WARPS = 16;
+constexpr int TM_FIRST_EPI_WARP = 4;
+constexpr int TM_THREADS = 32 * (TM_FIRST_EPI_WARP + TM_EPI_WARPS);   // 640
+constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
+constexpr int TM_MAX_DS = 1024;
+constexpr int TM_BAR_BYTES = 1024;
+
+struct TokParams {
+  int B, N, NT, C, Ds;       // NT = N rounded up to 16 (UMMA K-steps along tokens, UMMA N of the output GEMM)
+  int tiles_c;               // ceil(C / 128)
+  int n_tiles;               // B * tiles_c
+  int n_pairs;               // ceil(n_tiles / 2)
+  int n_chunks;              // ceil(Ds / 64)
+  int last_n1;               // hidden columns of the last chunk, rounded up to 16
+  int kf;                    // full 64-wide K atoms along the token axis (NT / 64)
+  int tail;                  // NT % 64: 0, or 16 (SWIZZLE_32B tail atom), or 32 / 48 (a full SWIZZLE_128B atom)
+  int wa_stage;              // bytes of one [32 rows x NT k] weight stage (G1 / G2-of-backward B operand)
+  int wb_stage;              // bytes of one [NT/2 rows x 64 k] weight stage (output-GEMM B operand)
+  int s_wa, s_wb;            // ring depths
+  float inv_tiles_c;
+  const __nv_bfloat16* b1;   // [Ds]
+  const __nv_bfloat16* b2;   // [N]         (forward)
+  const __nv_bfloat16* resid;// [B, N, C]   (forward: x)
+  __nv_bfloat16* out;        // [B, N, C]   forward: u; backward: dXh
+  float* db1;                // [Ds] fp32   backward: += sum over (b, c) of dZ (the hidden-bias gradient)
+};
+
+// shared-memory descriptor high words (SBO, version 1, layout type); K-major operands never use LBO
+constexpr uint32_t TM_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t TM_DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);
+
+__device__ __forceinline__ void tm_arrive_leader(uint64_t* bar, bool is_leader) {
+  if (is_leader) mbar_arrive(bar);
+  else mbar_arrive_remote(bar, 0);
+}
+__device__ __forceinline__ uint32_t ldg_u16(const __nv_bfloat16* p) {
+  unsigned short v;
+  asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_u16(__nv_bfloat16* p, uint32_t v) {
+  asm volatile("st.global.u16 [%0], %1;" ::"l"(p), "h"(static_cast<unsigned short>(v)) : "memory");
+}
+__device__ __forceinline__ uint32_t bf16_bits(float f) {
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  return *reinterpret_cast<unsigned short*>(&h);
+}
+
+// TMA loads of one [32 rows x NT k] weight stage (K-major): kf full SWIZZLE_128B atoms + the tail atom
+__device__ __forceinline__ void tm_load_wa(uint32_t dst, uint64_t map128, uint64_t map32, uint32_t bar, int row,
+                                           const TokParams& p) {
+  for (int a = 0; a < p.kf; ++a) tma_load_3d_u32<2>(dst + a * 4096, map128, bar, a * 64, row, 0);
+  if (p.tail == 16) tma_load_3d_u32<2>(dst + p.kf * 4096, map32, bar, p.kf * 64, row, 0);
+  else if (p.tail) tma_load_3d_u32<2>(dst + p.kf * 4096, map128, bar, p.kf * 64, row, 0);
+}
+// G1-type MMA: D[tmem] = A (MN-major activation tile, k-steps over the token axis) * B (weight stage); n1 = UMMA N
+__device__ __forceinline__ void tm_mma_over_tokens(uint32_t d_tmem, uint32_t act_addr, uint32_t w_addr, uint32_t idesc,
+                                                   const TokParams& p) {
+  const uint32_t a_lbo = (static_cast<uint32_t>(p.NT) * 128u) >> 4;      // distance between the two 64-channel atoms
+  uint32_t a_lo = (act_addr >> 4) | (a_lbo << 16);
+  const uint32_t b_base = w_addr >> 4;
+  const int ks_full = p.kf * 4;
+  for (int ks = 0; ks < ks_full; ++ks) {
+    umma_bf16_lo<2>(d_tmem, a_lo, b_base + (ks >> 2) * 256 + (ks & 3) * 2, TM_DESC_HI_SW128, idesc, ks ? 1u : 0u);
+    a_lo += 2048u >> 4;                                                   // 16 token rows of 128 B
+  }
+  if (p.tail == 16) {
+    umma_bf16_lo<2>(d_tmem, a_lo, b_base + p.kf * 256, TM_DESC_HI_SW32, idesc, ks_full ? 1u : 0u);
+  } else {
+    for (int ks = 0; ks < (p.tail >> 4); ++ks) {
+      umma_bf16_lo<2>(d_tmem, a_lo, b_base + p.kf * 256 + ks * 2, TM_DESC_HI_SW128, idesc, (ks_full + ks) ? 1u : 0u);
+      a_lo += 2048u >> 4;
+    }
+  }
+}
+// G2/G3-type MMA: D[tmem] (+)= A (hidden tile in SMEM, K-major) * B ([NT/2 rows x 64 k] weight stage), ksteps of 16
+__device__ __forceinline__ void tm_mma_over_hidden(uint32_t d_tmem, uint32_t h_addr, uint32_t w_addr, uint32_t idesc,
+                                                   int ksteps, bool first) {
+  const uint32_t a_base = h_addr >> 4, b_base = w_addr >> 4;
+  for (int ks = 0; ks < ksteps; ++ks)
+    umma_bf16_lo<2>(d_tmem, a_base + ks * 2, b_base + ks * 2, TM_DESC_HI_SW128, idesc, (first && ks == 0) ? 0u : 1u);
+}
+
+struct TokTile {
+  int b, c0;
+  bool valid;
+};
+__device__ __forceinline__ TokTile tm_tile(const TokParams& p, int pair, int cta_rank) {
+  TokTile t;
+  const int tile = 2 * pair + cta_rank;
+  t.valid = tile < p.n_tiles;
+  int b = __float2int_rz(static_cast<float>(tile) * p.inv_tiles_c);
+  int ct = tile - b * p.tiles_c;
+  if (ct < 0) { ct += p.tiles_c; --b; }
+  else if (ct >= p.tiles_c) { ct -= p.tiles_c; ++b; }
+  t.b = t.valid ? b : p.B;          // a dead CTA (odd tile count) loads zero-filled boxes and stores nothing
+  t.c0 = ct * 128;
+  return t;
+}
+
+// One epilogue thread's 16 packed bf16 values -> its row of the [128 x 64] SWIZZLE_128B hidden tile
+__device__ __forceinline__ void tm_store_hidden_row(uint32_t tile_addr, int row, int cq, const uint32_t (&o)[8]) {
+  const uint32_t base = tile_addr + (row >> 3) * 1024 + (row & 7) * 128;
+  const int sw = row & 7;
+  st_shared_v4(base + (((2 * cq) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
+  st_shared_v4(base + (((2 * cq + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Forward.  SMEM: [barriers 1 KB][Xh^T tile NT*256][W1 ring][W2 ring][H tiles 2 x 16 KB][b1 fp32][b2 fp32]
+// TMEM: Z double buffer at columns [0, 128), U accumulator at [128, 128 + NT).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TM_THREADS, 1)
+tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]   box (64 c, NT rows)
+                 const __grid_constant__ CUtensorMap tmW1,     // W1   [Ds, N]     box (64 k, 32 rows) SWIZZLE_128B
+                 const __grid_constant__ CUtensorMap tmW1t,    // W1   tail        box (16 k, 32 rows) SWIZZLE_32B
+                 const __grid_constant__ CUtensorMap tmW2,     // W2   [N, Ds]     box (64 k, NT/2 rows)
+                 const __grid_constant__ CUtensorMap tmH,      // H^T  [B, C, Ds]  box (64 m, 128 c)  (saved for backward)
+                 const __grid_constant__ CUtensorMap tmR,      // x    [B, N, C]   box (128 c, NT rows), L2 prefetch only
+                 const TokParams p, const int save_hidden) {
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* xt_full = bars + 0;     uint64_t* xt_empty = bars + 1;
+  uint64_t* u_full = bars + 2;      uint64_t* u_empty = bars + 3;
+  uint64_t* z_full = bars + 4;      uint64_t* z_empty = bars + 6;      // [2] each
+  uint64_t* h_full = bars + 8;      uint64_t* h_empty = bars + 10;
+  uint64_t* h_done = bars + 12;     uint64_t* hs_empty = bars + 14;
+  uint64_t* wa_full = bars + 16;    uint64_t* wa_empty = bars + 24;    // up to 8 stages each
+  uint64_t* wb_full = bars + 32;    uint64_t* wb_empty = bars + 40;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_xt = s_base + TM_BAR_BYTES;
+  const uint32_t s_wa = s_xt + p.NT * 256;
+  const uint32_t s_wb = s_wa + p.s_wa * p.wa_stage;
+  const uint32_t s_h = s_wb + p.s_wb * p.wb_stage;
+  float* sb1 = reinterpret_cast<float*>(smem + (s_h - s_base) + 2 * TM_HTILE);
+  float* sb2 = sb1 + p.n_chunks * TM_CH;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW1t); tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmR);
+    mbar_init(xt_full, 1); mbar_init(xt_empty, 1);
+    mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2 * TM_EPI_WARPS);
+      mbar_init(&h_full[i], 2 * TM_EPI_WARPS);  mbar_init(&h_empty[i], 1);
+      mbar_init(&h_done[i], TM_EPI_WARPS);      mbar_init(&hs_empty[i], 1);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&wa_full[i], 1); mbar_init(&wa_empty[i], 1);
+      mbar_init(&wb_full[i], 1); mbar_init(&wb_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_THREADS) sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
+  for (int i = threadIdx.x; i < p.NT; i += TM_THREADS) sb2[i] = i < p.N ? __bfloat162float(p.b2[i]) : 0.f;
+  if (warp == 1) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int NC = p.n_chunks;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer (both CTAs; bytes signalled on the leader)
+    const uint64_t mX = reinterpret_cast<uint64_t>(&tmX), mW1 = reinterpret_cast<uint64_t>(&tmW1),
+                   mW1t = reinterpret_cast<uint64_t>(&tmW1t), mW2 = reinterpret_cast<uint64_t>(&tmW2);
+    const uint32_t b_xt = leader_cta_addr(smem_u32(xt_full));
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    auto load_wa = [&](int j) {
+      const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+      mbar_wait(&wa_empty[sa], pa ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(&wa_full[sa], 2 * p.wa_stage);
+        tm_load_wa(s_wa + sa * p.wa_stage, mW1, mW1t, leader_cta_addr(smem_u32(&wa_full[sa])),
+                   j * TM_CH + cta_rank * (n1 >> 1), p);
+      }
+      __syncwarp();
+      if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
+    };
+    auto load_wb = [&](int j) {
+      mbar_wait(&wb_empty[sb], pb ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(&wb_full[sb], 2 * p.wb_stage);
+        tma_load_3d_u32<2>(s_wb + sb * p.wb_stage, mW2, leader_cta_addr(smem_u32(&wb_full[sb])), j * TM_CH,
+                           cta_rank * (p.NT >> 1), 0);
+      }
+      __syncwarp();
+      if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
+    };
+    // loads are issued in the order the MMA warp consumes them: within an item W1(j) runs two chunks ahead of W2(j - 2);
+    // the last two W2 chunks are requested before the producer waits for the activation buffer of the next item
+    int it = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      mbar_wait(xt_empty, (it & 1) ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(xt_full, 2 * p.NT * 256);
+        tma_load_3d_u32<2>(s_xt, mX, b_xt, t.c0, 0, t.b);
+        tma_load_3d_u32<2>(s_xt + p.NT * 128, mX, b_xt, t.c0 + 64, 0, t.b);
+        if (t.valid) tma_prefetch_l2_3d(&tmR, t.c0, 0, t.b);
+      }
+      __syncwarp();
+      for (int j = 0; j < NC; ++j) {
+        load_wa(j);
+        if (j >= 2) load_wb(j - 2);
+      }
+      if (NC >= 2) load_wb(NC - 2);
+      load_wb(NC - 1);
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA)
+    if (is_leader) {
+      const uint32_t idesc_g2 = umma_idesc_bf16(256, p.NT, 0, 0);
+      int my_items = 0;
+      for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
+      const int total = my_items * NC;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      int j1 = 0, it1 = 0;        // chunk / item of the next G1
+      int j2 = 0, it2 = 0;        // chunk / item of the next G2
+      int t1 = 0, t2 = 0;         // global chunk counters of the next G1 / G2
+      auto do_g1 = [&]() {        // ---- G1(t1): Z^T = Xh^T * W1chunk^T
+        const int n1 = (j1 == NC - 1) ? p.last_n1 : TM_CH;
+        if (j1 == 0) mbar_wait(xt_full, it1 & 1);
+        const int zb = t1 & 1;
+        mbar_wait(&z_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        mbar_wait(&wa_full[sa], pa);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_wa + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
+          umma_commit_2cta_mc(&wa_empty[sa]);
+          umma_commit_2cta_mc(&z_full[zb]);
+          if (j1 == NC - 1) umma_commit_2cta_mc(xt_empty);
+        }
+        __syncwarp();
+        if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
+        if (++j1 == NC) { j1 = 0; ++it1; }
+        ++t1;
+      };
+      auto do_g2 = [&]() {        // ---- G2(t2): U^T (+)= H^T * W2chunk^T
+        const int hb = t2 & 1;
+        mbar_wait(&h_full[hb], (t2 >> 1) & 1);
+        mbar_wait(&wb_full[sb], pb);
+        if (j2 == 0) mbar_wait(u_empty, (it2 & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int ksteps = (j2 == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
+          tm_mma_over_hidden(tmem_base + 2 * TM_CH, s_h + hb * TM_HTILE, s_wb + sb * p.wb_stage, idesc_g2, ksteps, j2 == 0);
+          umma_commit_2cta_mc(&wb_empty[sb]);
+          umma_commit_2cta_mc(&h_empty[hb]);
+          if (j2 == NC - 1) umma_commit_2cta_mc(u_full);
+        }
+        __syncwarp();
+        if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
+        if (++j2 == NC) { j2 = 0; ++it2; }
+        ++t2;
+      };
+      // G1 runs two chunks ahead of G2.  Inside an item G1(t) is issued before G2(t - 2) (it only needs the Z buffer that
+      // the epilogue released long ago); across an item boundary the two trailing G2 of the previous item go first, so
+      // that they never queue behind the wait for the next item's activation tile.
+      for (int t = 0; t < total + 2; ++t) {
+        const bool g1 = t < total, g2 = t >= 2;
+        const bool g2_first = g2 && (!g1 || j1 < 2);
+        if (g2 && g2_first) do_g2();
+        if (g1) do_g1();
+        if (g2 && !g2_first) do_g2();
+      }
+    }
+  } else if (warp == 2) {
+    // ================================================================ TMA store of the saved hidden tile (each CTA its own)
+    int g = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      for (int j = 0; j < NC; ++j, ++g) {
+        const int hb = g & 1;
+        mbar_wait(&h_done[hb], (g >> 1) & 1);
+        if (elect_one_sync()) {
+          if (save_hidden && t.valid) {
+            tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          mbar_arrive(&hs_empty[hb]);
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one_sync()) tma_store_wait_all<0>();
+    __syncwarp();
+  } else if (warp >= TM_FIRST_EPI_WARP) {
+    // ================================================================ epilogue warps
+    const int q = warp & 3;                               // TMEM lane quarter
+    const int cq = (warp - TM_FIRST_EPI_WARP) >> 2;       // 16-column group of the 64-column chunk
+    const int row = q * 32 + lane;                        // channel within the tile
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int ngrp = p.NT >> 4;
+    int g = 0, it = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      const int ch = t.c0 + row;
+      const bool ch_ok = t.valid && ch < p.C;
+      for (int j = 0; j < NC; ++j, ++g) {
+        const int zb = g & 1;
+        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+        const bool live = cq * 16 < n1;
+        mbar_wait(&z_full[zb], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t v[16];
+        if (live) {
+          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, v);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tm_arrive_leader(&z_empty[zb], is_leader);
+        uint32_t o[8];
+        if (live) {
+          const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bv = bp[e4];
+            f32x2 gl, dg;
+            gelu_erf_pair<false>(pack2(__uint_as_float(v[4 * e4]) + bv.x, __uint_as_float(v[4 * e4 + 1]) + bv.y), gl, dg);
+            o[2 * e4] = pack_bf16x2_f2(gl);
+            gelu_erf_pair<false>(pack2(__uint_as_float(v[4 * e4 + 2]) + bv.z, __uint_as_float(v[4 * e4 + 3]) + bv.w), gl, dg);
+            o[2 * e4 + 1] = pack_bf16x2_f2(gl);
+          }
+        }
+        mbar_wait(&h_empty[zb], ((g >> 1) & 1) ^ 1);     // G2(g - 2) has consumed this hidden buffer
+        mbar_wait(&hs_empty[zb], ((g >> 1) & 1) ^ 1);    // ... and its TMA store has read it
+        if (live) tm_store_hidden_row(s_h + zb * TM_HTILE, row, cq, o);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tm_arrive_leader(&h_full[zb], is_leader);
+          mbar_arrive(&h_done[zb]);
+        }
+      }
+      // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch]   (this thread = one channel; 16 tokens per step)
+      const __nv_bfloat16* rbase = p.resid + ((long long)t.b * p.N) * p.C + ch;
+      __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
+      uint32_t rcur[16], rnxt[16];
+      auto load_res = [&](int grp, uint32_t (&r)[16]) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = grp * 16 + i;
+          r[i] = (ch_ok && grp < ngrp && n < p.N) ? ldg_u16(rbase + (long long)n * p.C) : 0u;
+        }
+      };
+      load_res(cq, rcur);
+      mbar_wait(u_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int grp = cq; grp < ngrp + 4; grp += 4) {
+        const bool has = grp < ngrp;
+        const bool last = grp + 4 >= ngrp;                // this warp's last visit (possibly an empty one)
+        uint32_t v[16];
+        if (has) {
+          load_res(grp + 4, rnxt);
+          tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + grp * 16 + lane_addr, v);
+          tmem_ld_wait();
+        }
+        if (last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tm_arrive_leader(u_empty, is_leader);
+        }
+        if (has && ch_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = grp * 16 + i;
+            if (n < p.N) {
+              const float f = __uint_as_float(v[i]) + sb2[n] + __uint_as_float(rcur[i] << 16);
+              stg_u16(obase + (long long)n * p.C, bf16_bits(f));
+            }
+          }
+        }
+        if (has) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rcur[i] = rnxt[i];
+        }
+        if (last) break;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward (data-gradient chain).  SMEM: [barriers][Xh^T tile][dU^T tile][W1 ring][W2^T ring][W1^T ring][dZ tiles 2 x 16 KB][b1]
+// TMEM: Z double buffer [0, 128), dH double buffer [128, 256), dXh accumulator [256, 256 + NT).
+// Per hidden chunk: G1 Z^T = Xh^T * W1chunk^T (recomputed, never stored), G2 dH^T = dU^T * W2[:, chunk],
+// epilogue dZ^T = dH^T .* gelu'(Z^T + b1) -> bf16 SMEM tile (+ TMA store into dZ^T [B, C, Ds] for the weight gradient),
+// G3 dXh^T += dZ^T * W1[chunk, :].  The weight operands are all K-major copies prepared once per step by
+// vmlp_tokmix_prepare: W1 [Ds, Np], W2^T [Ds, Np], W1^T [N, Ds].
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TM_THREADS, 1)
+tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C]   box (64 c, NT rows)
+                 const __grid_constant__ CUtensorMap tmDU,     // dU    [B, N, C]   box (64 c, NT rows)
+                 const __grid_constant__ CUtensorMap tmW1,     // W1    [Ds, N]     box (64 k, 32 rows)
+                 const __grid_constant__ CUtensorMap tmW1t,    // W1    tail        box (16 k, 32 rows) SWIZZLE_32B
+                 const __grid_constant__ CUtensorMap tmW2T,    // W2^T  [Ds, N]     box (64 k, 32 rows)
+                 const __grid_constant__ CUtensorMap tmW2Tt,   // W2^T  tail
+                 const __grid_constant__ CUtensorMap tmW1T,    // W1^T  [N, Ds]     box (64 k, NT/2 rows)
+                 const __grid_constant__ CUtensorMap tmDZ,     // dZ^T  [B, C, Ds]  box (64 m, 128 c)
+                 const TokParams p) {
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* in_full = bars + 0;     uint64_t* in_empty = bars + 1;
+  uint64_t* dx_full = bars + 2;     uint64_t* dx_empty = bars + 3;
+  uint64_t* zd_full = bars + 4;     uint64_t* zd_empty = bars + 6;     // [2] each
+  uint64_t* dz_full = bars + 8;     uint64_t* dz_empty = bars + 10;
+  uint64_t* dz_done = bars + 12;    uint64_t* dzs_empty = bars + 14;
+  uint64_t* w1_full = bars + 16;    uint64_t* w1_empty = bars + 20;    // up to 4 stages each
+  uint64_t* w2_full = bars + 24;    uint64_t* w2_empty = bars + 28;
+  uint64_t* w3_full = bars + 32;    uint64_t* w3_empty = bars + 36;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_xt = s_base + TM_BAR_BYTES;
+  const uint32_t s_dut = s_xt + p.NT * 256;
+  const uint32_t s_w1 = s_dut + p.NT * 256;
+  const uint32_t s_w2 = s_w1 + p.s_wa * p.wa_stage;
+  const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
+  const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
+  float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + 2 * TM_HTILE);
+  float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW1t);
+    tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW2Tt); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
+    mbar_init(in_full, 1); mbar_init(in_empty, 1);
+    mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * TM_EPI_WARPS);
+      mbar_init(&dz_full[i], 2 * TM_EPI_WARPS);  mbar_init(&dz_empty[i], 1);
+      mbar_init(&dz_done[i], TM_EPI_WARPS);      mbar_init(&dzs_empty[i], 2);   // store warp + column-sum warp
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1);
+      mbar_init(&w2_full[i], 1); mbar_init(&w2_empty[i], 1);
+      mbar_init(&w3_full[i], 1); mbar_init(&w3_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_THREADS) {
+    sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
+    sdb[i] = 0.f;
+  }
+  if (warp == 1) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int NC = p.n_chunks;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    const uint64_t mX = reinterpret_cast<uint64_t>(&tmX), mDU = reinterpret_cast<uint64_t>(&tmDU),
+                   mW1 = reinterpret_cast<uint64_t>(&tmW1), mW1t = reinterpret_cast<uint64_t>(&tmW1t),
+                   mW2T = reinterpret_cast<uint64_t>(&tmW2T), mW2Tt = reinterpret_cast<uint64_t>(&tmW2Tt),
+                   mW1T = reinterpret_cast<uint64_t>(&tmW1T);
+    const uint32_t b_in = leader_cta_addr(smem_u32(in_full));
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    auto load_w12 = [&](int j) {
+      const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+      const int row = j * TM_CH + cta_rank * (n1 >> 1);
+      mbar_wait(&w1_empty[sa], pa ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
+        tm_load_wa(s_w1 + sa * p.wa_stage, mW1, mW1t, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
+      }
+      __syncwarp();
+      mbar_wait(&w2_empty[sa], pa ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
+        tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, mW2Tt, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
+      }
+      __syncwarp();
+      if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
+    };
+    auto load_w3 = [&](int j) {
+      mbar_wait(&w3_empty[sb], pb ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(&w3_full[sb], 2 * p.wb_stage);
+        tma_load_3d_u32<2>(s_w3 + sb * p.wb_stage, mW1T, leader_cta_addr(smem_u32(&w3_full[sb])), j * TM_CH,
+                           cta_rank * (p.NT >> 1), 0);
+      }
+      __syncwarp();
+      if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
+    };
+    int it = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      mbar_wait(in_empty, (it & 1) ^ 1);
+      if (elect_one_sync()) {
+        if (is_leader) mbar_arrive_expect_tx(in_full, 4 * p.NT * 256);
+        tma_load_3d_u32<2>(s_xt, mX, b_in, t.c0, 0, t.b);
+        tma_load_3d_u32<2>(s_xt + p.NT * 128, mX, b_in, t.c0 + 64, 0, t.b);
+        tma_load_3d_u32<2>(s_dut, mDU, b_in, t.c0, 0, t.b);
+        tma_load_3d_u32<2>(s_dut + p.NT * 128, mDU, b_in, t.c0 + 64, 0, t.b);
+      }
+      __syncwarp();
+      for (int j = 0; j < NC; ++j) {
+        load_w12(j);
+        if (j >= 2) load_w3(j - 2);
+      }
+      if (NC >= 2) load_w3(NC - 2);
+      load_w3(NC - 1);
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA)
+    if (is_leader) {
+      const uint32_t idesc_g3 = umma_idesc_bf16(256, p.NT, 0, 0);
+      int my_items = 0;
+      for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
+      const int total = my_items * NC;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      int j1 = 0, it1 = 0, j3 = 0, it3 = 0;
+      int t1 = 0, t3 = 0;
+      auto do_g12 = [&]() {       // ---- Z^T = Xh^T * W1chunk^T and dH^T = dU^T * W2[:, chunk]
+        const int n1 = (j1 == NC - 1) ? p.last_n1 : TM_CH;
+        if (j1 == 0) mbar_wait(in_full, it1 & 1);
+        const int zb = t1 & 1;
+        mbar_wait(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        mbar_wait(&w1_full[sa], pa);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_w1 + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
+          umma_commit_2cta_mc(&w1_empty[sa]);
+        }
+        __syncwarp();
+        mbar_wait(&w2_full[sa], pa);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          tm_mma_over_tokens(tmem_base + 2 * TM_CH + zb * TM_CH, s_dut, s_w2 + sa * p.wa_stage,
+                             umma_idesc_bf16(256, n1, 1, 0), p);
+          umma_commit_2cta_mc(&w2_empty[sa]);
+          umma_commit_2cta_mc(&zd_full[zb]);
+          if (j1 == NC - 1) umma_commit_2cta_mc(in_empty);
+        }
+        __syncwarp();
+        if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
+        if (++j1 == NC) { j1 = 0; ++it1; }
+        ++t1;
+      };
+      auto do_g3 = [&]() {        // ---- dXh^T (+)= dZ^T * W1[chunk, :]
+        const int hb = t3 & 1;
+        mbar_wait(&dz_full[hb], (t3 >> 1) & 1);
+        mbar_wait(&w3_full[sb], pb);
+        if (j3 == 0) mbar_wait(dx_empty, (it3 & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int ksteps = (j3 == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
+          tm_mma_over_hidden(tmem_base + 4 * TM_CH, s_dz + hb * TM_HTILE, s_w3 + sb * p.wb_stage, idesc_g3, ksteps, j3 == 0);
+          umma_commit_2cta_mc(&w3_empty[sb]);
+          umma_commit_2cta_mc(&dz_empty[hb]);
+          if (j3 == NC - 1) umma_commit_2cta_mc(dx_full);
+        }
+        __syncwarp();
+        if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
+        if (++j3 == NC) { j3 = 0; ++it3; }
+        ++t3;
+      };
+      for (int t = 0; t < total + 2; ++t) {      // same issue order as the forward kernel
+        const bool g1 = t < total, g3 = t >= 2;
+        const bool g3_first = g3 && (!g1 || j1 < 2);
+        if (g3 && g3_first) do_g3();
+        if (g1) do_g12();
+        if (g3 && !g3_first) do_g3();
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ================================================================ helper warps: warp 2 stores the dZ^T tile by TMA;
+    // both sum the tile's columns over their 64 channel rows (d b1[m] = sum over (b, c) of dZ): lane l owns hidden
+    // columns 2l, 2l+1 of the chunk and reads one 32-bit word per row (the 16-byte chunk index is un-swizzled per row).
+    const int r0 = (warp - 2) * 64;
+    const uint32_t kq = lane >> 2, wofs = (lane & 3) * 4;
+    int g = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      for (int j = 0; j < NC; ++j, ++g) {
+        const int hb = g & 1;
+        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+        mbar_wait(&dz_done[hb], (g >> 1) & 1);
+        if (warp == 2 && elect_one_sync()) {
+          if (t.valid) {
+            tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
+            tma_store_commit();
+          }
+        }
+        __syncwarp();
+        float s0 = 0.f, s1 = 0.f;
+        if (t.valid && 2 * lane < n1) {
+          const uint32_t tb = s_dz + hb * TM_HTILE;
+#pragma unroll 8
+          for (int r = r0; r < r0 + 64; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tb + r * 128 + ((kq ^ (r & 7)) << 4) + wofs) : "memory");
+            s0 += bf16lo(w);
+            s1 += bf16hi(w);
+          }
+          atomicAdd(&sdb[j * TM_CH + 2 * lane], s0);
+          atomicAdd(&sdb[j * TM_CH + 2 * lane + 1], s1);
+        }
+        __syncwarp();
+        if (elect_one_sync()) {
+          if (warp == 2) tma_store_wait_read<0>();
+          mbar_arrive(&dzs_empty[hb]);
+        }
+        __syncwarp();
+      }
+    }
+    if (warp == 2 && elect_one_sync()) tma_store_wait_all<0>();
+    __syncwarp();
+  } else if (warp >= TM_FIRST_EPI_WARP) {
+    // ================================================================ epilogue warps
+    const int q = warp & 3;
+    const int cq = (warp - TM_FIRST_EPI_WARP) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int ngrp = p.NT >> 4;
+    int g = 0, it = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      const int ch = t.c0 + row;
+      const bool ch_ok = t.valid && ch < p.C;
+      for (int j = 0; j < NC; ++j, ++g) {
+        const int zb = g & 1;
+        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+        const bool live = cq * 16 < n1;
+        mbar_wait(&zd_full[zb], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t vz[16], vh[16];
+        if (live) {
+          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vz);
+          tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
+        uint32_t o[8];
+        if (live) {
+          const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bv = bp[e4];
+            f32x2 gl, dg;
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dg);
+            o[2 * e4] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4]), __uint_as_float(vh[4 * e4 + 1]))));
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dg);
+            o[2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
+          }
+        }
+        mbar_wait(&dz_empty[zb], ((g >> 1) & 1) ^ 1);
+        mbar_wait(&dzs_empty[zb], ((g >> 1) & 1) ^ 1);
+        if (live) tm_store_hidden_row(s_dz + zb * TM_HTILE, row, cq, o);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tm_arrive_leader(&dz_full[zb], is_leader);
+          mbar_arrive(&dz_done[zb]);
+        }
+      }
+      // ---- output: dXh[b, n, ch] = dXh^T[ch, n]
+      __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
+      mbar_wait(dx_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int grp = cq; grp < ngrp + 4; grp += 4) {
+        const bool has = grp < ngrp;
+        const bool last = grp + 4 >= ngrp;
+        uint32_t v[16];
+        if (has) {
+          tmem_ld_32x32b_x16(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);
+          tmem_ld_wait();
+        }
+        if (last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
+        }
+        if (has && ch_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = grp * 16 + i;
+            if (n < p.N) stg_u16(obase + (long long)n * p.C, bf16_bits(__uint_as_float(v[i])));
+          }
+        }
+        if (last) break;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+  if (p.db1 != nullptr)
+    for (int i = threadIdx.x; i < p.Ds; i += TM_THREADS) red_add_f32(p.db1 + i, sdb[i]);
+}
+
+// W [rows, cols] -> padded copy [rows, ld] (zero fill) and/or transposed copy [cols, ldt] (zero fill): the K-major weight
+// operands of the fused kernels (a few hundred KB per block, once per step)
+__global__ void tokmix_prepare_kernel(const __nv_bfloat16* __restrict__ w, int rows, int cols, __nv_bfloat16* __restrict__ pad,
+                                      int ld, __nv_bfloat16* __restrict__ tr, int ldt) {
+  const long long total_p = pad ? (long long)rows * ld : 0;
+  const long long total_t = tr ? (long long)cols * ldt : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_p + total_t; i += (long long)gridDim.x * blockDim.x) {
+    if (i < total_p) {
+      const int r = (int)(i / ld), c = (int)(i % ld);
+      pad[i] = c < cols ? w[(long long)r * cols + c] : __float2bfloat16(0.f);
+    } else {
+      const long long k = i - total_p;
+      const int c = (int)(k / ldt), r = (int)(k % ldt);
+      tr[k] = r < rows ? w[(long long)r * cols + c] : __float2bfloat16(0.f);
+    }
+  }
+}
+
+}  // namespace vmlp

@@ -40,9 +40,16 @@ class DataParallel(torch.nn.Module):
     def forward(self, *a, **kw):
         return self.module(*a, **kw)
 
-    # called by the fused block backward (ops.py) with the block's flat bf16 gradient buffer
-    def reduce_bucket_async(self, flat):
+    # called by the fused block backward (ops.py) with the block's flat bf16 gradient buffer and its owning parameters
+    def reduce_bucket_async(self, flat, owners=()):
         if self.world == 1:
+            return
+        # The in-place reduction of `flat` is only sound when autograd will STEAL its views as the new p.grad (p.grad is
+        # None).  With gradient accumulation / zero_grad(set_to_none=False), AccumulateGrad runs `p.grad += view` on the
+        # compute stream while the collective rewrites the buffer, and finish() would average p.grad a second time.
+        # Such a bucket is not exchanged here at all: its parameters fall through to finish()'s "rest" path, which
+        # averages the accumulated p.grad once, after backward.
+        if any(p.grad is not None for p in owners):
             return
         if self.mode == "end":          # exchange after the whole backward: no SM contention with the persistent GEMMs
             self._deferred.append(flat)

@@ -154,14 +154,45 @@ class BatchNormFn(torch.autograd.Function):
         return da, g[:C], g[C:], None, None, None, None, (dy if ctx.has_res else None), None
 
 
+class BatchNormEvalFn(torch.autograd.Function):
+    """nn.BatchNorm2d in eval(): a per-channel affine with the running statistics (fp32 coefficients) + optional
+    residual.  An autograd node, so frozen-BN fine-tuning / saliency / linear probes through ConvMixer.eval() get
+    gradients for every block, like the reference's nn.BatchNorm2d (conv_mixer.py:20,27,31):
+        da = dy * A,  dres = dy,  dgamma = sum dy * (a - running_mean) * rstd,  dbeta = sum dy."""
+
+    @staticmethod
+    def forward(ctx, a, gamma, beta, running_mean, running_var, eps, res):
+        _chk(a, "a"); _chk(gamma, "gamma"); _chk(beta, "beta"); _chk(res, "res")
+        C = a.shape[-1]
+        rs = torch.rsqrt(running_var.float() + eps)
+        A = (gamma.float() * rs).contiguous()
+        Cc = (beta.float() - running_mean.float() * A).contiguous()
+        y = torch.empty_like(a)
+        ones = torch.ones(C, dtype=torch.float32, device=a.device) if res is not None else None
+        L.check(L.lib().vmlp_chan_lin(a.data_ptr(), res.data_ptr() if res is not None else 0, 0, A.data_ptr(),
+                                      ones.data_ptr() if ones is not None else 0, Cc.data_ptr(), y.data_ptr(),
+                                      a.numel() // C, C, L.stream_ptr()))
+        ctx.save_for_backward(a, A, rs, running_mean.float())
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, A, rs, rm = ctx.saved_tensors
+        C = a.shape[-1]
+        R = a.numel() // C
+        dy = dy.contiguous()
+        _chk(dy, "dy")
+        st = _f32(3 * C, a.device)
+        sdy, sdya, zero = (st[i * C:(i + 1) * C] for i in range(3))
+        colsum2_into(sdy, sdya, dy.view(R, C), a.view(R, C))          # sum dy, sum dy * a in one pass
+        da = torch.empty_like(a)
+        L.check(L.lib().vmlp_chan_lin(dy.data_ptr(), 0, 0, A.data_ptr(), 0, zero.data_ptr(), da.data_ptr(), R, C,
+                                      L.stream_ptr()))
+        dgamma = ((sdya - rm * sdy) * rs).to(a.dtype)
+        return da, dgamma, sdy.to(a.dtype), None, None, None, (dy if ctx.has_res else None)
+
+
 def batch_norm_eval(a, bn, res=None):
     """eval(): BatchNorm uses the running statistics -> a per-channel affine with fp32 coefficients."""
-    C = a.shape[-1]
-    A = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps))
-    Cc = bn.bias.float() - bn.running_mean.float() * A
-    y = torch.empty_like(a)
-    ones = torch.ones(C, dtype=torch.float32, device=a.device) if res is not None else None
-    L.check(L.lib().vmlp_chan_lin(a.data_ptr(), res.data_ptr() if res is not None else 0, 0, A.contiguous().data_ptr(),
-                                  ones.data_ptr() if ones is not None else 0, Cc.contiguous().data_ptr(), y.data_ptr(),
-                                  a.numel() // C, C, L.stream_ptr()))
-    return y
+    return BatchNormEvalFn.apply(a, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, res)

@@ -11,7 +11,9 @@ import torch
 
 
 class GraphedStep:
-    """loss = loss_fn(model(x)); loss.backward() as one CUDA graph.  Gradients land in ``p.grad`` (static tensors).
+    """loss = loss_fn(model(x)); loss.backward() as one CUDA graph.  Gradients land in ``p.grad`` (static tensors that
+    every replay OVERWRITES -- the captured step starts from grad=None, so there is no accumulation across replays;
+    ``run()`` re-attaches them if ``zero_grad(set_to_none=True)`` detached them in between).
 
     ``step_fn(x) -> loss`` replaces the default body; the data-parallel step (``dp.DataParallel.step_fwd_bwd``: the same
     fwd+bwd with the per-block NCCL gradient all-reduces enqueued from inside backward) is captured this way, so an
@@ -38,9 +40,15 @@ class GraphedStep:
         model.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.static_loss = step_fn(self.static_x)
+        # the replay writes gradients into exactly these tensors (graph-private memory): keep them, so that a
+        # zero_grad(set_to_none=True) between replays cannot orphan them
+        self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
 
     def run(self, x=None, non_blocking=True):
         if x is not None:
             self.static_x.copy_(x, non_blocking=non_blocking)
         self.graph.replay()
+        for p, g in self._grads:          # re-attach after model.zero_grad() / optimizer.zero_grad() (set_to_none=True)
+            if p.grad is not g:
+                p.grad = g
         return self.static_loss

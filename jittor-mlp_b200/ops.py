@@ -24,6 +24,11 @@ def _chk(t, name, dtype=BF16):
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype} (call .bfloat16() on the module and its input)")
     if not t.is_contiguous():
         raise ValueError(f"{name}: must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device's stream (like the reference, which wraps its launch in
+        # torch.cuda.device_of(input), shift_cuda.py:115): refuse a tensor that lives elsewhere
+        raise ValueError(f"{name}: tensor is on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                         f"(wrap the call in torch.cuda.device(...))")
 
 
 def _ptr(t):
@@ -128,13 +133,17 @@ class MixerBlockFn(torch.autograd.Function):
         dev = x.device
         new = lambda *s: torch.empty(*s, dtype=BF16, device=dev)
         y = new(B, N, C)
-        sv = dict(xhat1=new(B, N, C), z1=new(B, Ds, C), h1=new(B, Ds, C), u=new(B, N, C), xhat2=new(B, N, C),
-                  z2=new(B * N, Dc), h2=new(B * N, Dc),
-                  stats=torch.empty(4, B * N, dtype=torch.float32, device=dev), w1t_pad=new(Ds, (N + 7) // 8 * 8))
-        s = L.MixerSaved(**{k: v.data_ptr() for k, v in sv.items()})
         p = _mixer_params(B, N, C, Ds, Dc, eps, params)
+        # fused token half (vmlp_tokmix_*): no pre-activation tensor, hidden activation saved transposed [B, C, Ds]
+        fused = bool(L.lib().vmlp_mixer_token_fused(ctypes.byref(p)))
+        sv = dict(xhat1=new(B, N, C), z1=None if fused else new(B, Ds, C), h1=new(B, C, Ds) if fused else new(B, Ds, C),
+                  u=new(B, N, C), xhat2=new(B, N, C), z2=new(B * N, Dc), h2=new(B * N, Dc),
+                  stats=torch.empty(4, B * N, dtype=torch.float32, device=dev), w1t_pad=new(Ds, (N + 7) // 8 * 8))
+        s = L.MixerSaved(**{k: _ptr(v) for k, v in sv.items()})
         L.check(L.lib().vmlp_mixer_block_fwd(ctypes.byref(p), x.data_ptr(), y.data_ptr(), ctypes.byref(s),
                                              L.stream_ptr()))
+        if fused:
+            sv.pop("z1")
         ctx.eps = eps
         ctx.dims = (B, N, C, Ds, Dc)
         ctx.save_for_backward(x, *params, *sv.values())
@@ -149,7 +158,7 @@ class MixerBlockFn(torch.autograd.Function):
         dy = dy.contiguous()
         _chk(dy, "dy")
         sv = dict(zip(ctx.sv_keys, svt))
-        s = L.MixerSaved(**{k: v.data_ptr() for k, v in sv.items()})
+        s = L.MixerSaved(**{k: v.data_ptr() for k, v in sv.items()})       # z1 stays NULL on the fused token path
         p = _mixer_params(B, N, C, Ds, Dc, ctx.eps, params)
         lib = L.lib()
         n_grad = lib.vmlp_mixer_grad_elems(ctypes.byref(p))
@@ -162,7 +171,7 @@ class MixerBlockFn(torch.autograd.Function):
         gb = cast_f32_to_bf16(grads)
         from . import dp
         if dp.active() is not None:       # data parallel: average this block's gradients while backward continues
-            dp.active().reduce_bucket_async(gb)
+            dp.active().reduce_bucket_async(gb, params)
         outs, off = [], 0
         for t in params:
             outs.append(gb[off:off + t.numel()].view(t.shape))
@@ -261,7 +270,7 @@ def _finish_grads(flat32, params):
     gb = cast_f32_to_bf16(flat32)
     from . import dp
     if dp.active() is not None:
-        dp.active().reduce_bucket_async(gb)
+        dp.active().reduce_bucket_async(gb, params)
     outs, off = [], 0
     for t in params:
         outs.append(gb[off:off + t.numel()].view(t.shape))
@@ -427,3 +436,54 @@ def gemm_raw(M, N, K, A, B, epilogue, batch=1, D=None, D2=None, bias=None, bias_
         g.bias, g.bias_mode = bias.data_ptr(), bias_mode
     g.aux, g.aux_ld, g.aux_bs = aux_ptr, aux_ld, aux_bs
     L.check(L.lib().vmlp_gemm_bf16(ctypes.byref(g), L.stream_ptr()))
+
+
+# --------------------------------------------------------------------------------------------- fused token-mixing MLP
+def tokmix_supported(B, N, C, Ds, backward=False):
+    return bool(L.lib().vmlp_tokmix_supported(B, N, C, Ds, int(backward)))
+
+
+def tokmix_prepare(w, pad=False, transpose=False, ldt=None):
+    """K-major operand copies of a [rows, cols] weight for the fused kernels: (zero-padded [rows, ceil8(cols)] copy,
+    transposed [cols, ldt] copy); entries not asked for are None."""
+    _chk(w, "w")
+    rows, cols = w.shape
+    ld = (cols + 7) // 8 * 8
+    ldt = rows if ldt is None else ldt
+    wp = _new(rows, ld, like=w) if pad else None
+    wt = _new(cols, ldt, like=w) if transpose else None
+    L.check(L.lib().vmlp_tokmix_prepare(w.data_ptr(), rows, cols, _ptr(wp), ld, _ptr(wt), ldt, L.stream_ptr()))
+    return wp, wt
+
+
+def tokmix_fwd(xhat, x, w1, b1, w2, b2, save_hidden=True):
+    """u = x + W2 gelu(W1 xhat + b1) + b2 along the token axis of [B, N, C] (mlp_mixer.py:16-27,37) in one kernel.
+    Returns (u, hT) with hT = gelu(..) transposed to [B, C, Ds] (None unless save_hidden)."""
+    for t, n in ((xhat, "xhat"), (x, "x"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        _chk(t, n)
+    B, N, C = xhat.shape
+    Ds = w1.shape[0]
+    w1p, _ = tokmix_prepare(w1.view(Ds, N), pad=True)
+    u = torch.empty_like(x)
+    hT = _new(B, C, Ds, like=x) if save_hidden else None
+    L.check(L.lib().vmlp_tokmix_fwd(xhat.data_ptr(), x.data_ptr(), w1p.data_ptr(), w1p.shape[1], w2.data_ptr(),
+                                    b1.data_ptr(), b2.data_ptr(), u.data_ptr(), _ptr(hT), B, N, C, Ds, L.stream_ptr()))
+    return u, hT
+
+
+def tokmix_bwd(xhat, du, w1, b1, w2):
+    """Data-gradient chain of the token MLP in one kernel -> (dxhat [B, N, C], dzT [B, C, Ds], db1 fp32 [Ds])."""
+    for t, n in ((xhat, "xhat"), (du, "du"), (w1, "w1"), (b1, "b1"), (w2, "w2")):
+        _chk(t, n)
+    B, N, C = xhat.shape
+    Ds = w1.shape[0]
+    Np = (N + 7) // 8 * 8
+    w1p, w1T = tokmix_prepare(w1.view(Ds, N), pad=True, transpose=True)
+    _, w2T = tokmix_prepare(w2.view(N, Ds), transpose=True, ldt=Np)
+    dxh = torch.empty_like(xhat)
+    dzT = _new(B, C, Ds, like=xhat)
+    db1 = _f32(Ds, xhat.device)
+    L.check(L.lib().vmlp_tokmix_bwd(xhat.data_ptr(), du.data_ptr(), w1p.data_ptr(), w2T.data_ptr(), Np, w1T.data_ptr(),
+                                    b1.data_ptr(), dxh.data_ptr(), dzT.data_ptr(), db1.data_ptr(), B, N, C, Ds,
+                                    L.stream_ptr()))
+    return dxh, dzT, db1

@@ -27,7 +27,11 @@ CASES = {
     "s2v1_tiny": ("s2_mlp_v1", "S2MLPv1", dict(image_size=32, patch_size=[4, 2], d_model=[32, 64], depth=[1, 2],
                                                expansion_factor=[2, 3], num_classes=10), (2, 3, 32, 32)),
     "s2v2_tiny": ("s2_mlp_v2", "S2MLPv2", dict(image_size=(32, 24), patch_size=[4, 2], d_model=[24, 64], depth=[1, 2],
-                                               expansion_factor=[2, 3], num_classes=10), (2, 3, 32, 24)),
+                                               expansion_factor=[2, 3], num_classes=10), (2, 3, 32, 24),
+                  # SplitAttention pools by a token SUM (s2_mlp_v2.py:44); with every weight perturbed by 0.1 its softmax
+                  # logits reach ~50 and the block output flips with one bf16 ulp of the pooled vector.  Scaled weights
+                  # keep the logits O(1) like a trained model's, so the fixture tests the arithmetic, not the conditioning.
+                  {"split_attention": 0.15}),
     "asmlp_tiny": ("as_mlp", "AS_MLP", dict(img_size=32, patch_size=4, embed_dim=24, depths=[1, 2], shift_size=5,
                                             num_classes=10, drop_path_rate=0.), (2, 3, 32, 32)),
     "hire_tiny": ("hire_mlp", "HireMLP", dict(patch_size=4, d_model=[16, 32], h=[4, 3], w=[4, 3], cross_region_step=[2, 1],
@@ -40,10 +44,15 @@ CASES = {
 
 
 def make(name):
-    mod, cls, kwargs, xshape = CASES[name]
+    mod, cls, kwargs, xshape = CASES[name][:4]
     torch.manual_seed(0)
     model = getattr(R.load(mod), cls)(**kwargs)
     R.randomize_(model, 0.1, seed=1)
+    for key, scale in (CASES[name][4] if len(CASES[name]) > 4 else {}).items():
+        with torch.no_grad():
+            for k, p in model.named_parameters():
+                if key in k:
+                    p.mul_(scale)
     model.train()
     x = torch.randn(*xshape, generator=torch.Generator().manual_seed(2)).requires_grad_(True)
     out = model(x)

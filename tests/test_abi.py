@@ -19,7 +19,7 @@ def test_header_symbols_are_exported_and_bound():
     lib = L.lib()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.vmlp_abi_version() == 1
+    assert lib.vmlp_abi_version() == L.ABI_VERSION
 
 
 def test_ctypes_struct_layout_matches_header_order():

@@ -72,3 +72,80 @@ def test_two_rank_gradient_average_matches_single_process_big_batch(mode):
     ref(xs).square().mean().backward()
     for k, p in ref.named_parameters():
         assert torch.allclose(ga[k], p.grad, atol=1e-6), k
+
+
+class _FlatLinearFn(torch.autograd.Function):
+    """CPU stand-in for a fused block: its backward produces all parameter gradients as views of ONE flat buffer and
+    registers that buffer as a DP bucket, exactly like ops._finish_grads does for the CUDA blocks."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w, b)
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        from jittor_mlp_b200 import dp
+        x, w, b = ctx.saved_tensors
+        flat = torch.cat([(dy.t() @ x).flatten(), dy.sum(0)])
+        if dp.active() is not None:
+            dp.active().reduce_bucket_async(flat, (w, b))
+            for work, _ in dp.active()._pending:      # a fast network: the collective lands before AccumulateGrad runs
+                work.wait()
+        return dy @ w, flat[:w.numel()].view_as(w), flat[w.numel():]
+
+
+def _accum_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      VMLP_DP_MODE="overlap")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jittor_mlp_b200 import dp
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(5)
+            self.w = torch.nn.Parameter(torch.randn(4, 8))
+            self.b = torch.nn.Parameter(torch.randn(4))
+            self.head = torch.nn.Linear(4, 2)
+
+        def forward(self, x):
+            return self.head(_FlatLinearFn.apply(x, self.w, self.b))
+
+    model = M()
+    ddp = dp.DataParallel(model)
+    xs = torch.randn(2, 4, 8, generator=torch.Generator().manual_seed(7))    # 2 micro-batches x global batch 4
+    for mb in range(2):                                                       # no zero_grad in between: accumulation
+        ddp.step_fwd_bwd(xs[mb, rank * 2:(rank + 1) * 2], lambda o: o.square().mean())
+    q.put((rank, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_accumulation_over_two_micro_batches():
+    """with an existing p.grad the block bucket must not be reduced in place while AccumulateGrad adds its
+    views into p.grad (and must not be averaged twice): the accumulated gradient equals the single-process sum of the
+    two global-batch gradients on every rank."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(5)
+    w = torch.randn(4, 8, requires_grad=True)
+    b = torch.randn(4, requires_grad=True)
+    torch.manual_seed(5)
+    _ = torch.randn(4, 8), torch.randn(4)
+    head = torch.nn.Linear(4, 2)
+    xs = torch.randn(2, 4, 8, generator=torch.Generator().manual_seed(7))
+    for mb in range(2):
+        head(xs[mb] @ w.t() + b).square().mean().backward()
+    ref = {"w": w.grad, "b": b.grad, "head.weight": head.weight.grad, "head.bias": head.bias.grad}
+    for rank, grads in res:
+        for k, g in ref.items():
+            assert torch.allclose(grads[k], g, atol=1e-5), (rank, k, (grads[k] - g).abs().max())

@@ -106,3 +106,98 @@ def test_cuda_graph_step_matches_eager():
     assert abs(float(l1) - l0) < 1e-3 * abs(l0)
     for k, p in m.named_parameters():
         assert restate.rel_l2(p.grad.cpu(), ref[k].cpu()) < 2e-3, k
+
+
+def _grad_check(named_grads, ref_grads, scale, tol=3 * TOL):
+    """Every parameter gradient within `tol` (rel-L2), tensors that are numerically zero at this scale by an absolute
+    bound; and all of them together within 2e-2."""
+    ours, refs = [], []
+    for k, g in named_grads.items():
+        rg = ref_grads[k]
+        err = restate.rel_l2(g.cpu(), rg.cpu())
+        assert err < tol or float((g.cpu().float() - rg.cpu()).abs().max()) < 1e-4 * scale, (k, err)
+        ours.append(g.cpu().float().flatten()); refs.append(rg.cpu().float().flatten())
+    assert restate.rel_l2(torch.cat(ours), torch.cat(refs)) < 2 * TOL
+
+
+def test_whole_mixer_b16_as_benchmarked():
+    """BASELINE config 2 exactly as bench.py runs it (d_model 768, depth 12, 224 px, patch 16, 1000 classes) on 4 images
+    against the fp32 oracle on the CPU: output <= 1e-2, input gradient and all 150 parameter gradients <= 3e-2
+    (12 blocks of bf16 error accumulation, 196-token GEMMs through the fused token kernels)."""
+    torch.manual_seed(0)
+    kw = dict(d_model=768, depth=12, image_size=224, patch_size=16, num_classes=1000)
+    m = J.MLPMixerForImageClassification(**kw)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+            p.copy_(p.bfloat16().float())                  # both sides start from the same bf16-representable weights
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(1)).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    ref = restate.mixer_forward(sd, xr, kw["depth"])
+    ref.square().mean().backward()
+    out, dx, grads = run_model(m, x)
+    assert restate.rel_l2(out.cpu(), ref) < TOL, restate.rel_l2(out.cpu(), ref)
+    assert restate.compare_py_metric(out.cpu(), ref.detach()) < 1e-2       # the reference's own parity metric (compare.py:179-186)
+    assert restate.rel_l2(dx.cpu(), xr.grad) < 3 * TOL
+    _grad_check(grads, {k: v.grad for k, v in sd.items()}, float(xr.grad.abs().max() + 1))
+
+
+def test_block_at_the_benchmarked_batch_256():
+    """One MixerBlock at the bench shape (B 256, N 196, C 768, Ds 784, Dc 3072: 5376-tile token kernels, 392-tile channel
+    GEMMs, split-K weight gradients over 50176 rows) against the oracle restatement evaluated in fp32 ON THE GPU (the
+    oracle is plain torch; TF32 off) -- y, dx and every parameter gradient."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    B, N, C = 256, 196, 768
+    m = J.MLPMixer(N, C, 1)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    sd = {k: v.detach().clone().bfloat16().float().to(DEV).requires_grad_(True) for k, v in m.state_dict().items()}
+    x = torch.randn(B, N, C, generator=torch.Generator().manual_seed(1)).bfloat16()
+    dy = torch.randn(B, N, C, generator=torch.Generator().manual_seed(2)).bfloat16()
+    xr = x.float().to(DEV).requires_grad_(True)
+    ref = restate.mixer_block(sd, "model.0.", xr)
+    ref.backward(dy.float().to(DEV))
+    m = m.to(DEV).bfloat16()
+    xg = x.to(DEV).requires_grad_(True)
+    y = m(xg)
+    y.backward(dy.to(DEV))
+    torch.cuda.synchronize()
+    assert restate.rel_l2(y.float(), ref.detach()) < TOL
+    assert restate.rel_l2(xg.grad.float(), xr.grad) < TOL
+    for b0 in (0, 100, 255):                                # per-image: no sample is left behind by the tile schedule
+        assert restate.rel_l2(y[b0].float(), ref[b0].detach()) < TOL and restate.rel_l2(xg.grad[b0].float(), xr.grad[b0]) < TOL
+    _grad_check({k: p.grad for k, p in m.named_parameters()}, {k: v.grad for k, v in sd.items()},
+                float(xr.grad.abs().max() + 1), tol=2 * TOL)
+
+
+def test_fused_and_unfused_token_paths_agree():
+    """VMLP_TOKMIX=0 (read at library load) selects the unfused GEMM sequence: run it in a subprocess on the same seeded
+    block and compare with the fused path of this process."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import jittor_mlp_b200 as J
+torch.manual_seed(0)
+m = J.MLPMixer(196, 256, 2).to("cuda").bfloat16()
+x = torch.randn(6, 196, 256, generator=torch.Generator().manual_seed(1)).to("cuda").bfloat16().requires_grad_(True)
+y = m(x)
+y.backward(torch.ones_like(y))
+torch.save({"y": y.cpu(), "dx": x.grad.cpu(), "g": {k: p.grad.cpu() for k, p in m.named_parameters()}}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("1", "0"):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env={**os.environ, "VMLP_TOKMIX": flag}, timeout=600)
+            outs.append(torch.load(f.name))
+    a, b = outs
+    assert restate.rel_l2(a["y"], b["y"].float()) < 5e-3 and restate.rel_l2(a["dx"], b["dx"].float()) < 5e-3
+    for k in a["g"]:
+        assert restate.rel_l2(a["g"][k], b["g"][k].float()) < 1e-2, k

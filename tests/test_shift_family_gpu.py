@@ -31,12 +31,9 @@ def test_against_reference_golden(golden, name):
     m = getattr(J, fx["cls"])(**fx["kwargs"])
     m.load_state_dict(fx["state_dict"], strict=True)
     out, dx, grads = run_model(m, fx["x"])
-    # s2v2_tiny: the randomised fixture has split-attention logits of magnitude ~50 fed by a token SUM that passes through
-    # bf16 (one flipped ulp of the pooled vector moves a logit by ~0.2), so its output is ill-conditioned in bf16 and
-    # varies with the fp32-atomic summation order; the config-4 widths below hold the 1e-2 bound
-    assert restate.rel_l2(out.cpu(), fx["out"]) < (4 * TOL if name == "s2v2_tiny" else TOL)
-    if name == "s2v2_tiny":
-        return                                # gradients of the ill-conditioned fixture are covered by the op-level test
+    # (s2v2_tiny was regenerated in round 2 with O(1) split-attention logits -- oracle/gen_golden.py -- and now holds the
+    # same bounds as the other fixtures, gradients included)
+    assert restate.rel_l2(out.cpu(), fx["out"]) < TOL
     assert restate.rel_l2(dx.cpu(), fx["dx"]) < 3 * TOL
     scale = float(fx["dx"].abs().max() + 1)
     ours, refs = [], []
@@ -45,9 +42,9 @@ def test_against_reference_golden(golden, name):
             assert grads[k] is None, k
             continue
         err = restate.rel_l2(grads[k].cpu(), g)
-        # 1-D parameters of these tiny fixtures are sums over < 100 rows: a larger bf16 noise floor per tensor
-        lim = (8 if g.dim() == 1 else 6) * TOL
-        assert err < lim or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * scale, (k, err)
+        # bound: 3e-2 per tensor; tensors whose gradient is numerically zero at this fixture's scale (sums over < 100
+        # rows that cancel) are held to an absolute bound instead
+        assert err < 3 * TOL or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * scale, (k, err)
         ours.append(grads[k].cpu().float().flatten()); refs.append(g.flatten())
     assert restate.rel_l2(torch.cat(ours), torch.cat(refs)) < 2 * TOL      # all parameter gradients together
 
@@ -200,7 +197,8 @@ def test_hire_region_ops_are_exact_data_movement(H, W, h, w, step):
     ("ConvMixer", dict(dim=256, depth=2, kernel_size=7, patch_size=7, n_classes=16), (8, 3, 56, 56)),
 ])
 def test_config4_channel_widths_against_oracle(cls, kw, xshape):
-    """Real channel widths of BASELINE config 4 (C 96/192/384) at small spatial size, forward + input gradient."""
+    """Real channel widths of BASELINE config 4 (C 96/192/384) at small spatial size: forward, input gradient and every
+    parameter gradient."""
     torch.manual_seed(0)
     m = getattr(J, cls)(**kw)
     with torch.no_grad():
@@ -209,9 +207,20 @@ def test_config4_channel_widths_against_oracle(cls, kw, xshape):
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     x = torch.randn(*xshape, generator=torch.Generator().manual_seed(1))
     xr = x.clone().requires_grad_(True)
-    ref = models.forward(cls, kw, sd, xr)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ref = models.forward(cls, kw, sdg, xr)
     ref.square().mean().backward()
-    out, dx, _ = run_model(m, x)
-    # Hire-MLP has the highest pure-bf16 noise floor of the family (6.7e-3 for the reference itself)
-    assert restate.rel_l2(out.cpu(), ref) < (1.5 * TOL if cls == "HireMLP" else TOL)
+    out, dx, grads = run_model(m, x)
+    assert restate.rel_l2(out.cpu(), ref) < TOL          # north_star: 1e-2 on forward outputs, every model
     assert restate.rel_l2(dx.cpu(), xr.grad) < 3 * TOL
+    scale = float(xr.grad.abs().max() + 1)
+    ours, refs = [], []
+    for k, g in grads.items():
+        rg = sdg[k].grad
+        if g is None or rg is None:                       # never-used parameters on both sides
+            assert g is None and (rg is None or float(rg.abs().max()) == 0), k
+            continue
+        err = restate.rel_l2(g.cpu(), rg)
+        assert err < 3 * TOL or float((g.cpu().float() - rg).abs().max()) < 1e-4 * scale, (k, err)
+        ours.append(g.cpu().float().flatten()); refs.append(rg.flatten())
+    assert restate.rel_l2(torch.cat(ours), torch.cat(refs)) < 2 * TOL
