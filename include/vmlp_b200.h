@@ -49,6 +49,10 @@ int vmlp_abi_struct_bytes(int32_t which);
 const char* vmlp_last_error(void);          /* thread-local message for the last failing call */
 int vmlp_device_check(void);                /* VMLP_OK iff current device is compute capability 10.x */
 int vmlp_sm_count(void);
+/* Diagnostics of a kernel that ended in a bounded-wait trap (protocol bug): out[0] = number of records, then from
+ * out[4] on 4 words per record (block, warp, shared-memory address of the mbarrier, parity).  Host memory: readable
+ * after the CUDA context has died.  Returns the number of words copied. */
+int vmlp_debug_read(uint32_t* out, int32_t n_words);
 int64_t vmlp_launch_count(void);             /* kernels launched by this library in this process */
 
 /* --------------------------------------------------------------------------------------------
@@ -93,10 +97,11 @@ typedef struct {
   const void* aux; int64_t aux_ld, aux_bs;
   float* out_f32; int64_t out_ld;      /* VMLP_EPI_ATOMIC destination [M, N] (caller zero-fills) */
   int32_t split_k;                     /* 0 = choose automatically */
-  int32_t block_n;                     /* 0 = choose automatically (256 or 128) */
+  int32_t block_n;                     /* 0 = choose automatically (128, 256; 208 for VMLP_EPI_ATOMIC with 128 < N <= 208) */
   int32_t cta_group;                   /* 0 = automatic, 1 = one CTA per 128-row tile, 2 = CTA pair per 256-row tile */
   float* red_out; int32_t red_mode;    /* optional: += sums of the stored D per column (1) or per row (2): the bias
                                           gradient when D is d(pre-activation); caller zero-fills */
+  int32_t out_trans;                   /* VMLP_EPI_ATOMIC: add element (m, n) at out_f32[n * out_ld + m] */
 } vmlp_gemm_args;
 
 int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream);
@@ -235,7 +240,7 @@ int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H,
  * the epilogue holds them in):  hT = gelu(..)^T (forward, optional), dzT = d(pre-activation)^T (backward).
  * Weight operands are K-major copies made by vmlp_tokmix_prepare (w [rows, cols] -> pad [rows, ld] zero-padded and / or
  * tr [cols, ldt] transposed, zero-padded; either may be NULL):
- *     w1_pad  = pad(W1)  [Ds, Np]      w2T_pad = tr(W2) [Ds, Np]      w1T = tr(W1) [N, Ds]        Np = ceil8(N)
+ *     w1_pad  = pad(W1)  [Ds, Np]      w2T_pad = tr(W2) [Ds, Np]      w1T = tr(W1) [N, Ds]        Np >= ceil16(N)
  * db1 (fp32 [Ds], optional) += sum over (b, c) of dz.  vmlp_tokmix_supported: N <= 256, Ds <= 1024, C % 8 == Ds % 8 == 0
  * and the tiles of that shape fit in shared memory; otherwise the caller composes vmlp_gemm_bf16 calls.
  * ------------------------------------------------------------------------------------------ */
@@ -268,7 +273,7 @@ typedef struct {
  *   When vmlp_mixer_token_fused(p) != 0 the token half runs as vmlp_tokmix_fwd/_bwd: z1 is not used (may be NULL) and
  *   h1 holds the transposed hidden activation [B, C, Ds] (same element count).
  *   stats: fp32 [4][B*N] = mean1, rstd1, mean2, rstd2
- *   w1t_pad: bf16 [Ds, ceil8(N)] scratch for the 16-byte-pitch copy of W1t */
+ *   w1t_pad: bf16 [Ds, ceil16(N)] scratch for the zero-padded copy of W1t (16-byte pitch, whole k-steps of 16) */
 typedef struct {
   void *xhat1, *z1, *h1, *u, *xhat2, *z2, *h2;
   float* stats;

@@ -89,7 +89,7 @@ class GemmArgs(ctypes.Structure):
                 ("bias", c_void_p), ("bias_mode", c_int32), ("colscale", c_void_p),
                 ("aux", c_void_p), ("aux_ld", c_int64), ("aux_bs", c_int64),
                 ("out_f32", c_void_p), ("out_ld", c_int64), ("split_k", c_int32), ("block_n", c_int32),
-                ("cta_group", c_int32), ("red_out", c_void_p), ("red_mode", c_int32)]
+                ("cta_group", c_int32), ("red_out", c_void_p), ("red_mode", c_int32), ("out_trans", c_int32)]
 
 
 class MixerParams(ctypes.Structure):
@@ -117,6 +117,7 @@ SYMBOLS = [
     ("vmlp_last_error", ctypes.c_char_p, []),
     ("vmlp_device_check", c_int32, []),
     ("vmlp_sm_count", c_int32, []),
+    ("vmlp_debug_read", c_int32, [_P(ctypes.c_uint32), c_int32]),
     ("vmlp_launch_count", c_int64, []),
     ("vmlp_gemm_bf16", c_int32, [_P(GemmArgs), c_void_p]),
     ("vmlp_layernorm_fwd", c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
@@ -179,6 +180,14 @@ SYMBOLS = [
 ]
 
 _lib = None
+
+
+def debug_records():
+    """Records left by kernels that died in a bounded mbarrier wait: [(block, warp, barrier smem address, parity), ...]."""
+    buf = (ctypes.c_uint32 * 804)()
+    n = lib().vmlp_debug_read(buf, 804)
+    cnt = min(int(buf[0]), 200) if n else 0
+    return [tuple(int(buf[4 + 4 * i + j]) for j in range(4)) for i in range(cnt)]
 
 
 class VmlpError(RuntimeError):

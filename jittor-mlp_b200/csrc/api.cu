@@ -53,7 +53,9 @@ EncodeTiledFn encode_tiled_fn() {
 struct DeviceInfo {
   int sms = 0, cc_major = 0, cc_minor = 0;
   bool ok = false;
+  unsigned int* dbg_host = nullptr;     // host-mapped record buffer of the bounded mbarrier waits (ptx.cuh)
 };
+constexpr int DBG_WORDS = 4 + 4 * 200;
 const DeviceInfo& device_info() {
   static DeviceInfo info[64];
   int dev = 0;
@@ -68,6 +70,14 @@ const DeviceInfo& device_info() {
     cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
     cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
     d.ok = d.sms > 0;
+    void* h = nullptr;
+    if (d.ok && cudaHostAlloc(&h, DBG_WORDS * sizeof(unsigned int), cudaHostAllocMapped) == cudaSuccess) {
+      memset(h, 0, DBG_WORDS * sizeof(unsigned int));
+      void* dptr = nullptr;
+      if (cudaHostGetDevicePointer(&dptr, h, 0) == cudaSuccess &&
+          cudaMemcpyToSymbol(g_vmlp_dbg, &dptr, sizeof(dptr)) == cudaSuccess)
+        d.dbg_host = static_cast<unsigned int*>(h);
+    }
   });
   return d;
 }
@@ -215,8 +225,14 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   const int epi = g.epilogue;
   if (epi != EPI_ATOMIC && (g.N % 8) != 0) return fail(VMLP_EINVAL, "N=%d must be a multiple of 8", g.N);
   int bn = g.block_n;
-  if (bn == 0) bn = (g.N <= 128) ? 128 : 256;
-  if (bn != 128 && bn != 256) return fail(VMLP_EINVAL, "block_n must be 128 or 256");
+  if (bn == 0) {
+    bn = (g.N <= 128) ? 128 : 256;
+    // weight gradients whose N is a token count (196 -> 13 x 16): a 208-column tile instead of 256 (K-major B only)
+    if (epi == EPI_ATOMIC && g.B.major == 0 && g.N > 128 && g.N <= 208) bn = 208;
+  }
+  if (bn != 128 && bn != 256 && bn != 208) return fail(VMLP_EINVAL, "block_n must be 128, 208 or 256");
+  if (bn == 208 && (epi != EPI_ATOMIC || g.B.major != 0 || g.cta_group == 2))
+    return fail(VMLP_EINVAL, "block_n 208 exists for EPI_ATOMIC with a K-major B operand on single CTAs only");
 
   // CTA-pair kernel (cta_group::2, 256 x 256 tiles) for the large un-batched GEMMs: channel-mixing fwd/dgrad/wgrad
   const bool one_output = (g.batch == 1 || g.contract_batch);
@@ -278,6 +294,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   p.aux_bs = g.aux_bs;
   p.out_f32 = g.out_f32;
   p.out_ld = g.out_ld;
+  p.out_trans = (epi == EPI_ATOMIC && g.out_trans) ? 1 : 0;
   p.red_out = g.red_out;
   p.red_mode = g.red_out ? g.red_mode : 0;
   if (p.red_mode < 0 || p.red_mode > 2 || (p.red_mode && epi == EPI_ATOMIC)) return fail(VMLP_EINVAL, "bad red_mode");
@@ -328,6 +345,7 @@ int gemm_impl(const vmlp_gemm_args& g, cudaStream_t st) {
   const long long clusters = dv.sms / cg;
   const int grid = (int)(total < clusters ? total : clusters) * cg;
   if (cg == 2) return launch_gemm_bn<256, 2>(epi, ta, tb, td, td2, tpf, p, grid, st);
+  if (bn == 208) return launch_gemm_t<208, EPI_ATOMIC, 1>(ta, tb, td, td2, tpf, p, grid, st);
   if (bn == 256) return launch_gemm_bn<256, 1>(epi, ta, tb, td, td2, tpf, p, grid, st);
   return launch_gemm_bn<128, 1>(epi, ta, tb, td, td2, tpf, p, grid, st);
 }
@@ -487,13 +505,13 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   const int smem = tokmix_plan(p, B, N, C, Ds, false);
   if (!smem) return fail(VMLP_EINVAL, "tokmix_fwd: unsupported shape B %d N %d C %d Ds %d", B, N, C, Ds);
   if (!xhat || !x || !w1_pad || !w2 || !b1 || !b2 || !u) return fail(VMLP_EINVAL, "tokmix_fwd null pointer");
-  if (Np < N || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_fwd: padded weight pitch %d", Np);
+  if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_fwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.b2 = (cbf)b2; p.resid = (cbf)x; p.out = (bf)u;
   CUtensorMap tX, tW1, tW1t, tW2, tH, tR;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
-  if ((rc = make_map(&tW1, w1_pad, N, Ds, 1, Np, 0, 64, 32))) return rc;
-  if ((rc = make_map(&tW1t, w1_pad, N, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tW1, w1_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
+  if ((rc = make_map(&tW1t, w1_pad, p.NT, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tW2, w2, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
   if (hT) { if ((rc = make_map(&tH, hT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc; }
   else tH = tW2;
@@ -517,16 +535,16 @@ int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const 
   const int smem = tokmix_plan(p, B, N, C, Ds, true);
   if (!smem) return fail(VMLP_EINVAL, "tokmix_bwd: unsupported shape B %d N %d C %d Ds %d", B, N, C, Ds);
   if (!xhat || !du || !w1_pad || !w2T_pad || !w1T || !b1 || !dxhat || !dzT) return fail(VMLP_EINVAL, "tokmix_bwd null pointer");
-  if (Np < N || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_bwd: padded weight pitch %d", Np);
+  if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_bwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.out = (bf)dxhat; p.db1 = db1;
   CUtensorMap tX, tDU, tW1, tW1t, tW2T, tW2Tt, tW1T, tDZ;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
   if ((rc = make_map(&tDU, du, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
-  if ((rc = make_map(&tW1, w1_pad, N, Ds, 1, Np, 0, 64, 32))) return rc;
-  if ((rc = make_map(&tW1t, w1_pad, N, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&tW2T, w2T_pad, N, Ds, 1, Np, 0, 64, 32))) return rc;
-  if ((rc = make_map(&tW2Tt, w2T_pad, N, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tW1, w1_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
+  if ((rc = make_map(&tW1t, w1_pad, p.NT, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  if ((rc = make_map(&tW2T, w2T_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
+  if ((rc = make_map(&tW2Tt, w2T_pad, p.NT, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tW1T, w1T, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
   if ((rc = make_map(&tDZ, dzT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc;
   static std::atomic<int> optin[64];
@@ -581,6 +599,13 @@ int vmlp_device_check(void) {
   return VMLP_OK;
 }
 int vmlp_sm_count(void) { return device_info().sms; }
+int vmlp_debug_read(uint32_t* out, int32_t n_words) {
+  const DeviceInfo& dv = device_info();
+  if (!dv.dbg_host || !out || n_words <= 0) return 0;
+  const int n = n_words < DBG_WORDS ? n_words : DBG_WORDS;
+  for (int i = 0; i < n; ++i) out[i] = reinterpret_cast<volatile unsigned int*>(dv.dbg_host)[i];
+  return n;
+}
 int64_t vmlp_launch_count(void) { return g_launches.load(); }
 
 int vmlp_gemm_bf16(const vmlp_gemm_args* args, vmlp_stream_t stream) {
@@ -1169,6 +1194,7 @@ static int mixer_check(const vmlp_mixer_params* p) {
   return VMLP_OK;
 }
 static inline int pad8(int n) { return (n + 7) & ~7; }
+static inline int pad16(int n) { return (n + 15) & ~15; }   // pitch of the zero-padded token weights (k-steps of 16)
 // The token-mixing half runs as the fused on-chip kernels (tokmix_sm100.cuh) whenever both directions support the
 // shape; VMLP_TOKMIX=0 (read once) keeps the unfused GEMM sequence for A/B measurements.
 static bool mixer_token_fused(const vmlp_mixer_params* p) {
@@ -1186,7 +1212,7 @@ int vmlp_mixer_block_fwd(const vmlp_mixer_params* p, const void* x, void* y, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = p->B, N = p->N, C = p->C, Ds = p->Ds, Dc = p->Dc;
   const long long R = (long long)B * N;
-  const int Np = pad8(N);
+  const int Np = pad16(N);
   float* mean1 = s->stats; float* rstd1 = mean1 + R; float* mean2 = rstd1 + R; float* rstd2 = mean2 + R;
 
   // ---- token mixing: u = x + W2t * gelu(W1t * LN1(x) + b1t) + b2t  (contraction over tokens, per image)
@@ -1257,7 +1283,7 @@ int64_t vmlp_mixer_bwd_workspace_elems(const vmlp_mixer_params* p) {
   const int64_t tok = (int64_t)p->Ds * C, chn = (int64_t)p->N * p->Dc;
   const int64_t hid = (int64_t)p->B * (tok > chn ? tok : chn);
   // dZ (max of both halves) + dXhat + dU + the transposed token weights of the fused backward (W2t^T [Ds, Np], W1t^T [N, Ds])
-  return hid + 2 * R * C + (int64_t)p->Ds * pad8(p->N) + (int64_t)pad8(p->N) * p->Ds;
+  return hid + 2 * R * C + (int64_t)p->Ds * pad16(p->N) + (int64_t)pad16(p->N) * p->Ds;
 }
 
 int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* dy, void* dx,
@@ -1270,7 +1296,7 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int B = p->B, N = p->N, C = p->C, Ds = p->Ds, Dc = p->Dc;
   const long long R = (long long)B * N;
-  const int Np = pad8(N);
+  const int Np = pad16(N);
   float* mean1 = s->stats; float* rstd1 = mean1 + R; float* mean2 = rstd1 + R; float* rstd2 = mean2 + R;
   // fp32 gradient accumulators, in vmlp_mixer_params order
   float* g_ln1w = grads;            float* g_ln1b = g_ln1w + C;
@@ -1320,9 +1346,11 @@ int vmlp_mixer_block_bwd(const vmlp_mixer_params* p, const void* x, const void* 
     if ((rc = tokmix_prepare_impl(p->w2t, N, Ds, nullptr, 0, w2T_pad, Np, st))) return rc;
     if ((rc = tokmix_prepare_impl(p->w1t, Ds, N, nullptr, 0, w1T, Ds, st))) return rc;
     if ((rc = tokmix_bwd_impl(s->xhat1, dU, s->w1t_pad, w2T_pad, Np, w1T, p->b1t, dXh, dZ, g_b1t, B, N, C, Ds, st))) return rc;
-    {  // dW2t [N, Ds] += sum_b dU[b] [N, C] * H^T[b] [C, Ds]        (B operand MN-major: rows = contraction index c)
-      vmlp_gemm_args g = gemm_args(N, Ds, C, B, opnd(dU, N, C, C, (long long)N * C, 0), opnd(s->h1, C, Ds, Ds, (long long)C * Ds, 1), VMLP_EPI_ATOMIC);
-      g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds;
+    {  // dW2t^T [Ds, N] += sum_b H^T[b]^T [Ds, C] * dU[b]^T [C, N], added transposed into dW2t [N, Ds]: the same
+       // (M = Ds in 128-row tiles, N = 196 in one 208-column tile) shape as dW1t below -- 1.2x padded MMA work
+       // instead of the 1.7x of a [256-row x 4 x 256-column] tiling of [196, 784]
+      vmlp_gemm_args g = gemm_args(Ds, N, C, B, opnd(s->h1, C, Ds, Ds, (long long)C * Ds, 1), opnd(dU, N, C, C, (long long)N * C, 0), VMLP_EPI_ATOMIC);
+      g.contract_batch = 1; g.out_f32 = g_w2t; g.out_ld = Ds; g.out_trans = 1;
       if ((rc = gemm_impl(g, st))) return rc;
     }
     if (!fused_sums && (rc = vmlp_rowsum_batched(dU, g_b2t, B, N, C, stream))) return rc;

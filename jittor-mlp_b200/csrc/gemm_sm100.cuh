@@ -61,6 +61,7 @@ struct GemmParams {
   long long aux_ld, aux_bs;       // row stride, batch stride (elements)
   float* out_f32;                 // EPI_ATOMIC destination
   long long out_ld;
+  int out_trans;                  // EPI_ATOMIC: element (m, n) is added at out_f32[n * out_ld + m] (the transposed gradient)
   float* red_out;                 // optional fp32 accumulator of the bf16-rounded D: per column (red_mode 1) or per row (2)
   int red_mode;                   //   = bias gradient of the layer whose d(pre-activation) this GEMM produces
   __nv_bfloat16* d2;              // second output of the *_DUAL / GELU epilogues (direct stores)
@@ -127,10 +128,11 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool is_leader = (cta_rank == 0);
   const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
   constexpr int STAGES = L::STAGES;
-  constexpr int NCHUNK = BN / 64;
+  constexpr int NCHUNK = (BN + 63) / 64;   // BN = 208 (token weight gradients, N = 196): the last chunk is 16 columns wide
   constexpr bool HAS_AUX = (epi_is_resid(EPI) || EPI == EPI_DGELU || epi_is_mul(EPI));
   constexpr bool DUAL = epi_is_dual(EPI);
   constexpr bool TMA_AUX = L::TMA_AUX;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256u : 512u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + L::STAGING_OFF;
@@ -163,9 +165,9 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 1) {
-    // 2 accumulator stages x BN fp32 columns (power of two: 256 / 512); for CG = 2 one warp of EACH CTA takes part
-    if (CG == 2) { tmem_alloc_2cta(tmem_slot, 2 * BN); tmem_relinquish_2cta(); }
-    else { tmem_alloc(tmem_slot, 2 * BN); tmem_relinquish(); }
+    // 2 accumulator stages x BN fp32 columns, rounded up to a power of two (256 / 512); for CG = 2 one warp of EACH CTA takes part
+    if (CG == 2) { tmem_alloc_2cta(tmem_slot, TMEM_COLS); tmem_relinquish_2cta(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -383,10 +385,17 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int cols = col0 + st * 16;
         if (EPI == EPI_ATOMIC) {
           if (row_ok) {
-            float* orow = p.out_f32 + (long long)grow * p.out_ld;
+            if (!p.out_trans) {
+              float* orow = p.out_f32 + (long long)grow * p.out_ld;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (cols + j < p.N) red_add_f32(orow + cols + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 16; ++j)
+                if (cols + j < p.N) red_add_f32(orow + cols + j, __uint_as_float(v[j]));
+            } else {          // lanes = consecutive rows m: each RED of the warp covers 32 consecutive floats
+              float* ocol = p.out_f32 + (long long)cols * p.out_ld + grow;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cols + j < p.N) red_add_f32(ocol + (long long)j * p.out_ld, __uint_as_float(v[j]));
+            }
           }
           continue;
         }
@@ -564,7 +573,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (CG == 2) cluster_sync_all(); else __syncthreads();   // neither CTA may exit while its peer still uses it
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 2) tmem_dealloc_2cta(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -64,15 +64,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded wait: a protocol bug must trap (CUDA error on the host) instead of
-// hanging the GPU box.  2^32 cycles is > 2 s at any B200 clock.
+// Bounded wait: a protocol bug must end the kernel (CUDA error on the host) instead of hanging the GPU box.
+// 2^31 cycles is > 1 s at any B200 clock.  Before trapping, lane 0 of the waiting warp records (block, warp, barrier
+// address, parity) in a host-mapped buffer (vmlp_debug_read): a trap discards the device printf buffer, host memory
+// survives the dead context.
+__device__ unsigned int* g_vmlp_dbg = nullptr;      // host-mapped: [0] = record count, then 4 words per record
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 32)) {
-      printf("vmlp: mbarrier timeout block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
+    if (clock64() - t0 > (1ll << 31)) {
+      if ((threadIdx.x & 31) == 0 && g_vmlp_dbg != nullptr) {
+        const unsigned int slot = atomicAdd_system(g_vmlp_dbg, 1u);
+        if (slot < 200) {
+          volatile unsigned int* r = g_vmlp_dbg + 4 + 4 * slot;
+          r[0] = blockIdx.x; r[1] = threadIdx.x >> 5; r[2] = smem_u32(bar); r[3] = parity;
+        }
+        __threadfence_system();
+      }
+      const long long t1 = clock64();
+      while (clock64() - t1 < (1ll << 27)) {}      // let the other waiters of the same deadlock record theirs
       __trap();
     }
   }

@@ -56,9 +56,12 @@ struct TokParams {
   float* db1;                // [Ds] fp32   backward: += sum over (b, c) of dZ (the hidden-bias gradient)
 };
 
-// shared-memory descriptor high words (SBO, version 1, layout type); K-major operands never use LBO
+// shared-memory descriptor high words (SBO, version 1, layout type).  K-major swizzled operands carry LBO = 1 (one
+// 16-byte unit between the two halves of a 32-byte k-step, the canonical ((8,n),2):((SW,SBO),1) layout of the tcgen05
+// descriptor): with LBO = 0 a SWIZZLE_32B operand read the first 16 bytes of every row twice (first bring-up run).
 constexpr uint32_t TM_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t TM_DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);
+constexpr uint32_t TM_LBO_K = 1u << 16;
 
 __device__ __forceinline__ void tm_arrive_leader(uint64_t* bar, bool is_leader) {
   if (is_leader) mbar_arrive(bar);
@@ -89,7 +92,7 @@ __device__ __forceinline__ void tm_mma_over_tokens(uint32_t d_tmem, uint32_t act
                                                    const TokParams& p) {
   const uint32_t a_lbo = (static_cast<uint32_t>(p.NT) * 128u) >> 4;      // distance between the two 64-channel atoms
   uint32_t a_lo = (act_addr >> 4) | (a_lbo << 16);
-  const uint32_t b_base = w_addr >> 4;
+  const uint32_t b_base = (w_addr >> 4) | TM_LBO_K;
   const int ks_full = p.kf * 4;
   for (int ks = 0; ks < ks_full; ++ks) {
     umma_bf16_lo<2>(d_tmem, a_lo, b_base + (ks >> 2) * 256 + (ks & 3) * 2, TM_DESC_HI_SW128, idesc, ks ? 1u : 0u);
@@ -107,7 +110,7 @@ __device__ __forceinline__ void tm_mma_over_tokens(uint32_t d_tmem, uint32_t act
 // G2/G3-type MMA: D[tmem] (+)= A (hidden tile in SMEM, K-major) * B ([NT/2 rows x 64 k] weight stage), ksteps of 16
 __device__ __forceinline__ void tm_mma_over_hidden(uint32_t d_tmem, uint32_t h_addr, uint32_t w_addr, uint32_t idesc,
                                                    int ksteps, bool first) {
-  const uint32_t a_base = h_addr >> 4, b_base = w_addr >> 4;
+  const uint32_t a_base = (h_addr >> 4) | TM_LBO_K, b_base = (w_addr >> 4) | TM_LBO_K;
   for (int ks = 0; ks < ksteps; ++ks)
     umma_bf16_lo<2>(d_tmem, a_base + ks * 2, b_base + ks * 2, TM_DESC_HI_SW128, idesc, (first && ks == 0) ? 0u : 1u);
 }

@@ -73,8 +73,12 @@ class S2v2SplitAttentionFn(torch.autograd.Function):
         a32 = _f32(B * C, t.device)
         L.check(lib.vmlp_s2v2_sum(t.data_ptr(), a32.data_ptr(), B, H, W, C, L.stream_ptr()))
         with torch.enable_grad():
+            # The pooled vector is a SUM over all tokens of three branches (s2_mlp_v2.py:44): one bf16 ulp of it moves the
+            # softmax logits visibly.  It enters the first Linear as hi + lo (two bf16 terms, ~16 mantissa bits): the GEMM
+            # contracts over [hi | lo] against [W1 | W1], so the tensor-core path keeps its bf16 operands.
             a_in = cast_f32_to_bf16(a32).view(B, C).requires_grad_(True)
-            hat = fn.linear(fn.linear_gelu(a_in, w1, None), w2, None)            # [B, 3C], graph kept for backward
+            a_lo = cast_f32_to_bf16(a32 - a_in.detach().float().view(-1)).view(B, C)
+            hat = fn.linear(fn.linear_gelu(torch.cat([a_in, a_lo], 1), torch.cat([w1, w1], 1), None), w2, None)   # [B, 3C]
         hat_d = hat.detach()
         out = torch.empty(B, H, W, C, dtype=BF16, device=t.device)
         L.check(lib.vmlp_s2v2_combine(t.data_ptr(), hat_d.data_ptr(), out.data_ptr(), B, H, W, C, L.stream_ptr()))

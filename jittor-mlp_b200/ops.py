@@ -44,7 +44,8 @@ def operand(t, major, batched=None):
 
 
 def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=None, D2=None, bias=None,
-         bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0, cta_group=0, red_out=None, red_mode=0):
+         bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0, cta_group=0, red_out=None, red_mode=0,
+         out_trans=False):
     """Generic fused GEMM, see vmlp_gemm_bf16 in include/vmlp_b200.h.  A/B are L.Operand."""
     g = L.GemmArgs()
     g.M, g.N, g.K, g.batch, g.contract_batch = M, N, K, batch, int(contract_batch)
@@ -67,7 +68,7 @@ def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=N
     if out_f32 is not None:
         _chk(out_f32, "out_f32", torch.float32)
         g.out_f32, g.out_ld = out_f32.data_ptr(), out_f32.stride(0)
-    g.split_k, g.block_n, g.cta_group = split_k, block_n, cta_group
+    g.split_k, g.block_n, g.cta_group, g.out_trans = split_k, block_n, cta_group, int(out_trans)
     if red_out is not None:
         _chk(red_out, "red_out", torch.float32)
         g.red_out, g.red_mode = red_out.data_ptr(), red_mode
@@ -138,7 +139,7 @@ class MixerBlockFn(torch.autograd.Function):
         fused = bool(L.lib().vmlp_mixer_token_fused(ctypes.byref(p)))
         sv = dict(xhat1=new(B, N, C), z1=None if fused else new(B, Ds, C), h1=new(B, C, Ds) if fused else new(B, Ds, C),
                   u=new(B, N, C), xhat2=new(B, N, C), z2=new(B * N, Dc), h2=new(B * N, Dc),
-                  stats=torch.empty(4, B * N, dtype=torch.float32, device=dev), w1t_pad=new(Ds, (N + 7) // 8 * 8))
+                  stats=torch.empty(4, B * N, dtype=torch.float32, device=dev), w1t_pad=new(Ds, (N + 15) // 16 * 16))
         s = L.MixerSaved(**{k: _ptr(v) for k, v in sv.items()})
         L.check(L.lib().vmlp_mixer_block_fwd(ctypes.byref(p), x.data_ptr(), y.data_ptr(), ctypes.byref(s),
                                              L.stream_ptr()))
@@ -444,11 +445,11 @@ def tokmix_supported(B, N, C, Ds, backward=False):
 
 
 def tokmix_prepare(w, pad=False, transpose=False, ldt=None):
-    """K-major operand copies of a [rows, cols] weight for the fused kernels: (zero-padded [rows, ceil8(cols)] copy,
+    """K-major operand copies of a [rows, cols] weight for the fused kernels: (zero-padded [rows, ceil16(cols)] copy,
     transposed [cols, ldt] copy); entries not asked for are None."""
     _chk(w, "w")
     rows, cols = w.shape
-    ld = (cols + 7) // 8 * 8
+    ld = (cols + 15) // 16 * 16
     ldt = rows if ldt is None else ldt
     wp = _new(rows, ld, like=w) if pad else None
     wt = _new(cols, ldt, like=w) if transpose else None
@@ -477,7 +478,7 @@ def tokmix_bwd(xhat, du, w1, b1, w2):
         _chk(t, n)
     B, N, C = xhat.shape
     Ds = w1.shape[0]
-    Np = (N + 7) // 8 * 8
+    Np = (N + 15) // 16 * 16
     w1p, w1T = tokmix_prepare(w1.view(Ds, N), pad=True, transpose=True)
     _, w2T = tokmix_prepare(w2.view(N, Ds), transpose=True, ldt=Np)
     dxh = torch.empty_like(xhat)

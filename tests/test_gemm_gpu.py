@@ -209,3 +209,24 @@ def test_fused_bias_gradient_reductions(cg):
     red = torch.zeros(Ds, dtype=torch.float32, device=DEV)
     ops.gemm(Ds, C, Nt, ops.operand(W, 1), ops.operand(dU, 1), L.EPI_DGELU, batch=Bn, D=dZ, aux=G, red_out=red, red_mode=2, cta_group=1)
     assert rel(red, dZ.float().sum((0, 2))) < 1e-4
+
+
+@pytest.mark.parametrize("Nt,Ds", [(196, 784), (144, 136), (208, 128)])
+def test_token_weight_gradient_tile_208_and_transposed_output(Nt, Ds):
+    """The token weight gradients of the fused Mixer block: out [Ds, Nt] with Nt in (128, 208] takes the 208-column
+    tile (one N tile instead of a 256-wide one), A is the transposed hidden tensor [B, C, Ds] (MN-major), contraction
+    over (batch, channels); out_trans adds the result transposed into a [Nt, Ds] gradient."""
+    Bn, C = 6, 192
+    HT, dU = rnd(Bn, C, Ds, seed=1), rnd(Bn, Nt, C, seed=2)
+    ref = torch.einsum("bcm,bnc->mn", HT.float(), dU.float())
+    out = torch.zeros(Ds, Nt, dtype=torch.float32, device=DEV)
+    ops.gemm(Ds, Nt, C, ops.operand(HT, 1), ops.operand(dU, 0), L.EPI_ATOMIC, batch=Bn, contract_batch=True, out_f32=out)
+    assert rel(out, ref) < 2e-3
+    out_t = torch.zeros(Nt, Ds, dtype=torch.float32, device=DEV)
+    ops.gemm(Ds, Nt, C, ops.operand(HT, 1), ops.operand(dU, 0), L.EPI_ATOMIC, batch=Bn, contract_batch=True, out_f32=out_t,
+             out_trans=True)
+    assert rel(out_t, ref.t()) < 2e-3
+    out256 = torch.zeros(Ds, Nt, dtype=torch.float32, device=DEV)
+    ops.gemm(Ds, Nt, C, ops.operand(HT, 1), ops.operand(dU, 0), L.EPI_ATOMIC, batch=Bn, contract_batch=True, out_f32=out256,
+             block_n=256)
+    assert rel(out256, ref) < 2e-3

@@ -1,13 +1,19 @@
 #!/bin/bash
-# bring-up of the fused token-mixing kernels: every shape in its own process, bounded by timeout
+# GPU call: bring-up of the fused token-mixing kernels, then the parity suite and the bench (fused and unfused token path)
 mkdir -p gpurun_out
-L=gpurun_out/tokmix_bringup.log
-: > $L
-for s in "2 16 64 64" "2 64 128 256" "3 64 128 256" "2 49 200 200" "5 80 256 136" "2 100 128 320" "2 20 128 128" "4 196 768 784" "2 196 1024 784" "1 256 384 1024" "256 196 768 784"; do
-  for w in fwd bwd; do
-    echo "== $s $w" >> $L
-    timeout 180 python tools/tokmix_check.py $s $w >> $L 2>&1
-    echo "exit $?" >> $L
-  done
-done
-grep -E "TOKMIX|exit|timeout|error|Error" $L | tail -60
+python tools/tokmix_check.py --all > gpurun_out/tokmix_bringup.log 2>&1
+rc=$?
+tail -40 gpurun_out/tokmix_bringup.log
+if [ $rc -eq 0 ]; then
+  ( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1
+  tail -30 gpurun_out/pytest_gpu.log
+  ( timeout 600 python bench.py ) > gpurun_out/bench_fused.log 2> gpurun_out/bench_fused.err
+  tail -c 1500 gpurun_out/bench_fused.log; tail -3 gpurun_out/bench_fused.err
+  ( VMLP_TOKMIX=0 timeout 600 python bench.py ) > gpurun_out/bench_unfused.log 2> gpurun_out/bench_unfused.err
+  tail -c 600 gpurun_out/bench_unfused.log
+else
+  ( time VMLP_TOKMIX=0 timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_tokmix_gpu.py ) > gpurun_out/pytest_gpu.log 2>&1
+  tail -30 gpurun_out/pytest_gpu.log
+  ( VMLP_TOKMIX=0 timeout 600 python bench.py ) > gpurun_out/bench_unfused.log 2> gpurun_out/bench_unfused.err
+  tail -c 600 gpurun_out/bench_unfused.log
+fi
