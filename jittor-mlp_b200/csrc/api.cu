@@ -460,21 +460,24 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   p.n_pairs = (p.n_tiles + 1) / 2;
   p.n_chunks = (Ds + TM_CH - 1) / TM_CH;
   p.last_n1 = (Ds - (p.n_chunks - 1) * TM_CH + 15) & ~15;
-  p.kf = p.NT / 64;
-  p.tail = p.NT % 64;
-  p.wa_stage = p.kf * 4096 + (p.tail == 16 ? 1024 : p.tail ? 4096 : 0);
+  p.ka = (p.NT + 63) / 64;
+  p.wa_stage = p.ka * 4096;
   p.wb_stage = p.NT * 64;
   p.inv_tiles_c = 1.0f / (float)p.tiles_c;
   if ((long long)p.n_tiles >= (1ll << 22)) return 0;
-  const int fixed = TM_BAR_BYTES + 1024 /* alignment slack */ + 2 * TM_HTILE + p.NT * 256 * (backward ? 2 : 1) +
-                    p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
-  for (int depth = 4; depth >= 2; --depth) {
-    const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
-    if (fixed + rings <= TM_SMEM_MAX) {
-      p.s_wa = p.s_wb = depth;
-      // never less than half an SM's shared memory: one CTA per SM, so the 512-column TMEM allocation of a CTA pair can
-      // never wait for a co-resident CTA of another pair (allocation order across two SMs could deadlock)
-      return fixed + rings > 120 * 1024 ? fixed + rings : 120 * 1024;
+  // shared memory: barriers + alignment slack, activation tile(s), weight rings, hidden tile(s), fp32 bias (+ d-bias sums)
+  for (int nhb = 2; nhb >= (backward ? 1 : 2); --nhb) {
+    const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * (backward ? 2 : 1) +
+                      p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
+    for (int depth = 4; depth >= 2; --depth) {
+      const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
+      if (fixed + rings <= TM_SMEM_MAX) {
+        p.s_wa = p.s_wb = depth;
+        p.nhb = nhb;
+        // never less than half an SM's shared memory: one CTA per SM, so the 512-column TMEM allocation of a CTA pair can
+        // never wait for a co-resident CTA of another pair (allocation order across two SMs could deadlock)
+        return fixed + rings > 120 * 1024 ? fixed + rings : 120 * 1024;
+      }
     }
   }
   return 0;
@@ -507,11 +510,10 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   if (!xhat || !x || !w1_pad || !w2 || !b1 || !b2 || !u) return fail(VMLP_EINVAL, "tokmix_fwd null pointer");
   if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_fwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.b2 = (cbf)b2; p.resid = (cbf)x; p.out = (bf)u;
-  CUtensorMap tX, tW1, tW1t, tW2, tH, tR;
+  CUtensorMap tX, tW1, tW2, tH, tR;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
   if ((rc = make_map(&tW1, w1_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
-  if ((rc = make_map(&tW1t, w1_pad, p.NT, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tW2, w2, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
   if (hT) { if ((rc = make_map(&tH, hT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc; }
   else tH = tW2;
@@ -521,7 +523,7 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   tokmix_launch_cfg(cfg, attr, p, smem, st);
-  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_fwd_sm100, tX, tW1, tW1t, tW2, tH, tR, p, hT ? 1 : 0));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_fwd_sm100, tX, tW1, tW2, tH, tR, p, hT ? 1 : 0));
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
@@ -537,14 +539,12 @@ int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const 
   if (!xhat || !du || !w1_pad || !w2T_pad || !w1T || !b1 || !dxhat || !dzT) return fail(VMLP_EINVAL, "tokmix_bwd null pointer");
   if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_bwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.out = (bf)dxhat; p.db1 = db1;
-  CUtensorMap tX, tDU, tW1, tW1t, tW2T, tW2Tt, tW1T, tDZ;
+  CUtensorMap tX, tDU, tW1, tW2T, tW1T, tDZ;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
   if ((rc = make_map(&tDU, du, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
   if ((rc = make_map(&tW1, w1_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
-  if ((rc = make_map(&tW1t, w1_pad, p.NT, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tW2T, w2T_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
-  if ((rc = make_map(&tW2Tt, w2T_pad, p.NT, Ds, 1, Np, 0, 16, 32, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   if ((rc = make_map(&tW1T, w1T, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
   if ((rc = make_map(&tDZ, dzT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc;
   static std::atomic<int> optin[64];
@@ -552,7 +552,7 @@ int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const 
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   tokmix_launch_cfg(cfg, attr, p, smem, st);
-  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_bwd_sm100, tX, tDU, tW1, tW1t, tW2T, tW2Tt, tW1T, tDZ, p));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_bwd_sm100, tX, tDU, tW1, tW2T, tW1T, tDZ, p));
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

@@ -43,9 +43,9 @@ struct TokParams {
   int n_pairs;               // ceil(n_tiles / 2)
   int n_chunks;              // ceil(Ds / 64)
   int last_n1;               // hidden columns of the last chunk, rounded up to 16
-  int kf;                    // full 64-wide K atoms along the token axis (NT / 64)
-  int tail;                  // NT % 64: 0, or 16 (SWIZZLE_32B tail atom), or 32 / 48 (a full SWIZZLE_128B atom)
-  int wa_stage;              // bytes of one [32 rows x NT k] weight stage (G1 / G2-of-backward B operand)
+  int ka;                    // 64-wide K atoms along the token axis: ceil(NT / 64) (the last one may be partly used)
+  int nhb;                   // hidden-tile buffers in shared memory: 2, or 1 when two do not fit (backward, NT = 208)
+  int wa_stage;              // bytes of one [32 rows x NT k] weight stage (G1 / G2-of-backward B operand): ka * 4 KB
   int wb_stage;              // bytes of one [NT/2 rows x 64 k] weight stage (output-GEMM B operand)
   int s_wa, s_wb;            // ring depths
   float inv_tiles_c;
@@ -56,11 +56,12 @@ struct TokParams {
   float* db1;                // [Ds] fp32   backward: += sum over (b, c) of dZ (the hidden-bias gradient)
 };
 
-// shared-memory descriptor high words (SBO, version 1, layout type).  K-major swizzled operands carry LBO = 1 (one
-// 16-byte unit between the two halves of a 32-byte k-step, the canonical ((8,n),2):((SW,SBO),1) layout of the tcgen05
-// descriptor): with LBO = 0 a SWIZZLE_32B operand read the first 16 bytes of every row twice (first bring-up run).
+// shared-memory descriptor high word (SBO = 1024 B between 8-row groups, version 1, SWIZZLE_128B); K-major swizzled
+// operands carry LBO = 1 (16 bytes), the canonical ((8,n),2):((8,SBO),1) form.  Every operand here is SWIZZLE_128B: a
+// SWIZZLE_32B tail atom for the 16 left-over token columns (NT = 208 = 3 x 64 + 16) produced wrong products and, behind
+// three full atoms, a launch failure on the first two bring-up runs -- the tail is a fourth 64-wide atom instead, of
+// which only the first k-step is issued.
 constexpr uint32_t TM_DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-constexpr uint32_t TM_DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);
 constexpr uint32_t TM_LBO_K = 1u << 16;
 
 __device__ __forceinline__ void tm_arrive_leader(uint64_t* bar, bool is_leader) {
@@ -80,12 +81,9 @@ __device__ __forceinline__ uint32_t bf16_bits(float f) {
   return *reinterpret_cast<unsigned short*>(&h);
 }
 
-// TMA loads of one [32 rows x NT k] weight stage (K-major): kf full SWIZZLE_128B atoms + the tail atom
-__device__ __forceinline__ void tm_load_wa(uint32_t dst, uint64_t map128, uint64_t map32, uint32_t bar, int row,
-                                           const TokParams& p) {
-  for (int a = 0; a < p.kf; ++a) tma_load_3d_u32<2>(dst + a * 4096, map128, bar, a * 64, row, 0);
-  if (p.tail == 16) tma_load_3d_u32<2>(dst + p.kf * 4096, map32, bar, p.kf * 64, row, 0);
-  else if (p.tail) tma_load_3d_u32<2>(dst + p.kf * 4096, map128, bar, p.kf * 64, row, 0);
+// TMA loads of one [32 rows x NT k] weight stage (K-major): ka SWIZZLE_128B atoms of [32 rows x 64 k]
+__device__ __forceinline__ void tm_load_wa(uint32_t dst, uint64_t map128, uint32_t bar, int row, const TokParams& p) {
+  for (int a = 0; a < p.ka; ++a) tma_load_3d_u32<2>(dst + a * 4096, map128, bar, a * 64, row, 0);
 }
 // G1-type MMA: D[tmem] = A (MN-major activation tile, k-steps over the token axis) * B (weight stage); n1 = UMMA N
 __device__ __forceinline__ void tm_mma_over_tokens(uint32_t d_tmem, uint32_t act_addr, uint32_t w_addr, uint32_t idesc,
@@ -93,18 +91,10 @@ __device__ __forceinline__ void tm_mma_over_tokens(uint32_t d_tmem, uint32_t act
   const uint32_t a_lbo = (static_cast<uint32_t>(p.NT) * 128u) >> 4;      // distance between the two 64-channel atoms
   uint32_t a_lo = (act_addr >> 4) | (a_lbo << 16);
   const uint32_t b_base = (w_addr >> 4) | TM_LBO_K;
-  const int ks_full = p.kf * 4;
-  for (int ks = 0; ks < ks_full; ++ks) {
+  const int ksteps = p.NT >> 4;
+  for (int ks = 0; ks < ksteps; ++ks) {
     umma_bf16_lo<2>(d_tmem, a_lo, b_base + (ks >> 2) * 256 + (ks & 3) * 2, TM_DESC_HI_SW128, idesc, ks ? 1u : 0u);
     a_lo += 2048u >> 4;                                                   // 16 token rows of 128 B
-  }
-  if (p.tail == 16) {
-    umma_bf16_lo<2>(d_tmem, a_lo, b_base + p.kf * 256, TM_DESC_HI_SW32, idesc, ks_full ? 1u : 0u);
-  } else {
-    for (int ks = 0; ks < (p.tail >> 4); ++ks) {
-      umma_bf16_lo<2>(d_tmem, a_lo, b_base + p.kf * 256 + ks * 2, TM_DESC_HI_SW128, idesc, (ks_full + ks) ? 1u : 0u);
-      a_lo += 2048u >> 4;
-    }
   }
 }
 // G2/G3-type MMA: D[tmem] (+)= A (hidden tile in SMEM, K-major) * B ([NT/2 rows x 64 k] weight stage), ksteps of 16
@@ -146,8 +136,7 @@ __device__ __forceinline__ void tm_store_hidden_row(uint32_t tile_addr, int row,
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TM_THREADS, 1)
 tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]   box (64 c, NT rows)
-                 const __grid_constant__ CUtensorMap tmW1,     // W1   [Ds, N]     box (64 k, 32 rows) SWIZZLE_128B
-                 const __grid_constant__ CUtensorMap tmW1t,    // W1   tail        box (16 k, 32 rows) SWIZZLE_32B
+                 const __grid_constant__ CUtensorMap tmW1,     // W1   [Ds, NT]    box (64 k, 32 rows) SWIZZLE_128B
                  const __grid_constant__ CUtensorMap tmW2,     // W2   [N, Ds]     box (64 k, NT/2 rows)
                  const __grid_constant__ CUtensorMap tmH,      // H^T  [B, C, Ds]  box (64 m, 128 c)  (saved for backward)
                  const __grid_constant__ CUtensorMap tmR,      // x    [B, N, C]   box (128 c, NT rows), L2 prefetch only
@@ -177,7 +166,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   float* sb2 = sb1 + p.n_chunks * TM_CH;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW1t); tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmR);
     mbar_init(xt_full, 1); mbar_init(xt_empty, 1);
     mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
@@ -204,7 +193,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs; bytes signalled on the leader)
     const uint64_t mX = reinterpret_cast<uint64_t>(&tmX), mW1 = reinterpret_cast<uint64_t>(&tmW1),
-                   mW1t = reinterpret_cast<uint64_t>(&tmW1t), mW2 = reinterpret_cast<uint64_t>(&tmW2);
+                   mW2 = reinterpret_cast<uint64_t>(&tmW2);
     const uint32_t b_xt = leader_cta_addr(smem_u32(xt_full));
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     auto load_wa = [&](int j) {
@@ -212,7 +201,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       mbar_wait(&wa_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&wa_full[sa], 2 * p.wa_stage);
-        tm_load_wa(s_wa + sa * p.wa_stage, mW1, mW1t, leader_cta_addr(smem_u32(&wa_full[sa])),
+        tm_load_wa(s_wa + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&wa_full[sa])),
                    j * TM_CH + cta_rank * (n1 >> 1), p);
       }
       __syncwarp();
@@ -443,10 +432,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
 __global__ void __launch_bounds__(TM_THREADS, 1)
 tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C]   box (64 c, NT rows)
                  const __grid_constant__ CUtensorMap tmDU,     // dU    [B, N, C]   box (64 c, NT rows)
-                 const __grid_constant__ CUtensorMap tmW1,     // W1    [Ds, N]     box (64 k, 32 rows)
-                 const __grid_constant__ CUtensorMap tmW1t,    // W1    tail        box (16 k, 32 rows) SWIZZLE_32B
-                 const __grid_constant__ CUtensorMap tmW2T,    // W2^T  [Ds, N]     box (64 k, 32 rows)
-                 const __grid_constant__ CUtensorMap tmW2Tt,   // W2^T  tail
+                 const __grid_constant__ CUtensorMap tmW1,     // W1    [Ds, NT]    box (64 k, 32 rows)
+                 const __grid_constant__ CUtensorMap tmW2T,    // W2^T  [Ds, NT]    box (64 k, 32 rows)
                  const __grid_constant__ CUtensorMap tmW1T,    // W1^T  [N, Ds]     box (64 k, NT/2 rows)
                  const __grid_constant__ CUtensorMap tmDZ,     // dZ^T  [B, C, Ds]  box (64 m, 128 c)
                  const TokParams p) {
@@ -474,12 +461,12 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t s_w2 = s_w1 + p.s_wa * p.wa_stage;
   const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
   const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
-  float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + 2 * TM_HTILE);
+  float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + p.nhb * TM_HTILE);
   float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW1t);
-    tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW2Tt); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
     mbar_init(in_full, 1); mbar_init(in_empty, 1);
     mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
@@ -508,8 +495,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   if (warp == 0) {
     // ================================================================ TMA producer
     const uint64_t mX = reinterpret_cast<uint64_t>(&tmX), mDU = reinterpret_cast<uint64_t>(&tmDU),
-                   mW1 = reinterpret_cast<uint64_t>(&tmW1), mW1t = reinterpret_cast<uint64_t>(&tmW1t),
-                   mW2T = reinterpret_cast<uint64_t>(&tmW2T), mW2Tt = reinterpret_cast<uint64_t>(&tmW2Tt),
+                   mW1 = reinterpret_cast<uint64_t>(&tmW1), mW2T = reinterpret_cast<uint64_t>(&tmW2T),
                    mW1T = reinterpret_cast<uint64_t>(&tmW1T);
     const uint32_t b_in = leader_cta_addr(smem_u32(in_full));
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
@@ -519,13 +505,13 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       mbar_wait(&w1_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
-        tm_load_wa(s_w1 + sa * p.wa_stage, mW1, mW1t, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
+        tm_load_wa(s_w1 + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
       }
       __syncwarp();
       mbar_wait(&w2_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
-        tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, mW2Tt, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
+        tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
       }
       __syncwarp();
       if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
@@ -596,8 +582,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         ++t1;
       };
       auto do_g3 = [&]() {        // ---- dXh^T (+)= dZ^T * W1[chunk, :]
-        const int hb = t3 & 1;
-        mbar_wait(&dz_full[hb], (t3 >> 1) & 1);
+        const int hb = p.nhb == 2 ? (t3 & 1) : 0;
+        mbar_wait(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1);
         mbar_wait(&w3_full[sb], pb);
         if (j3 == 0) mbar_wait(dx_empty, (it3 & 1) ^ 1);
         tc_fence_after();
@@ -631,9 +617,9 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
       const TokTile t = tm_tile(p, pair, cta_rank);
       for (int j = 0; j < NC; ++j, ++g) {
-        const int hb = g & 1;
+        const int hb = p.nhb == 2 ? (g & 1) : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        mbar_wait(&dz_done[hb], (g >> 1) & 1);
+        mbar_wait(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
         if (warp == 2 && elect_one_sync()) {
           if (t.valid) {
             tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
@@ -704,14 +690,16 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
             o[2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
           }
         }
-        mbar_wait(&dz_empty[zb], ((g >> 1) & 1) ^ 1);
-        mbar_wait(&dzs_empty[zb], ((g >> 1) & 1) ^ 1);
-        if (live) tm_store_hidden_row(s_dz + zb * TM_HTILE, row, cq, o);
+        const int hb = p.nhb == 2 ? zb : 0;                        // dZ tile buffer (single-buffered when two do not fit)
+        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        mbar_wait(&dz_empty[hb], hph);                             // G3 of the previous user of this buffer has read it
+        mbar_wait(&dzs_empty[hb], hph);                            // ... and so have its TMA store and column sums
+        if (live) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tm_arrive_leader(&dz_full[zb], is_leader);
-          mbar_arrive(&dz_done[zb]);
+          tm_arrive_leader(&dz_full[hb], is_leader);
+          mbar_arrive(&dz_done[hb]);
         }
       }
       // ---- output: dXh[b, n, ch] = dXh^T[ch, n]
