@@ -258,8 +258,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true")
     ap.add_argument("--graph", type=int, default=-1,
-                    help="1/0: replay the step as a CUDA graph (default: on for 1 GPU; N > 1 runs eager -- the captured "
-                         "NCCL step measured 0.98x linear at 2 GPUs vs 0.96x eager but hung at process-group teardown)")
+                    help="1/0: replay the step as a CUDA graph (default on; for N > 1 the graph holds the compute only and "
+                         "one grouped NCCL all-reduce of the gradient buffers follows every replay)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -286,14 +286,13 @@ def main():
     x_host = torch.randn(B, 3, 224, 224, generator=g).bfloat16().pin_memory()
     x_dev = x_host.to(dev)
 
-    use_graph = (args.graph == 1) or (args.graph == -1 and world == 1)
+    use_graph = args.graph != 0
     gs = None
     if use_graph:
         import jittor_mlp_b200 as J
         try:
-            # one capture; every step below is a single graph launch (N > 1: the NCCL gradient all-reduces are in it)
-            gs = J.GraphedStep(model, x_dev, loss_fn,
-                               step_fn=(lambda xb: ddp.step_fwd_bwd(xb, loss_fn)) if world > 1 else None)
+            # one capture; every step below is a single graph launch (N > 1: + one grouped NCCL gradient all-reduce)
+            gs = J.GraphedStep(model, x_dev, loss_fn, ddp=ddp if world > 1 else None)
         except Exception as e:                             # measurement plumbing only: time the eager step instead
             print(f"bench: CUDA-graph capture failed ({type(e).__name__}: {e}); timing eager steps", file=sys.stderr)
             use_graph = False
@@ -339,7 +338,7 @@ def main():
             cur.wait_event(staged)
             gs.static_x.copy_(staging, non_blocking=True)          # device-side hand-over into the graph's input
             consumed.record(cur)
-            gs.graph.replay()
+            gs.run()                                               # graph replay (+ the gradient all-reduce for N > 1)
             prefetch()                                             # H2D of the next step's images overlaps this step
             return read_loss(gs.static_loss)                       # D2H of this step's loss, consumed one step late
     else:
@@ -423,10 +422,7 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        if gs is not None:          # opt-in --graph 1 with NCCL inside the graph: drop it before tearing NCCL down
-            gs.graph.reset()
-            gs = None
-            torch.cuda.synchronize()
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 

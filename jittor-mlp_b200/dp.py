@@ -33,6 +33,8 @@ class DataParallel(torch.nn.Module):
         self._deferred = []
         self._pending = []      # (work handle, flat bucket tensor)
         self._bucketed = set()  # data_ptrs already covered by an in-flight bucket
+        self._collect = None    # list being filled while a CUDA-graph capture records the static gradient buffers
+        self._static = None     # gradient tensors of a captured step (fixed addresses): exchanged after every replay
         if self.world > 1:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)   # identical replicas
@@ -50,6 +52,9 @@ class DataParallel(torch.nn.Module):
         # Such a bucket is not exchanged here at all: its parameters fall through to finish()'s "rest" path, which
         # averages the accumulated p.grad once, after backward.
         if any(p.grad is not None for p in owners):
+            return
+        if self._collect is not None:   # CUDA-graph capture: no collective inside the graph, remember the buffer
+            self._collect.append(flat)
             return
         if self.mode == "end":          # exchange after the whole backward: no SM contention with the persistent GEMMs
             self._deferred.append(flat)
@@ -101,6 +106,34 @@ class DataParallel(torch.nn.Module):
             if not self._nccl:
                 flat.div_(self.world)
         self._pending.clear()
+
+    # ---- CUDA-graph mode: the captured step is compute only; ONE grouped NCCL all-reduce follows every replay ---------
+    def begin_static_capture(self):
+        """Call before capturing loss.backward() in a CUDA graph: block buckets are recorded instead of exchanged."""
+        self._collect = []
+
+    def end_static_capture(self):
+        """Call after the capture: fixes the list of gradient buffers (block buckets + every p.grad outside them)."""
+        buckets, self._collect = self._collect, None
+        covered = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in buckets]
+        rest = [p.grad for p in self.module.parameters()
+                if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in covered)]
+        self._static = buckets + rest
+
+    def reduce_static(self):
+        """Average the captured step's gradient buffers over ranks: a single grouped NCCL launch (ncclGroupStart/End over
+        all buffers) on NCCL's stream after the backward has finished -- nothing of the exchange shares SMs with the
+        persistent GEMM kernels, and the replayed graph contains no collective (no teardown-order hazards)."""
+        if self.world == 1 or not self._static:
+            return
+        if self._nccl:
+            with dist._coalescing_manager(group=self.group, device=self._static[0].device, async_ops=False):
+                for t in self._static:
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                   # gloo (CPU tests of this logic)
+            for t in self._static:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.div_(self.world)
 
     def step_fwd_bwd(self, x, loss_fn):
         """One data-parallel fwd+bwd on this rank's shard; gradients are averaged over ranks on return."""

@@ -149,3 +149,61 @@ def test_gradient_accumulation_over_two_micro_batches():
     for rank, grads in res:
         for k, g in ref.items():
             assert torch.allclose(grads[k], g, atol=1e-5), (rank, k, (grads[k] - g).abs().max())
+
+
+def _static_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jittor_mlp_b200 import dp
+    torch.manual_seed(5)
+    w = torch.nn.Parameter(torch.randn(4, 8))
+    b = torch.nn.Parameter(torch.randn(4))
+    head = torch.nn.Linear(4, 2)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w, self.b, self.head = w, b, head
+
+        def forward(self, x):
+            return self.head(_FlatLinearFn.apply(x, self.w, self.b))
+
+    model = M()
+    ddp = dp.DataParallel(model)
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(7))
+    # what GraphedStep(ddp=...) does around the capture, minus the CUDA graph: record the buffers, exchange afterwards
+    ddp.begin_static_capture()
+    with ddp:
+        model(xs[rank * 2:(rank + 1) * 2]).square().mean().backward()
+    ddp.end_static_capture()
+    n_static = len(ddp._static)
+    ddp.reduce_static()
+    q.put((rank, n_static, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_static_buffers_of_a_captured_step_are_exchanged_once():
+    """CUDA-graph mode of the DP wrapper (graph.GraphedStep(ddp=...)): block buckets are recorded during the capture, the
+    remaining p.grad tensors are added, and reduce_static() averages each buffer exactly once."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_static_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(5)
+    w = torch.randn(4, 8, requires_grad=True)
+    b = torch.randn(4, requires_grad=True)
+    head = torch.nn.Linear(4, 2)
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(7))
+    head(xs @ w.t() + b).square().mean().backward()
+    ref = {"w": w.grad, "b": b.grad, "head.weight": head.weight.grad, "head.bias": head.bias.grad}
+    for rank, n_static, grads in res:
+        assert n_static == 3                      # one block bucket (w, b) + head.weight + head.bias
+        for k, g in ref.items():
+            assert torch.allclose(grads[k], g, atol=1e-5), (rank, k)
