@@ -467,7 +467,8 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   if ((long long)p.n_tiles >= (1ll << 22)) return 0;
   // shared memory: barriers + alignment slack, activation tile(s), weight rings, hidden tile(s), fp32 bias (+ d-bias sums)
   for (int nhb = 2; nhb >= (backward ? 1 : 2); --nhb) {
-    const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * (backward ? 2 : 1) +
+    // forward: Xh tile + residual/output tile; backward: Xh tile + dU tile
+    const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 +
                       p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
     for (int depth = 4; depth >= 2; --depth) {
       const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
@@ -510,20 +511,24 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   if (!xhat || !x || !w1_pad || !w2 || !b1 || !b2 || !u) return fail(VMLP_EINVAL, "tokmix_fwd null pointer");
   if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_fwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.b2 = (cbf)b2; p.resid = (cbf)x; p.out = (bf)u;
-  CUtensorMap tX, tW1, tW2, tH, tR;
+  if (!aligned16(x) || !aligned16(u)) return fail(VMLP_EALIGN, "tokmix_fwd: x / u must be 16-byte aligned");
+  CUtensorMap tX, tW1, tW2, tH, tR, tU;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
   if ((rc = make_map(&tW1, w1_pad, p.NT, Ds, 1, Np, 0, 64, 32))) return rc;
   if ((rc = make_map(&tW2, w2, Ds, N, 1, Ds, 0, 64, p.NT / 2))) return rc;
   if (hT) { if ((rc = make_map(&tH, hT, Ds, C, B, Ds, (long long)C * Ds, 64, 128))) return rc; }
   else tH = tW2;
-  if ((rc = make_map(&tR, x, C, N, B, C, (long long)N * C, C < 128 ? C : 128, p.NT, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  // residual in / output out: [NT tokens x 128 channels] row-major tiles (256-byte rows, no swizzle); loads zero-fill and
+  // stores clip tokens >= N and channels >= C
+  if ((rc = make_map(&tR, x, C, N, B, C, (long long)N * C, 128, p.NT, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  if ((rc = make_map(&tU, u, C, N, B, C, (long long)N * C, 128, p.NT, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   static std::atomic<int> optin[64];
   if ((rc = smem_optin(tokmix_fwd_sm100, smem, optin))) return rc;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
   tokmix_launch_cfg(cfg, attr, p, smem, st);
-  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_fwd_sm100, tX, tW1, tW2, tH, tR, p, hT ? 1 : 0));
+  CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_fwd_sm100, tX, tW1, tW2, tH, tR, tU, p, hT ? 1 : 0));
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

@@ -204,7 +204,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // those loads into L2 hits.
       if (TMA_AUX && elect_one_sync()) tma_prefetch_l2_3d(&tmPf, tc.n0, tc.m0, tc.b_idx);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait<64>(&empty_bar[stage], phase ^ 1);   // a long wait in steady state: back off, leave the issue slots to the epilogue warps
         if (elect_one_sync()) {
           const uint32_t sa = sbase + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + GEMM_STAGE_A_BYTES;
@@ -255,7 +255,7 @@ gemm_bf16_sm100(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int kb1 = min(kb0 + kb_per_split, p.k_blocks);
         int kin = p.kbatch ? (kb0 % p.kpb) : kb0;
         const int as = tc & 1;
-        mbar_wait(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
+        mbar_wait<32>(&tmem_empty[as], ((tc >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {

@@ -69,23 +69,31 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 // address, parity) in a host-mapped buffer (vmlp_debug_read): a trap discards the device printf buffer, host memory
 // survives the dead context.
 __device__ unsigned int* g_vmlp_dbg = nullptr;      // host-mapped: [0] = record count, then 4 words per record
+__device__ __noinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0 && g_vmlp_dbg != nullptr) {
+    const unsigned int slot = atomicAdd_system(g_vmlp_dbg, 1u);
+    if (slot < 200) {
+      volatile unsigned int* r = g_vmlp_dbg + 4 + 4 * slot;
+      r[0] = blockIdx.x; r[1] = threadIdx.x >> 5; r[2] = smem_u32(bar); r[3] = parity;
+    }
+    __threadfence_system();
+  }
+  const long long t1 = clock64();
+  while (clock64() - t1 < (1ll << 27)) {}      // let the other waiters of the same deadlock record theirs
+  __trap();
+}
+// SLEEP_NS > 0: back off with nanosleep between polls.  The hardware-suspended try_wait comes back on every update of
+// the barrier word (each of 32 arrivals, each TMA transaction), so a service warp that waits most of the time (TMA
+// producer, MMA issuer, store warp) otherwise polls continuously: in the first fused token-mixing kernel those three
+// warps executed 29 % of all instructions of the SM, taking issue slots from the 16 epilogue warps that bound the kernel.
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > (1ll << 31)) {
-      if ((threadIdx.x & 31) == 0 && g_vmlp_dbg != nullptr) {
-        const unsigned int slot = atomicAdd_system(g_vmlp_dbg, 1u);
-        if (slot < 200) {
-          volatile unsigned int* r = g_vmlp_dbg + 4 + 4 * slot;
-          r[0] = blockIdx.x; r[1] = threadIdx.x >> 5; r[2] = smem_u32(bar); r[3] = parity;
-        }
-        __threadfence_system();
-      }
-      const long long t1 = clock64();
-      while (clock64() - t1 < (1ll << 27)) {}      // let the other waiters of the same deadlock record theirs
-      __trap();
-    }
+    if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);
+    if ((++polls & 255u) == 0 && clock64() - t0 > (1ll << 31)) mbar_timeout(bar, parity);
   }
 }
 

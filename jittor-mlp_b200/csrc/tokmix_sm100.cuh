@@ -131,7 +131,7 @@ __device__ __forceinline__ void tm_store_hidden_row(uint32_t tile_addr, int row,
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Forward.  SMEM: [barriers 1 KB][Xh^T tile NT*256][W1 ring][W2 ring][H tiles 2 x 16 KB][b1 fp32][b2 fp32]
+// Forward.  SMEM: [barriers 1 KB][Xh^T tile NT*256][residual/output tile NT*256][W1 ring][W2 ring][H tiles 2 x 16 KB][b1][b2]
 // TMEM: Z double buffer at columns [0, 128), U accumulator at [128, 128 + NT).
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TM_THREADS, 1)
@@ -139,7 +139,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
                  const __grid_constant__ CUtensorMap tmW1,     // W1   [Ds, NT]    box (64 k, 32 rows) SWIZZLE_128B
                  const __grid_constant__ CUtensorMap tmW2,     // W2   [N, Ds]     box (64 k, NT/2 rows)
                  const __grid_constant__ CUtensorMap tmH,      // H^T  [B, C, Ds]  box (64 m, 128 c)  (saved for backward)
-                 const __grid_constant__ CUtensorMap tmR,      // x    [B, N, C]   box (128 c, NT rows), L2 prefetch only
+                 const __grid_constant__ CUtensorMap tmR,      // x    [B, N, C]   box (128 c, NT rows), no swizzle (residual in)
+                 const __grid_constant__ CUtensorMap tmU,      // u    [B, N, C]   box (128 c, NT rows), no swizzle (output)
                  const TokParams p, const int save_hidden) {
   const int cta_rank = static_cast<int>(cluster_ctarank());
   const bool is_leader = cta_rank == 0;
@@ -156,10 +157,12 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   uint64_t* h_done = bars + 12;     uint64_t* hs_empty = bars + 14;
   uint64_t* wa_full = bars + 16;    uint64_t* wa_empty = bars + 24;    // up to 8 stages each
   uint64_t* wb_full = bars + 32;    uint64_t* wb_empty = bars + 40;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 48);
+  uint64_t* ro_full = bars + 48;    uint64_t* ro_done = bars + 49;    uint64_t* ro_free = bars + 50;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_xt = s_base + TM_BAR_BYTES;
-  const uint32_t s_wa = s_xt + p.NT * 256;
+  const uint32_t s_ro = s_xt + p.NT * 256;          // [NT tokens][128 channels] bf16, row-major: residual in, output out
+  const uint32_t s_wa = s_ro + p.NT * 256;
   const uint32_t s_wb = s_wa + p.s_wa * p.wa_stage;
   const uint32_t s_h = s_wb + p.s_wb * p.wb_stage;
   float* sb1 = reinterpret_cast<float*>(smem + (s_h - s_base) + 2 * TM_HTILE);
@@ -167,8 +170,9 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
-    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmR);
+    tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmU);
     mbar_init(xt_full, 1); mbar_init(xt_empty, 1);
+    mbar_init(ro_full, 1); mbar_init(ro_done, TM_EPI_WARPS); mbar_init(ro_free, 1);
     mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2 * TM_EPI_WARPS);
@@ -198,7 +202,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
     auto load_wa = [&](int j) {
       const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-      mbar_wait(&wa_empty[sa], pa ^ 1);
+      mbar_wait<128>(&wa_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&wa_full[sa], 2 * p.wa_stage);
         tm_load_wa(s_wa + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&wa_full[sa])),
@@ -208,7 +212,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
     };
     auto load_wb = [&](int j) {
-      mbar_wait(&wb_empty[sb], pb ^ 1);
+      mbar_wait<128>(&wb_empty[sb], pb ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&wb_full[sb], 2 * p.wb_stage);
         tma_load_3d_u32<2>(s_wb + sb * p.wb_stage, mW2, leader_cta_addr(smem_u32(&wb_full[sb])), j * TM_CH,
@@ -222,12 +226,19 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     int it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
-      mbar_wait(xt_empty, (it & 1) ^ 1);
+      mbar_wait<128>(xt_empty, (it & 1) ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(xt_full, 2 * p.NT * 256);
         tma_load_3d_u32<2>(s_xt, mX, b_xt, t.c0, 0, t.b);
         tma_load_3d_u32<2>(s_xt + p.NT * 128, mX, b_xt, t.c0 + 64, 0, t.b);
-        if (t.valid) tma_prefetch_l2_3d(&tmR, t.c0, 0, t.b);
+      }
+      __syncwarp();
+      // residual tile of this item -> the output staging buffer (own CTA, own barrier); the previous item's output must
+      // have left it (ro_free).  It is needed only at the end of the item, a whole item's worth of time from now.
+      mbar_wait<128>(ro_free, (it & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(ro_full, p.NT * 256);
+        tma_load_3d_u32<1>(s_ro, reinterpret_cast<uint64_t>(&tmR), smem_u32(ro_full), t.c0, 0, t.b);
       }
       __syncwarp();
       for (int j = 0; j < NC; ++j) {
@@ -250,10 +261,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       int t1 = 0, t2 = 0;         // global chunk counters of the next G1 / G2
       auto do_g1 = [&]() {        // ---- G1(t1): Z^T = Xh^T * W1chunk^T
         const int n1 = (j1 == NC - 1) ? p.last_n1 : TM_CH;
-        if (j1 == 0) mbar_wait(xt_full, it1 & 1);
+        if (j1 == 0) mbar_wait<32>(xt_full, it1 & 1);
         const int zb = t1 & 1;
-        mbar_wait(&z_empty[zb], ((t1 >> 1) & 1) ^ 1);
-        mbar_wait(&wa_full[sa], pa);
+        mbar_wait<32>(&z_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        mbar_wait<32>(&wa_full[sa], pa);
         tc_fence_after();
         if (elect_one_sync()) {
           tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_wa + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
@@ -268,9 +279,9 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       };
       auto do_g2 = [&]() {        // ---- G2(t2): U^T (+)= H^T * W2chunk^T
         const int hb = t2 & 1;
-        mbar_wait(&h_full[hb], (t2 >> 1) & 1);
-        mbar_wait(&wb_full[sb], pb);
-        if (j2 == 0) mbar_wait(u_empty, (it2 & 1) ^ 1);
+        mbar_wait<32>(&h_full[hb], (t2 >> 1) & 1);
+        mbar_wait<32>(&wb_full[sb], pb);
+        if (j2 == 0) mbar_wait<32>(u_empty, (it2 & 1) ^ 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const int ksteps = (j2 == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
@@ -302,7 +313,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       const TokTile t = tm_tile(p, pair, cta_rank);
       for (int j = 0; j < NC; ++j, ++g) {
         const int hb = g & 1;
-        mbar_wait(&h_done[hb], (g >> 1) & 1);
+        mbar_wait<128>(&h_done[hb], (g >> 1) & 1);
         if (elect_one_sync()) {
           if (save_hidden && t.valid) {
             tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
@@ -316,6 +327,24 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     }
     if (elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
+  } else if (warp == 3) {
+    // ================================================================ TMA store of the finished output tile
+    int it = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      mbar_wait<128>(ro_done, it & 1);
+      if (elect_one_sync()) {
+        if (t.valid) {
+          tma_store_3d(&tmU, smem + (s_ro - s_base), t.c0, 0, t.b);     // rows >= N and channels >= C are clipped
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        mbar_arrive(ro_free);
+      }
+      __syncwarp();
+    }
+    if (elect_one_sync()) tma_store_wait_all<0>();
+    __syncwarp();
   } else if (warp >= TM_FIRST_EPI_WARP) {
     // ================================================================ epilogue warps
     const int q = warp & 3;                               // TMEM lane quarter
@@ -325,9 +354,6 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     const int ngrp = p.NT >> 4;
     int g = 0, it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
-      const TokTile t = tm_tile(p, pair, cta_rank);
-      const int ch = t.c0 + row;
-      const bool ch_ok = t.valid && ch < p.C;
       for (int j = 0; j < NC; ++j, ++g) {
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
@@ -365,27 +391,20 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           mbar_arrive(&h_done[zb]);
         }
       }
-      // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch]   (this thread = one channel; 16 tokens per step)
-      const __nv_bfloat16* rbase = p.resid + ((long long)t.b * p.N) * p.C + ch;
-      __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
-      uint32_t rcur[16], rnxt[16];
-      auto load_res = [&](int grp, uint32_t (&r)[16]) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = grp * 16 + i;
-          r[i] = (ch_ok && grp < ngrp && n < p.N) ? ldg_u16(rbase + (long long)n * p.C) : 0u;
-        }
-      };
-      load_res(cq, rcur);
+      // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
+      // tokens per tcgen05.ld; the [token][channel] transposition goes through the shared residual/output tile: 2-byte
+      // accesses at [n * 256 + ch * 2] -- the 32 lanes of a warp touch 64 consecutive bytes, conflict-free -- updated in
+      // place, then ONE TMA store per tile (issued by warp 3) writes it out and clips rows >= N / channels >= C.
+      mbar_wait(ro_full, it & 1);
       mbar_wait(u_full, it & 1);
       tc_fence_after();
+      const uint32_t ro_col = s_ro + row * 2;
 #pragma unroll 1
       for (int grp = cq; grp < ngrp + 4; grp += 4) {
         const bool has = grp < ngrp;
         const bool last = grp + 4 >= ngrp;                // this warp's last visit (possibly an empty one)
         uint32_t v[16];
         if (has) {
-          load_res(grp + 4, rnxt);
           tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + grp * 16 + lane_addr, v);
           tmem_ld_wait();
         }
@@ -394,22 +413,28 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           __syncwarp();
           if (lane == 0) tm_arrive_leader(u_empty, is_leader);
         }
-        if (has && ch_ok) {
+        if (has) {
+          const uint32_t a0 = ro_col + grp * 16 * 256;
+          const float4* bp = reinterpret_cast<const float4*>(sb2 + grp * 16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = grp * 16 + i;
-            if (n < p.N) {
-              const float f = __uint_as_float(v[i]) + sb2[n] + __uint_as_float(rcur[i] << 16);
-              stg_u16(obase + (long long)n * p.C, bf16_bits(f));
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 bv = bp[i4];
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * i4 + e;
+              unsigned short r;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a0 + i * 256) : "memory");
+              const float f = __uint_as_float(v[i]) + bb[e] + __uint_as_float(static_cast<uint32_t>(r) << 16);
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(a0 + i * 256), "h"(static_cast<unsigned short>(bf16_bits(f))) : "memory");
             }
           }
         }
-        if (has) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) rcur[i] = rnxt[i];
-        }
         if (last) break;
       }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ro_done);
     }
   }
 
@@ -502,13 +527,13 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     auto load_w12 = [&](int j) {
       const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
       const int row = j * TM_CH + cta_rank * (n1 >> 1);
-      mbar_wait(&w1_empty[sa], pa ^ 1);
+      mbar_wait<128>(&w1_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
         tm_load_wa(s_w1 + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
       }
       __syncwarp();
-      mbar_wait(&w2_empty[sa], pa ^ 1);
+      mbar_wait<128>(&w2_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
         tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
@@ -517,7 +542,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
     };
     auto load_w3 = [&](int j) {
-      mbar_wait(&w3_empty[sb], pb ^ 1);
+      mbar_wait<128>(&w3_empty[sb], pb ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(&w3_full[sb], 2 * p.wb_stage);
         tma_load_3d_u32<2>(s_w3 + sb * p.wb_stage, mW1T, leader_cta_addr(smem_u32(&w3_full[sb])), j * TM_CH,
@@ -529,7 +554,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     int it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
-      mbar_wait(in_empty, (it & 1) ^ 1);
+      mbar_wait<128>(in_empty, (it & 1) ^ 1);
       if (elect_one_sync()) {
         if (is_leader) mbar_arrive_expect_tx(in_full, 4 * p.NT * 256);
         tma_load_3d_u32<2>(s_xt, mX, b_in, t.c0, 0, t.b);
@@ -557,17 +582,17 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       int t1 = 0, t3 = 0;
       auto do_g12 = [&]() {       // ---- Z^T = Xh^T * W1chunk^T and dH^T = dU^T * W2[:, chunk]
         const int n1 = (j1 == NC - 1) ? p.last_n1 : TM_CH;
-        if (j1 == 0) mbar_wait(in_full, it1 & 1);
+        if (j1 == 0) mbar_wait<32>(in_full, it1 & 1);
         const int zb = t1 & 1;
-        mbar_wait(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
-        mbar_wait(&w1_full[sa], pa);
+        mbar_wait<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        mbar_wait<32>(&w1_full[sa], pa);
         tc_fence_after();
         if (elect_one_sync()) {
           tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_w1 + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
           umma_commit_2cta_mc(&w1_empty[sa]);
         }
         __syncwarp();
-        mbar_wait(&w2_full[sa], pa);
+        mbar_wait<32>(&w2_full[sa], pa);
         tc_fence_after();
         if (elect_one_sync()) {
           tm_mma_over_tokens(tmem_base + 2 * TM_CH + zb * TM_CH, s_dut, s_w2 + sa * p.wa_stage,
@@ -583,9 +608,9 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       };
       auto do_g3 = [&]() {        // ---- dXh^T (+)= dZ^T * W1[chunk, :]
         const int hb = p.nhb == 2 ? (t3 & 1) : 0;
-        mbar_wait(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1);
-        mbar_wait(&w3_full[sb], pb);
-        if (j3 == 0) mbar_wait(dx_empty, (it3 & 1) ^ 1);
+        mbar_wait<32>(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1);
+        mbar_wait<32>(&w3_full[sb], pb);
+        if (j3 == 0) mbar_wait<32>(dx_empty, (it3 & 1) ^ 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const int ksteps = (j3 == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
@@ -619,7 +644,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       for (int j = 0; j < NC; ++j, ++g) {
         const int hb = p.nhb == 2 ? (g & 1) : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        mbar_wait(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
         if (warp == 2 && elect_one_sync()) {
           if (t.valid) {
             tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
@@ -721,10 +746,14 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
           if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
         }
         if (has && ch_ok) {
+          __nv_bfloat16* po = obase + (long long)(grp * 16) * p.C;
+          if (grp * 16 + 16 <= p.N) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = grp * 16 + i;
-            if (n < p.N) stg_u16(obase + (long long)n * p.C, bf16_bits(__uint_as_float(v[i])));
+            for (int i = 0; i < 16; ++i, po += p.C) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i, po += p.C)
+              if (grp * 16 + i < p.N) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
           }
         }
         if (last) break;

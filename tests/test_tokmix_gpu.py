@@ -23,7 +23,7 @@ SHAPES = [  # B, N, C, Ds
     (5, 80, 256, 136),       # NT 80: one full atom + SWIZZLE_32B tail
     (2, 100, 128, 320),      # NT 112: tail 48 (full-width tail atom, 3 k-steps)
     (2, 20, 128, 128),       # NT 32: tail only
-    (1, 256, 384, 1024),     # largest supported token count / hidden width (forward only)
+    (1, 240, 384, 1024),     # largest supported token count / hidden width (forward only)
 ]
 
 
@@ -111,7 +111,7 @@ def test_bench_shape_b256_slice():
 def test_unsupported_shapes_are_reported():
     assert not ops.tokmix_supported(2, 257, 128, 256)         # token axis beyond one accumulator
     assert not ops.tokmix_supported(2, 196, 132, 256)         # channel pitch not 16-byte aligned
-    assert not ops.tokmix_supported(2, 256, 128, 256, backward=True)   # two resident activation tiles do not fit
+    assert not ops.tokmix_supported(2, 240, 128, 256, backward=True)   # two resident activation tiles + weight rings do not fit
     x = rnd(2, 257, 128)
     with pytest.raises(ValueError):
         ops.tokmix_fwd(x, x, rnd(256, 257), rnd(256), rnd(257, 256), rnd(257))
