@@ -511,6 +511,7 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   if (!xhat || !x || !w1_pad || !w2 || !b1 || !b2 || !u) return fail(VMLP_EINVAL, "tokmix_fwd null pointer");
   if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_fwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.b2 = (cbf)b2; p.resid = (cbf)x; p.out = (bf)u;
+  if (const char* e = getenv("VMLP_TM_FLAGS")) p.flags = atoi(e);     // profiling experiments only
   if (!aligned16(x) || !aligned16(u)) return fail(VMLP_EALIGN, "tokmix_fwd: x / u must be 16-byte aligned");
   CUtensorMap tX, tW1, tW2, tH, tR, tU;
   int rc;
@@ -544,6 +545,7 @@ int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const 
   if (!xhat || !du || !w1_pad || !w2T_pad || !w1T || !b1 || !dxhat || !dzT) return fail(VMLP_EINVAL, "tokmix_bwd null pointer");
   if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_bwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.out = (bf)dxhat; p.db1 = db1;
+  if (const char* e = getenv("VMLP_TM_FLAGS")) p.flags = atoi(e);     // profiling experiments only
   CUtensorMap tX, tDU, tW1, tW2T, tW1T, tDZ;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;

@@ -54,6 +54,8 @@ struct TokParams {
   const __nv_bfloat16* resid;// [B, N, C]   (forward: x)
   __nv_bfloat16* out;        // [B, N, C]   forward: u; backward: dXh
   float* db1;                // [Ds] fp32   backward: += sum over (b, c) of dZ (the hidden-bias gradient)
+  int flags;                 // profiling experiments only (VMLP_TM_FLAGS): 1 no GELU math, 2 no hidden-tile TMA store,
+                             // 4 no column sums, 8 no hidden-tile SMEM write, 16 no TMEM load  -- results are then WRONG
 };
 
 // shared-memory descriptor high word (SBO = 1024 B between 8-row groups, version 1, SWIZZLE_128B); K-major swizzled
@@ -157,7 +159,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   uint64_t* h_done = bars + 12;     uint64_t* hs_empty = bars + 14;
   uint64_t* wa_full = bars + 16;    uint64_t* wa_empty = bars + 24;    // up to 8 stages each
   uint64_t* wb_full = bars + 32;    uint64_t* wb_empty = bars + 40;
-  uint64_t* ro_full = bars + 48;    uint64_t* ro_done = bars + 49;    uint64_t* ro_free = bars + 50;
+  uint64_t* ro_full = bars + 48;    uint64_t* ro_done = bars + 49;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 56);
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_xt = s_base + TM_BAR_BYTES;
@@ -172,7 +174,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmU);
     mbar_init(xt_full, 1); mbar_init(xt_empty, 1);
-    mbar_init(ro_full, 1); mbar_init(ro_done, TM_EPI_WARPS); mbar_init(ro_free, 1);
+    mbar_init(ro_full, 1); mbar_init(ro_done, TM_EPI_WARPS);
     mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2 * TM_EPI_WARPS);
@@ -231,14 +233,6 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         if (is_leader) mbar_arrive_expect_tx(xt_full, 2 * p.NT * 256);
         tma_load_3d_u32<2>(s_xt, mX, b_xt, t.c0, 0, t.b);
         tma_load_3d_u32<2>(s_xt + p.NT * 128, mX, b_xt, t.c0 + 64, 0, t.b);
-      }
-      __syncwarp();
-      // residual tile of this item -> the output staging buffer (own CTA, own barrier); the previous item's output must
-      // have left it (ro_free).  It is needed only at the end of the item, a whole item's worth of time from now.
-      mbar_wait<128>(ro_free, (it & 1) ^ 1);
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(ro_full, p.NT * 256);
-        tma_load_3d_u32<1>(s_ro, reinterpret_cast<uint64_t>(&tmR), smem_u32(ro_full), t.c0, 0, t.b);
       }
       __syncwarp();
       for (int j = 0; j < NC; ++j) {
@@ -315,7 +309,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         const int hb = g & 1;
         mbar_wait<128>(&h_done[hb], (g >> 1) & 1);
         if (elect_one_sync()) {
-          if (save_hidden && t.valid) {
+          if (save_hidden && t.valid && !(p.flags & 2)) {
             tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
             tma_store_commit();
             tma_store_wait_read<0>();
@@ -328,7 +322,17 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     if (elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
   } else if (warp == 3) {
-    // ================================================================ TMA store of the finished output tile
+    // ================================================================ residual-in / output-out tile (each CTA its own):
+    // TMA load of the item's residual x tile into the staging buffer, and -- once the 16 epilogue warps have turned it into
+    // the output in place (ro_done) -- TMA store of the tile, then the load of the NEXT item's residual.  A separate warp,
+    // so that neither the weight producer nor the hidden-tile store warp ever waits for the end of an item.
+    auto load_residual = [&](int pair) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      mbar_arrive_expect_tx(ro_full, p.NT * 256);
+      tma_load_3d_u32<1>(s_ro, reinterpret_cast<uint64_t>(&tmR), smem_u32(ro_full), t.c0, 0, t.b);
+    };
+    if (cluster_id < p.n_pairs && elect_one_sync()) load_residual(cluster_id);
+    __syncwarp();
     int it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
@@ -339,7 +343,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           tma_store_commit();
           tma_store_wait_read<0>();
         }
-        mbar_arrive(ro_free);
+        if (pair + num_clusters < p.n_pairs) load_residual(pair + num_clusters);
       }
       __syncwarp();
     }
@@ -361,7 +365,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         mbar_wait(&z_full[zb], (g >> 1) & 1);
         tc_fence_after();
         uint32_t v[16];
-        if (live) {
+        if (live && !(p.flags & 16)) {
           tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, v);
           tmem_ld_wait();
         }
@@ -369,7 +373,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&z_empty[zb], is_leader);
         uint32_t o[8];
-        if (live) {
+        if (live && (p.flags & 1)) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+        } else if (live) {
           const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
@@ -383,7 +390,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         }
         mbar_wait(&h_empty[zb], ((g >> 1) & 1) ^ 1);     // G2(g - 2) has consumed this hidden buffer
         mbar_wait(&hs_empty[zb], ((g >> 1) & 1) ^ 1);    // ... and its TMA store has read it
-        if (live) tm_store_hidden_row(s_h + zb * TM_HTILE, row, cq, o);
+        if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + zb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -646,14 +653,14 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
         if (warp == 2 && elect_one_sync()) {
-          if (t.valid) {
+          if (t.valid && !(p.flags & 2)) {
             tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
             tma_store_commit();
           }
         }
         __syncwarp();
         float s0 = 0.f, s1 = 0.f;
-        if (t.valid && 2 * lane < n1) {
+        if (t.valid && 2 * lane < n1 && !(p.flags & 4)) {
           const uint32_t tb = s_dz + hb * TM_HTILE;
 #pragma unroll 8
           for (int r = r0; r < r0 + 64; ++r) {
@@ -694,7 +701,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         mbar_wait(&zd_full[zb], (g >> 1) & 1);
         tc_fence_after();
         uint32_t vz[16], vh[16];
-        if (live) {
+        if (live && !(p.flags & 16)) {
           tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vz);
           tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
           tmem_ld_wait();
@@ -703,7 +710,10 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
         uint32_t o[8];
-        if (live) {
+        if (live && (p.flags & 1)) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(vz[2 * e]) + __uint_as_float(vh[2 * e]), __uint_as_float(vz[2 * e + 1]) + __uint_as_float(vh[2 * e + 1]));
+        } else if (live) {
           const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
@@ -719,7 +729,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
         mbar_wait(&dz_empty[hb], hph);                             // G3 of the previous user of this buffer has read it
         mbar_wait(&dzs_empty[hb], hph);                            // ... and so have its TMA store and column sums
-        if (live) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
+        if (live && !(p.flags & 8)) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
