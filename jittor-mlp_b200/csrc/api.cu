@@ -465,12 +465,17 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   p.wb_stage = p.NT * 64;
   p.inv_tiles_c = 1.0f / (float)p.tiles_c;
   if ((long long)p.n_tiles >= (1ll << 22)) return 0;
-  // shared memory: barriers + alignment slack, activation tile(s), weight rings, hidden tile(s), fp32 bias (+ d-bias sums)
-  for (int nhb = 2; nhb >= (backward ? 1 : 2); --nhb) {
-    // forward: Xh tile + residual/output tile; backward: Xh tile + dU tile
-    const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 +
-                      p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
-    for (int depth = 4; depth >= 2; --depth) {
+  // shared memory: barriers + alignment slack, two activation-sized tiles (forward: Xh + residual/output; backward: Xh + dU),
+  // weight rings, hidden tile(s), fp32 bias (+ d-bias sums).  The weight stream is latency-bound (one 30 / 46 KB stage per
+  // hidden chunk out of L2): ring depth comes first, a second hidden-tile buffer only if it still fits.
+  const int force_depth = [] { const char* e = getenv("VMLP_TM_DEPTH"); return e ? atoi(e) : 0; }();
+  const int force_nhb = [] { const char* e = getenv("VMLP_TM_NHB"); return e ? atoi(e) : 0; }();
+  for (int depth = 4; depth >= 2; --depth) {
+    if (force_depth && depth != force_depth) continue;
+    for (int nhb = 2; nhb >= 1; --nhb) {
+      if (force_nhb && nhb != force_nhb) continue;
+      const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 +
+                        p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
       const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
       if (fixed + rings <= TM_SMEM_MAX) {
         p.s_wa = p.s_wb = depth;

@@ -55,7 +55,8 @@ struct TokParams {
   __nv_bfloat16* out;        // [B, N, C]   forward: u; backward: dXh
   float* db1;                // [Ds] fp32   backward: += sum over (b, c) of dZ (the hidden-bias gradient)
   int flags;                 // profiling experiments only (VMLP_TM_FLAGS): 1 no GELU math, 2 no hidden-tile TMA store,
-                             // 4 no column sums, 8 no hidden-tile SMEM write, 16 no TMEM load  -- results are then WRONG
+                             // 4 no column sums, 8 no hidden-tile SMEM write, 16 no TMEM load, 32 no weight TMA loads
+                             // -- results are then WRONG; 64 chunk rotation off (results unchanged)
 };
 
 // shared-memory descriptor high word (SBO = 1024 B between 8-row groups, version 1, SWIZZLE_128B); K-major swizzled
@@ -105,6 +106,14 @@ __device__ __forceinline__ void tm_mma_over_hidden(uint32_t d_tmem, uint32_t h_a
   const uint32_t a_base = (h_addr >> 4) | TM_LBO_K, b_base = (w_addr >> 4) | TM_LBO_K;
   for (int ks = 0; ks < ksteps; ++ks)
     umma_bf16_lo<2>(d_tmem, a_base + ks * 2, b_base + ks * 2, TM_DESC_HI_SW128, idesc, (first && ks == 0) ? 0u : 1u);
+}
+
+// Hidden chunks are visited in a per-cluster ROTATED order (chunk index = position + cluster_id, mod n_chunks): the sum
+// over chunks is order-free, and 74 CTA pairs no longer stream the same 30 KB of W1 / W2 out of the same L2 lines at the
+// same moment.  VMLP_TM_FLAGS bit 64 switches the rotation off (A/B measurements).
+__device__ __forceinline__ int tm_chunk(int pos, int rot, int nc) {
+  const int j = pos + rot;
+  return j < nc ? j : j - nc;
 }
 
 struct TokTile {
@@ -167,7 +176,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   const uint32_t s_wa = s_ro + p.NT * 256;
   const uint32_t s_wb = s_wa + p.s_wa * p.wa_stage;
   const uint32_t s_h = s_wb + p.s_wb * p.wb_stage;
-  float* sb1 = reinterpret_cast<float*>(smem + (s_h - s_base) + 2 * TM_HTILE);
+  float* sb1 = reinterpret_cast<float*>(smem + (s_h - s_base) + p.nhb * TM_HTILE);
   float* sb2 = sb1 + p.n_chunks * TM_CH;
 
   if (warp == 0 && lane == 0) {
@@ -195,6 +204,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int NC = p.n_chunks;
+  const int rot = (p.flags & 64) ? 0 : cluster_id % NC;
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs; bytes signalled on the leader)
@@ -202,23 +212,31 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
                    mW2 = reinterpret_cast<uint64_t>(&tmW2);
     const uint32_t b_xt = leader_cta_addr(smem_u32(xt_full));
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-    auto load_wa = [&](int j) {
+    auto load_wa = [&](int pos) {
+      const int j = tm_chunk(pos, rot, NC);
       const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
       mbar_wait<128>(&wa_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
-        if (is_leader) mbar_arrive_expect_tx(&wa_full[sa], 2 * p.wa_stage);
-        tm_load_wa(s_wa + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&wa_full[sa])),
-                   j * TM_CH + cta_rank * (n1 >> 1), p);
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&wa_full[sa]); }
+        else {
+          if (is_leader) mbar_arrive_expect_tx(&wa_full[sa], 2 * p.wa_stage);
+          tm_load_wa(s_wa + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&wa_full[sa])),
+                     j * TM_CH + cta_rank * (n1 >> 1), p);
+        }
       }
       __syncwarp();
       if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
     };
-    auto load_wb = [&](int j) {
+    auto load_wb = [&](int pos) {
+      const int j = tm_chunk(pos, rot, NC);
       mbar_wait<128>(&wb_empty[sb], pb ^ 1);
       if (elect_one_sync()) {
-        if (is_leader) mbar_arrive_expect_tx(&wb_full[sb], 2 * p.wb_stage);
-        tma_load_3d_u32<2>(s_wb + sb * p.wb_stage, mW2, leader_cta_addr(smem_u32(&wb_full[sb])), j * TM_CH,
-                           cta_rank * (p.NT >> 1), 0);
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&wb_full[sb]); }
+        else {
+          if (is_leader) mbar_arrive_expect_tx(&wb_full[sb], 2 * p.wb_stage);
+          tma_load_3d_u32<2>(s_wb + sb * p.wb_stage, mW2, leader_cta_addr(smem_u32(&wb_full[sb])), j * TM_CH,
+                             cta_rank * (p.NT >> 1), 0);
+        }
       }
       __syncwarp();
       if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
@@ -254,7 +272,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       int j2 = 0, it2 = 0;        // chunk / item of the next G2
       int t1 = 0, t2 = 0;         // global chunk counters of the next G1 / G2
       auto do_g1 = [&]() {        // ---- G1(t1): Z^T = Xh^T * W1chunk^T
-        const int n1 = (j1 == NC - 1) ? p.last_n1 : TM_CH;
+        const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
         if (j1 == 0) mbar_wait<32>(xt_full, it1 & 1);
         const int zb = t1 & 1;
         mbar_wait<32>(&z_empty[zb], ((t1 >> 1) & 1) ^ 1);
@@ -272,13 +290,13 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         ++t1;
       };
       auto do_g2 = [&]() {        // ---- G2(t2): U^T (+)= H^T * W2chunk^T
-        const int hb = t2 & 1;
-        mbar_wait<32>(&h_full[hb], (t2 >> 1) & 1);
+        const int hb = p.nhb == 2 ? (t2 & 1) : 0;
+        mbar_wait<32>(&h_full[hb], (p.nhb == 2 ? (t2 >> 1) : t2) & 1);
         mbar_wait<32>(&wb_full[sb], pb);
         if (j2 == 0) mbar_wait<32>(u_empty, (it2 & 1) ^ 1);
         tc_fence_after();
         if (elect_one_sync()) {
-          const int ksteps = (j2 == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
+          const int ksteps = (tm_chunk(j2, rot, NC) == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
           tm_mma_over_hidden(tmem_base + 2 * TM_CH, s_h + hb * TM_HTILE, s_wb + sb * p.wb_stage, idesc_g2, ksteps, j2 == 0);
           umma_commit_2cta_mc(&wb_empty[sb]);
           umma_commit_2cta_mc(&h_empty[hb]);
@@ -306,11 +324,11 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
       const TokTile t = tm_tile(p, pair, cta_rank);
       for (int j = 0; j < NC; ++j, ++g) {
-        const int hb = g & 1;
-        mbar_wait<128>(&h_done[hb], (g >> 1) & 1);
+        const int hb = p.nhb == 2 ? (g & 1) : 0;
+        mbar_wait<128>(&h_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
         if (elect_one_sync()) {
           if (save_hidden && t.valid && !(p.flags & 2)) {
-            tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
+            tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
             tma_store_commit();
             tma_store_wait_read<0>();
           }
@@ -358,7 +376,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     const int ngrp = p.NT >> 4;
     int g = 0, it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
-      for (int j = 0; j < NC; ++j, ++g) {
+      for (int pos = 0; pos < NC; ++pos, ++g) {
+        const int j = tm_chunk(pos, rot, NC);
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live = cq * 16 < n1;
@@ -388,14 +407,16 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
             o[2 * e4 + 1] = pack_bf16x2_f2(gl);
           }
         }
-        mbar_wait(&h_empty[zb], ((g >> 1) & 1) ^ 1);     // G2(g - 2) has consumed this hidden buffer
-        mbar_wait(&hs_empty[zb], ((g >> 1) & 1) ^ 1);    // ... and its TMA store has read it
-        if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + zb * TM_HTILE, row, cq, o);
+        const int hb = p.nhb == 2 ? zb : 0;                          // hidden tile buffer (one when two do not fit)
+        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        mbar_wait(&h_empty[hb], hph);                                // G2 of the previous user of this buffer has read it
+        mbar_wait(&hs_empty[hb], hph);                               // ... and so has its TMA store
+        if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tm_arrive_leader(&h_full[zb], is_leader);
-          mbar_arrive(&h_done[zb]);
+          tm_arrive_leader(&h_full[hb], is_leader);
+          mbar_arrive(&h_done[hb]);
         }
       }
       // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
@@ -523,6 +544,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int NC = p.n_chunks;
+  const int rot = (p.flags & 64) ? 0 : cluster_id % NC;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -531,29 +553,40 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
                    mW1T = reinterpret_cast<uint64_t>(&tmW1T);
     const uint32_t b_in = leader_cta_addr(smem_u32(in_full));
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-    auto load_w12 = [&](int j) {
+    auto load_w12 = [&](int pos) {
+      const int j = tm_chunk(pos, rot, NC);
       const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
       const int row = j * TM_CH + cta_rank * (n1 >> 1);
       mbar_wait<128>(&w1_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
-        if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
-        tm_load_wa(s_w1 + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&w1_full[sa]); }
+        else {
+          if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
+          tm_load_wa(s_w1 + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
+        }
       }
       __syncwarp();
       mbar_wait<128>(&w2_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
-        if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
-        tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&w2_full[sa]); }
+        else {
+          if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
+          tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
+        }
       }
       __syncwarp();
       if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
     };
-    auto load_w3 = [&](int j) {
+    auto load_w3 = [&](int pos) {
+      const int j = tm_chunk(pos, rot, NC);
       mbar_wait<128>(&w3_empty[sb], pb ^ 1);
       if (elect_one_sync()) {
-        if (is_leader) mbar_arrive_expect_tx(&w3_full[sb], 2 * p.wb_stage);
-        tma_load_3d_u32<2>(s_w3 + sb * p.wb_stage, mW1T, leader_cta_addr(smem_u32(&w3_full[sb])), j * TM_CH,
-                           cta_rank * (p.NT >> 1), 0);
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&w3_full[sb]); }
+        else {
+          if (is_leader) mbar_arrive_expect_tx(&w3_full[sb], 2 * p.wb_stage);
+          tma_load_3d_u32<2>(s_w3 + sb * p.wb_stage, mW1T, leader_cta_addr(smem_u32(&w3_full[sb])), j * TM_CH,
+                             cta_rank * (p.NT >> 1), 0);
+        }
       }
       __syncwarp();
       if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
@@ -588,7 +621,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       int j1 = 0, it1 = 0, j3 = 0, it3 = 0;
       int t1 = 0, t3 = 0;
       auto do_g12 = [&]() {       // ---- Z^T = Xh^T * W1chunk^T and dH^T = dU^T * W2[:, chunk]
-        const int n1 = (j1 == NC - 1) ? p.last_n1 : TM_CH;
+        const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
         if (j1 == 0) mbar_wait<32>(in_full, it1 & 1);
         const int zb = t1 & 1;
         mbar_wait<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
@@ -620,7 +653,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         if (j3 == 0) mbar_wait<32>(dx_empty, (it3 & 1) ^ 1);
         tc_fence_after();
         if (elect_one_sync()) {
-          const int ksteps = (j3 == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
+          const int ksteps = (tm_chunk(j3, rot, NC) == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
           tm_mma_over_hidden(tmem_base + 4 * TM_CH, s_dz + hb * TM_HTILE, s_w3 + sb * p.wb_stage, idesc_g3, ksteps, j3 == 0);
           umma_commit_2cta_mc(&w3_empty[sb]);
           umma_commit_2cta_mc(&dz_empty[hb]);
@@ -648,7 +681,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     int g = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
       const TokTile t = tm_tile(p, pair, cta_rank);
-      for (int j = 0; j < NC; ++j, ++g) {
+      for (int pos = 0; pos < NC; ++pos, ++g) {
+        const int j = tm_chunk(pos, rot, NC);
         const int hb = p.nhb == 2 ? (g & 1) : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
@@ -694,7 +728,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       const TokTile t = tm_tile(p, pair, cta_rank);
       const int ch = t.c0 + row;
       const bool ch_ok = t.valid && ch < p.C;
-      for (int j = 0; j < NC; ++j, ++g) {
+      for (int pos = 0; pos < NC; ++pos, ++g) {
+        const int j = tm_chunk(pos, rot, NC);
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live = cq * 16 < n1;
