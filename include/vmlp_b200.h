@@ -245,6 +245,8 @@ int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H,
  * and the tiles of that shape fit in shared memory; otherwise the caller composes vmlp_gemm_bf16 calls.
  * ------------------------------------------------------------------------------------------ */
 int vmlp_tokmix_supported(int32_t B, int32_t N, int32_t C, int32_t Ds, int32_t backward);
+/* bring-up: int64 device buffer [4][64][8] that the forward kernel's CTA 0 fills with clock64 stamps (NULL = off) */
+int vmlp_tokmix_set_trace(void* buf);
 int vmlp_tokmix_prepare(const void* w, int32_t rows, int32_t cols, void* pad, int32_t ld, void* tr, int32_t ldt,
                         vmlp_stream_t stream);
 int vmlp_tokmix_fwd(const void* xhat, const void* x, const void* w1_pad, int32_t Np, const void* w2, const void* b1,

@@ -165,6 +165,7 @@ SYMBOLS = [
     ("vmlp_dwconv_dgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_dwconv_wgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_patchify", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_tokmix_set_trace", c_int32, [c_void_p]),
     ("vmlp_tokmix_supported", c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     ("vmlp_tokmix_prepare", c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
     ("vmlp_tokmix_fwd", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -448,6 +448,7 @@ int layernorm_bwd_impl(const void* dy, int64_t dy_ld, const void* x, int64_t x_l
 
 // ------------------------------------------------------------------------------------------- fused token-mixing MLP
 constexpr int TM_SMEM_MAX = 227 * 1024;
+long long* g_tokmix_trace = nullptr;     // bring-up only: device buffer for the clock64 timeline of CTA 0 (vmlp_tokmix_set_trace)
 
 // Fills the shape-derived fields; returns the dynamic shared memory the kernel needs (0 = shape not supported).
 int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
@@ -1179,6 +1180,7 @@ int vmlp_patchify(const void* src, void* dst, int32_t B, int32_t Cin, int32_t H,
 }
 
 // ============================================================================================ fused token-mixing MLP
+int vmlp_tokmix_set_trace(void* buf) { g_tokmix_trace = static_cast<long long*>(buf); return VMLP_OK; }
 int vmlp_tokmix_supported(int32_t B, int32_t N, int32_t C, int32_t Ds, int32_t backward) {
   TokParams p;
   return tokmix_plan(p, B, N, C, Ds, backward != 0) ? 1 : 0;

@@ -54,6 +54,7 @@ struct TokParams {
   const __nv_bfloat16* resid;// [B, N, C]   (forward: x)
   __nv_bfloat16* out;        // [B, N, C]   forward: u; backward: dXh
   float* db1;                // [Ds] fp32   backward: += sum over (b, c) of dZ (the hidden-bias gradient)
+  long long* trace;          // optional timeline of CTA 0 (clock64 stamps, bring-up only): [role 0..3][chunk < 64][8 events]
   int flags;                 // profiling experiments only (VMLP_TM_FLAGS): 1 no GELU math, 2 no hidden-tile TMA store,
                              // 4 no column sums, 8 no hidden-tile SMEM write, 16 no TMEM load, 32 no weight TMA loads
                              // -- results are then WRONG; 64 chunk rotation off (results unchanged)
@@ -120,6 +121,10 @@ struct TokTile {
   int b, c0;
   bool valid;
 };
+// bring-up timeline: one elected/first lane of a role in CTA 0 stamps clock64() at event `ev` of global chunk `g`
+__device__ __forceinline__ void tm_stamp(const TokParams& p, int role, int g, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && g < 64) p.trace[(role * 64 + g) * 8 + ev] = clock64();
+}
 __device__ __forceinline__ TokTile tm_tile(const TokParams& p, int pair, int cta_rank) {
   TokTile t;
   const int tile = 2 * pair + cta_rank;
@@ -273,10 +278,14 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       int t1 = 0, t2 = 0;         // global chunk counters of the next G1 / G2
       auto do_g1 = [&]() {        // ---- G1(t1): Z^T = Xh^T * W1chunk^T
         const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
+        if (lane == 0) tm_stamp(p, 0, t1, 0);
         if (j1 == 0) mbar_wait<32>(xt_full, it1 & 1);
         const int zb = t1 & 1;
+        if (lane == 0) tm_stamp(p, 0, t1, 1);
         mbar_wait<32>(&z_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        if (lane == 0) tm_stamp(p, 0, t1, 2);
         mbar_wait<32>(&wa_full[sa], pa);
+        if (lane == 0) tm_stamp(p, 0, t1, 3);
         tc_fence_after();
         if (elect_one_sync()) {
           tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_wa + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
@@ -285,6 +294,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           if (j1 == NC - 1) umma_commit_2cta_mc(xt_empty);
         }
         __syncwarp();
+        if (lane == 0) tm_stamp(p, 0, t1, 4);
         if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
         if (++j1 == NC) { j1 = 0; ++it1; }
         ++t1;
@@ -292,8 +302,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       auto do_g2 = [&]() {        // ---- G2(t2): U^T (+)= H^T * W2chunk^T
         const int hb = p.nhb == 2 ? (t2 & 1) : 0;
         mbar_wait<32>(&h_full[hb], (p.nhb == 2 ? (t2 >> 1) : t2) & 1);
+        if (lane == 0) tm_stamp(p, 0, t2, 5);
         mbar_wait<32>(&wb_full[sb], pb);
         if (j2 == 0) mbar_wait<32>(u_empty, (it2 & 1) ^ 1);
+        if (lane == 0) tm_stamp(p, 0, t2, 6);
         tc_fence_after();
         if (elect_one_sync()) {
           const int ksteps = (tm_chunk(j2, rot, NC) == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
@@ -305,6 +317,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         __syncwarp();
         if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
         if (++j2 == NC) { j2 = 0; ++it2; }
+        if (lane == 0) tm_stamp(p, 0, t2, 7);
         ++t2;
       };
       // G1 runs two chunks ahead of G2.  Inside an item G1(t) is issued before G2(t - 2) (it only needs the Z buffer that
@@ -381,7 +394,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live = cq * 16 < n1;
+        const bool tr = warp == TM_FIRST_EPI_WARP && lane == 0;
+        if (tr) tm_stamp(p, 1, g, 0);
         mbar_wait(&z_full[zb], (g >> 1) & 1);
+        if (tr) tm_stamp(p, 1, g, 1);
         tc_fence_after();
         uint32_t v[16];
         if (live && !(p.flags & 16)) {
@@ -391,6 +407,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&z_empty[zb], is_leader);
+        if (tr) tm_stamp(p, 1, g, 2);
         uint32_t o[8];
         if (live && (p.flags & 1)) {
 #pragma unroll
@@ -409,15 +426,20 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         }
         const int hb = p.nhb == 2 ? zb : 0;                          // hidden tile buffer (one when two do not fit)
         const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        if (tr) tm_stamp(p, 1, g, 3);
         mbar_wait(&h_empty[hb], hph);                                // G2 of the previous user of this buffer has read it
+        if (tr) tm_stamp(p, 1, g, 4);
         mbar_wait(&hs_empty[hb], hph);                               // ... and so has its TMA store
+        if (tr) tm_stamp(p, 1, g, 5);
         if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
+        if (tr) tm_stamp(p, 1, g, 6);
         if (lane == 0) {
           tm_arrive_leader(&h_full[hb], is_leader);
           mbar_arrive(&h_done[hb]);
         }
+        if (tr) tm_stamp(p, 1, g, 7);
       }
       // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
       // tokens per tcgen05.ld; the [token][channel] transposition goes through the shared residual/output tile: 2-byte
