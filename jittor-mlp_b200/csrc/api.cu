@@ -519,6 +519,7 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   p.b1 = (cbf)b1; p.b2 = (cbf)b2; p.resid = (cbf)x; p.out = (bf)u;
   if (const char* e = getenv("VMLP_TM_FLAGS")) p.flags = atoi(e);     // profiling experiments only
   if (!aligned16(x) || !aligned16(u)) return fail(VMLP_EALIGN, "tokmix_fwd: x / u must be 16-byte aligned");
+  p.trace = g_tokmix_trace;
   CUtensorMap tX, tW1, tW2, tH, tR, tU;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;
