@@ -467,14 +467,14 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   p.inv_tiles_c = 1.0f / (float)p.tiles_c;
   if ((long long)p.n_tiles >= (1ll << 22)) return 0;
   // shared memory: barriers + alignment slack, two activation-sized tiles (forward: Xh + residual/output; backward: Xh + dU),
-  // weight rings, hidden tile(s), fp32 bias (+ d-bias sums).  The weight stream is latency-bound (one 30 / 46 KB stage per
-  // hidden chunk out of L2): ring depth comes first, a second hidden-tile buffer only if it still fits.
+  // weight rings, hidden tile(s), fp32 bias (+ d-bias sums).  Measured: without any weight traffic the kernels are as fast
+  // as with it (the L2 -> SMEM stream is not the limiter), so a second hidden-tile buffer comes before ring depth.
   const int force_depth = [] { const char* e = getenv("VMLP_TM_DEPTH"); return e ? atoi(e) : 0; }();
   const int force_nhb = [] { const char* e = getenv("VMLP_TM_NHB"); return e ? atoi(e) : 0; }();
-  for (int depth = 4; depth >= 2; --depth) {
-    if (force_depth && depth != force_depth) continue;
-    for (int nhb = 2; nhb >= 1; --nhb) {
-      if (force_nhb && nhb != force_nhb) continue;
+  for (int nhb = 2; nhb >= 1; --nhb) {
+    if (force_nhb && nhb != force_nhb) continue;
+    for (int depth = 4; depth >= 2; --depth) {
+      if (force_depth && depth != force_depth) continue;
       const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 +
                         p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
       const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
@@ -490,12 +490,12 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   return 0;
 }
 
-int tokmix_launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const TokParams& p, int smem, cudaStream_t st) {
+int tokmix_launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, const TokParams& p, int smem, int threads, cudaStream_t st) {
   const DeviceInfo& dv = device_info();
   memset(&cfg, 0, sizeof(cfg));
   const int clusters = p.n_pairs < dv.sms / 2 ? p.n_pairs : dv.sms / 2;
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(TM_THREADS);
+  cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -535,7 +535,7 @@ int tokmix_fwd_impl(const void* xhat, const void* x, const void* w1_pad, int Np,
   if ((rc = smem_optin(tokmix_fwd_sm100, smem, optin))) return rc;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  tokmix_launch_cfg(cfg, attr, p, smem, st);
+  tokmix_launch_cfg(cfg, attr, p, smem, TM_FWD_THREADS, st);
   CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_fwd_sm100, tX, tW1, tW2, tH, tR, tU, p, hT ? 1 : 0));
   CUDA_OK(cudaGetLastError());
   ++g_launches;
@@ -565,7 +565,7 @@ int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const 
   if ((rc = smem_optin(tokmix_bwd_sm100, smem, optin))) return rc;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  tokmix_launch_cfg(cfg, attr, p, smem, st);
+  tokmix_launch_cfg(cfg, attr, p, smem, TM_BWD_THREADS, st);
   CUDA_OK(cudaLaunchKernelEx(&cfg, tokmix_bwd_sm100, tX, tDU, tW1, tW2T, tW1T, tDZ, p));
   CUDA_OK(cudaGetLastError());
   ++g_launches;

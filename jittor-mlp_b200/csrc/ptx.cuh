@@ -370,6 +370,61 @@ __device__ __forceinline__ void gelu_erf_pair(f32x2 z, f32x2& gelu, f32x2& dgelu
   gelu = mul2(z, cdf);
   if (WITH_GRAD) dgelu = fma2(mul2(z, pack2(0.3989422804014327f, 0.3989422804014327f)), e, cdf);   // Phi(z) + z * phi(z)
 }
+
+// erf-GELU with ONE MUFU per element (the epilogues of the fused token-mixing kernels are MUFU-bound with the rcp + ex2 of
+// gelu_erf_pair: 16 lanes/clk/SM).  Abramowitz-Stegun 7.1.28:  erfc(x) = P(x)^-16,  P = 1 + a1 x + ... + a6 x^6, x >= 0,
+// |err| <= 3e-7.  With a = |z| and the 1/sqrt2 of x = a/sqrt2 folded into the coefficients:
+//     r = 1 / P(a),  h = 0.5 r^16 = 1 - Phi(a),   gelu(z) = 0.5 z + a (0.5 - h)                       (exact identity in h)
+//     phi(a) = -dh/da = 8 P'(a) r^17,             gelu'(z) = 0.5 + sgn(z) (0.5 + r^16 (8 a P'(a) r - 0.5))
+// i.e. the density comes from the DERIVATIVE of the same rational form -- no exp.  Against fp64 erf/exp over |z| <= 9:
+// |gelu err| <= 9e-7, |gelu' err| <= 1.5e-6 (tools/ check in DESIGN.md), far below the bf16 quantum of what is stored.
+__device__ __forceinline__ f32x2 abs2(f32x2 v) {
+  f32x2 r;
+  asm("and.b64 %0, %1, 0x7fffffff7fffffff;" : "=l"(r) : "l"(v));
+  return r;
+}
+#define VMLP_P2(c) pack2((c), (c))
+template <bool WITH_GRAD>
+__device__ __forceinline__ void gelu_rcp16_pair(f32x2 z, f32x2& gelu, f32x2& dgelu) {
+  constexpr float B1 = 0.0705230784f * 0.70710678118654752f, B2 = 0.0422820123f * 0.5f,
+                  B3 = 0.0092705272f * 0.35355339059327376f, B4 = 0.0001520143f * 0.25f,
+                  B5 = 0.0002765672f * 0.17677669529663688f, B6 = 0.0000430638f * 0.125f;
+  const f32x2 a = abs2(z);
+  f32x2 pp = fma2(VMLP_P2(B6), a, VMLP_P2(B5));
+  pp = fma2(pp, a, VMLP_P2(B4));
+  pp = fma2(pp, a, VMLP_P2(B3));
+  pp = fma2(pp, a, VMLP_P2(B2));
+  pp = fma2(pp, a, VMLP_P2(B1));
+  pp = fma2(pp, a, VMLP_P2(1.0f));
+  float p0, p1;
+  unpack2(pp, p0, p1);
+  const f32x2 r = pack2(rcp_approx(p0), rcp_approx(p1));
+  f32x2 r16 = mul2(r, r);
+  r16 = mul2(r16, r16);
+  r16 = mul2(r16, r16);
+  r16 = mul2(r16, r16);
+  if (!WITH_GRAD) {
+    const f32x2 g = fma2(r16, VMLP_P2(-0.5f), VMLP_P2(0.5f));            // Phi(a) - 0.5
+    gelu = fma2(a, g, mul2(z, VMLP_P2(0.5f)));
+  } else {
+    f32x2 q = fma2(VMLP_P2(6.0f * B6), a, VMLP_P2(5.0f * B5));
+    q = fma2(q, a, VMLP_P2(4.0f * B4));
+    q = fma2(q, a, VMLP_P2(3.0f * B3));
+    q = fma2(q, a, VMLP_P2(2.0f * B2));
+    q = fma2(q, a, VMLP_P2(B1));                                          // P'(a)
+    const f32x2 t = mul2(mul2(a, q), r);
+    const f32x2 u = fma2(t, VMLP_P2(8.0f), VMLP_P2(-0.5f));
+    const f32x2 w = fma2(r16, u, VMLP_P2(0.5f));                          // Phi(a) + a phi(a) - 0.5  (>= 0)
+    f32x2 ws;
+    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xf8;" : "=r"(*reinterpret_cast<uint32_t*>(&ws)) : "r"((uint32_t)z), "r"((uint32_t)w));
+    uint32_t hi;
+    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xf8;" : "=r"(hi) : "r"((uint32_t)(z >> 32)), "r"((uint32_t)(w >> 32)));
+    ws = (ws & 0xffffffffull) | (static_cast<f32x2>(hi) << 32);            // copysign(w, z) per half: (z & sign) | w
+    dgelu = add2(ws, VMLP_P2(0.5f));
+    gelu = z;   // not needed by the callers of the gradient form
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2_f2(f32x2 v) {
   float lo, hi;
   unpack2(v, lo, hi);

@@ -18,11 +18,21 @@
 // Hidden chunks of 64 divide Ds = 784 with 16 left over (UMMA N = 16 for the tail chunk): no padded MMA work along Ds;
 // the token axis N = 196 is padded to NT = 208 by TMA zero fill (13 k-steps of 16).
 //
-// Warp roles (640 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA) + TMEM owner, warp 2 = TMA store of
-// the saved hidden tile, warp 3 idle, warps 4..19 = epilogue (TMEM lane quarter = warp % 4, 16 of the chunk's 64 columns
-// each).  The MMA warp issues G1 two chunks ahead of G2 so that the tensor pipe works on Z(g+1), Z(g+2) while the
-// epilogue warps run GELU on Z(g); all hand-offs are mbarriers (multicast tcgen05.commit towards both CTAs, remote
-// arrives towards the leader), no block-wide barrier in the steady state.
+// Warp roles, forward (640 threads): warp 0 = TMA producer of the weight rings and the activation tile, warp 1 = issuer of
+// G1 + TMEM owner, warp 3 = issuer of G2, warp 2 = TMA store of the hidden tile + the residual-in / output-out tile,
+// warps 4..19 = epilogue (TMEM lane quarter = warp % 4, 16 of the chunk's 64 columns each).  Backward (768 threads): warp
+// 0 = producer, warps 1 / 2 / 3 = issuers of Z / dH / G3, warp 4 = TMA store of the dZ tile, warps 4..7 = column sums,
+// warps 8..23 = epilogue.  All hand-offs are mbarriers (multicast tcgen05.commit towards both CTAs, remote arrives
+// towards the leader).
+//
+// What the first versions taught (clock64 timeline of CTA 0, tools/tokmix_trace.py; ncu source page): every mbarrier
+// operation costs a warp 100-200 cycles of latency even when it succeeds at once, so ONE issuer warp that waits on five
+// barriers and issues 17 MMAs per chunk needs ~1900 cycles for 832 cycles of tensor work, and an epilogue warp that does
+// wait / load / arrive / math / wait / wait / write / fence / arrive / arrive strictly in sequence needs ~1100 cycles of
+// pure hand-off latency per chunk on top of a MUFU-bound GELU (rcp + ex2 per element: 1024 cycles per chunk and SM).
+// Hence: two issuer warps; barrier probes issued back to back (test_wait) so their latencies overlap; the "buffer is
+// free" conditions merged into one barrier; the NEXT chunk's accumulator prefetched into registers before the math of
+// the current one; erf-GELU (and its derivative) with a single MUFU per element (ptx.cuh: gelu_rcp16_pair).
 #pragma once
 #include "ptx.cuh"
 
@@ -30,8 +40,11 @@ namespace vmlp {
 
 constexpr int TM_CH = 64;                              // hidden chunk (UMMA N of G1, K of G2 per chunk)
 constexpr int TM_EPI_WARPS = 16;
-constexpr int TM_FIRST_EPI_WARP = 4;
-constexpr int TM_THREADS = 32 * (TM_FIRST_EPI_WARP + TM_EPI_WARPS);   // 640
+// Registers are allocated to warps in groups of four: 20 warps leave 96 registers per thread, 21..24 warps leave 80.
+constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 16 epilogue warps
+constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_EPI_WARPS);   // 640
+constexpr int TM_BWD_EPI0 = 8;                                   // backward: 8 service warps + 16 epilogue warps
+constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 768
 constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
 constexpr int TM_MAX_DS = 1024;
 constexpr int TM_BAR_BYTES = 1024;
@@ -138,6 +151,37 @@ __device__ __forceinline__ TokTile tm_tile(const TokParams& p, int pair, int cta
   return t;
 }
 
+// non-suspending probe of an mbarrier phase (the suspending try_wait is used once the probe has failed)
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// wait for two barriers: both probes are in flight together (one ~150-cycle latency instead of two in sequence)
+template <int SLEEP_NS>
+__device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+  const uint32_t oa = mbar_test(a, pa), ob = mbar_test(b, pb);
+  if (!oa) mbar_wait<SLEEP_NS>(a, pa);
+  if (!ob) mbar_wait<SLEEP_NS>(b, pb);
+}
+// tcgen05.wait::ld that also names the 16 registers an earlier (prefetching) tcgen05.ld targets: their first use must not
+// be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
 // One epilogue thread's 16 packed bf16 values -> its row of the [128 x 64] SWIZZLE_128B hidden tile
 __device__ __forceinline__ void tm_store_hidden_row(uint32_t tile_addr, int row, int cq, const uint32_t (&o)[8]) {
   const uint32_t base = tile_addr + (row >> 3) * 1024 + (row & 7) * 128;
@@ -145,12 +189,17 @@ __device__ __forceinline__ void tm_store_hidden_row(uint32_t tile_addr, int row,
   st_shared_v4(base + (((2 * cq) ^ sw) << 4), make_uint4(o[0], o[1], o[2], o[3]));
   st_shared_v4(base + (((2 * cq + 1) ^ sw) << 4), make_uint4(o[4], o[5], o[6], o[7]));
 }
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
-// Forward.  SMEM: [barriers 1 KB][Xh^T tile NT*256][residual/output tile NT*256][W1 ring][W2 ring][H tiles 2 x 16 KB][b1][b2]
+// Forward.  SMEM: [barriers 1 KB][Xh^T tile NT*256][residual/output tile NT*256][W1 ring][W2 ring][H tiles][b1][b2]
 // TMEM: Z double buffer at columns [0, 128), U accumulator at [128, 128 + NT).
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TM_THREADS, 1)
+__global__ void __launch_bounds__(TM_FWD_THREADS, 1)
 tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]   box (64 c, NT rows)
                  const __grid_constant__ CUtensorMap tmW1,     // W1   [Ds, NT]    box (64 k, 32 rows) SWIZZLE_128B
                  const __grid_constant__ CUtensorMap tmW2,     // W2   [N, Ds]     box (64 k, NT/2 rows)
@@ -169,8 +218,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   uint64_t* xt_full = bars + 0;     uint64_t* xt_empty = bars + 1;
   uint64_t* u_full = bars + 2;      uint64_t* u_empty = bars + 3;
   uint64_t* z_full = bars + 4;      uint64_t* z_empty = bars + 6;      // [2] each
-  uint64_t* h_full = bars + 8;      uint64_t* h_empty = bars + 10;
-  uint64_t* h_done = bars + 12;     uint64_t* hs_empty = bars + 14;
+  uint64_t* h_full = bars + 8;      uint64_t* h_free = bars + 10;      // h_free: G2 has read the tile AND its TMA store has
+  uint64_t* h_done = bars + 12;                                        // h_done: this CTA's 16 epilogue warps have written it
   uint64_t* wa_full = bars + 16;    uint64_t* wa_empty = bars + 24;    // up to 8 stages each
   uint64_t* wb_full = bars + 32;    uint64_t* wb_empty = bars + 40;
   uint64_t* ro_full = bars + 48;    uint64_t* ro_done = bars + 49;
@@ -181,8 +230,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   const uint32_t s_wa = s_ro + p.NT * 256;
   const uint32_t s_wb = s_wa + p.s_wa * p.wa_stage;
   const uint32_t s_h = s_wb + p.s_wb * p.wb_stage;
-  float* sb1 = reinterpret_cast<float*>(smem + (s_h - s_base) + p.nhb * TM_HTILE);
-  float* sb2 = sb1 + p.n_chunks * TM_CH;
+  const uint32_t s_b1 = s_h + p.nhb * TM_HTILE;     // fp32 biases
+  const uint32_t s_b2 = s_b1 + p.n_chunks * TM_CH * 4;
+  float* sb1 = reinterpret_cast<float*>(smem + (s_b1 - s_base));
+  float* sb2 = reinterpret_cast<float*>(smem + (s_b2 - s_base));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
@@ -192,8 +243,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2 * TM_EPI_WARPS);
-      mbar_init(&h_full[i], 2 * TM_EPI_WARPS);  mbar_init(&h_empty[i], 1);
-      mbar_init(&h_done[i], TM_EPI_WARPS);      mbar_init(&hs_empty[i], 1);
+      mbar_init(&h_full[i], 2 * TM_EPI_WARPS);  mbar_init(&h_free[i], 2);
+      mbar_init(&h_done[i], TM_EPI_WARPS);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&wa_full[i], 1); mbar_init(&wa_empty[i], 1);
@@ -201,8 +252,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_THREADS) sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
-  for (int i = threadIdx.x; i < p.NT; i += TM_THREADS) sb2[i] = i < p.N ? __bfloat162float(p.b2[i]) : 0.f;
+  for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_FWD_THREADS) sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
+  for (int i = threadIdx.x; i < p.NT; i += TM_FWD_THREADS) sb2[i] = i < p.N ? __bfloat162float(p.b2[i]) : 0.f;
   if (warp == 1) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
   tc_fence_before();
   cluster_sync_all();
@@ -210,6 +261,9 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   const uint32_t tmem_base = *tmem_slot;
   const int NC = p.n_chunks;
   const int rot = (p.flags & 64) ? 0 : cluster_id % NC;
+  int my_items = 0;
+  for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
+  const int total = my_items * NC;                  // hidden chunks this cluster processes
 
   if (warp == 0) {
     // ================================================================ TMA producer (both CTAs; bytes signalled on the leader)
@@ -246,8 +300,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       __syncwarp();
       if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
     };
-    // loads are issued in the order the MMA warp consumes them: within an item W1(j) runs two chunks ahead of W2(j - 2);
-    // the last two W2 chunks are requested before the producer waits for the activation buffer of the next item
+    // within an item W1(j) is requested two chunks ahead of W2(j - 2) (the order the issuer warps consume them in); the
+    // last two W2 chunks of an item go out before the producer waits for the activation buffer of the next one
     int it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
@@ -266,26 +320,17 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       load_wb(NC - 1);
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (leader CTA)
+    // ================================================================ issuer of G1: Z^T = Xh^T * W1chunk^T (leader CTA)
     if (is_leader) {
-      const uint32_t idesc_g2 = umma_idesc_bf16(256, p.NT, 0, 0);
-      int my_items = 0;
-      for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
-      const int total = my_items * NC;
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      int j1 = 0, it1 = 0;        // chunk / item of the next G1
-      int j2 = 0, it2 = 0;        // chunk / item of the next G2
-      int t1 = 0, t2 = 0;         // global chunk counters of the next G1 / G2
-      auto do_g1 = [&]() {        // ---- G1(t1): Z^T = Xh^T * W1chunk^T
+      uint32_t sa = 0, pa = 0;
+      int j1 = 0, it1 = 0;
+      for (int t1 = 0; t1 < total; ++t1) {
         const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
+        const int zb = t1 & 1;
         if (lane == 0) tm_stamp(p, 0, t1, 0);
         if (j1 == 0) mbar_wait<32>(xt_full, it1 & 1);
-        const int zb = t1 & 1;
+        mbar_wait2<32>(&z_empty[zb], ((t1 >> 1) & 1) ^ 1, &wa_full[sa], pa);
         if (lane == 0) tm_stamp(p, 0, t1, 1);
-        mbar_wait<32>(&z_empty[zb], ((t1 >> 1) & 1) ^ 1);
-        if (lane == 0) tm_stamp(p, 0, t1, 2);
-        mbar_wait<32>(&wa_full[sa], pa);
-        if (lane == 0) tm_stamp(p, 0, t1, 3);
         tc_fence_after();
         if (elect_one_sync()) {
           tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_wa + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
@@ -294,69 +339,43 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           if (j1 == NC - 1) umma_commit_2cta_mc(xt_empty);
         }
         __syncwarp();
-        if (lane == 0) tm_stamp(p, 0, t1, 4);
+        if (lane == 0) tm_stamp(p, 0, t1, 2);
         if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
         if (++j1 == NC) { j1 = 0; ++it1; }
-        ++t1;
-      };
-      auto do_g2 = [&]() {        // ---- G2(t2): U^T (+)= H^T * W2chunk^T
+      }
+    }
+  } else if (warp == 3) {
+    // ================================================================ issuer of G2: U^T (+)= H^T * W2chunk^T (leader CTA)
+    if (is_leader) {
+      const uint32_t idesc_g2 = umma_idesc_bf16(256, p.NT, 0, 0);
+      uint32_t sb = 0, pb = 0;
+      int j2 = 0, it2 = 0;
+      for (int t2 = 0; t2 < total; ++t2) {
         const int hb = p.nhb == 2 ? (t2 & 1) : 0;
-        mbar_wait<32>(&h_full[hb], (p.nhb == 2 ? (t2 >> 1) : t2) & 1);
-        if (lane == 0) tm_stamp(p, 0, t2, 5);
-        mbar_wait<32>(&wb_full[sb], pb);
+        if (lane == 0) tm_stamp(p, 0, t2, 4);
         if (j2 == 0) mbar_wait<32>(u_empty, (it2 & 1) ^ 1);
-        if (lane == 0) tm_stamp(p, 0, t2, 6);
+        mbar_wait2<32>(&h_full[hb], (p.nhb == 2 ? (t2 >> 1) : t2) & 1, &wb_full[sb], pb);
+        if (lane == 0) tm_stamp(p, 0, t2, 5);
         tc_fence_after();
         if (elect_one_sync()) {
           const int ksteps = (tm_chunk(j2, rot, NC) == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
           tm_mma_over_hidden(tmem_base + 2 * TM_CH, s_h + hb * TM_HTILE, s_wb + sb * p.wb_stage, idesc_g2, ksteps, j2 == 0);
           umma_commit_2cta_mc(&wb_empty[sb]);
-          umma_commit_2cta_mc(&h_empty[hb]);
+          umma_commit_2cta_mc(&h_free[hb]);
           if (j2 == NC - 1) umma_commit_2cta_mc(u_full);
         }
         __syncwarp();
+        if (lane == 0) tm_stamp(p, 0, t2, 6);
         if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
         if (++j2 == NC) { j2 = 0; ++it2; }
-        if (lane == 0) tm_stamp(p, 0, t2, 7);
-        ++t2;
-      };
-      // G1 runs two chunks ahead of G2.  Inside an item G1(t) is issued before G2(t - 2) (it only needs the Z buffer that
-      // the epilogue released long ago); across an item boundary the two trailing G2 of the previous item go first, so
-      // that they never queue behind the wait for the next item's activation tile.
-      for (int t = 0; t < total + 2; ++t) {
-        const bool g1 = t < total, g2 = t >= 2;
-        const bool g2_first = g2 && (!g1 || j1 < 2);
-        if (g2 && g2_first) do_g2();
-        if (g1) do_g1();
-        if (g2 && !g2_first) do_g2();
       }
     }
   } else if (warp == 2) {
-    // ================================================================ TMA store of the saved hidden tile (each CTA its own)
-    int g = 0;
-    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
-      const TokTile t = tm_tile(p, pair, cta_rank);
-      for (int j = 0; j < NC; ++j, ++g) {
-        const int hb = p.nhb == 2 ? (g & 1) : 0;
-        mbar_wait<128>(&h_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
-        if (elect_one_sync()) {
-          if (save_hidden && t.valid && !(p.flags & 2)) {
-            tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
-            tma_store_commit();
-            tma_store_wait_read<0>();
-          }
-          mbar_arrive(&hs_empty[hb]);
-        }
-        __syncwarp();
-      }
-    }
-    if (elect_one_sync()) tma_store_wait_all<0>();
-    __syncwarp();
-  } else if (warp == 3) {
-    // ================================================================ residual-in / output-out tile (each CTA its own):
-    // TMA load of the item's residual x tile into the staging buffer, and -- once the 16 epilogue warps have turned it into
-    // the output in place (ro_done) -- TMA store of the tile, then the load of the NEXT item's residual.  A separate warp,
-    // so that neither the weight producer nor the hidden-tile store warp ever waits for the end of an item.
+    // ================================================================ TMA stores (each CTA its own tiles): the saved hidden
+    // tile of every chunk, and per item the residual-in / output-out tile: once the 16 epilogue warps have turned the
+    // residual into the output in place (ro_done) it is stored and the NEXT item's residual is loaded behind it.  (While
+    // this warp waits for ro_done the epilogue is in its output phase and writes no hidden tile; the first hidden tiles of
+    // the next item are stored a little late, which the double buffer absorbs.)
     auto load_residual = [&](int pair) {
       const TokTile t = tm_tile(p, pair, cta_rank);
       mbar_arrive_expect_tx(ro_full, p.NT * 256);
@@ -364,10 +383,23 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     };
     if (cluster_id < p.n_pairs && elect_one_sync()) load_residual(cluster_id);
     __syncwarp();
-    int it = 0;
+    int g = 0, it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
-      mbar_wait<128>(ro_done, it & 1);
+      for (int j = 0; j < NC; ++j, ++g) {
+        const int hb = p.nhb == 2 ? (g & 1) : 0;
+        mbar_wait<64>(&h_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        if (elect_one_sync()) {
+          if (save_hidden && t.valid && !(p.flags & 2)) {
+            tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          mbar_arrive(&h_free[hb]);
+        }
+        __syncwarp();
+      }
+      mbar_wait<64>(ro_done, it & 1);
       if (elect_one_sync()) {
         if (t.valid) {
           tma_store_3d(&tmU, smem + (s_ro - s_base), t.c0, 0, t.b);     // rows >= N and channels >= C are clipped
@@ -380,13 +412,16 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     }
     if (elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
-  } else if (warp >= TM_FIRST_EPI_WARP) {
-    // ================================================================ epilogue warps
+  } else if (warp >= TM_FWD_EPI0) {
+    // ================================================================ epilogue warps (software-pipelined over chunks)
     const int q = warp & 3;                               // TMEM lane quarter
-    const int cq = (warp - TM_FIRST_EPI_WARP) >> 2;       // 16-column group of the 64-column chunk
+    const int cq = (warp - TM_FWD_EPI0) >> 2;       // 16-column group of the 64-column chunk
     const int row = q * 32 + lane;                        // channel within the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
+    const bool tr = warp == TM_FWD_EPI0 && lane == 0;
+    uint32_t vn[16];                                      // accumulator columns of the NEXT chunk (in flight or landed)
+    bool have = false;                                    // vn holds (a pending load of) chunk g
     int g = 0, it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       for (int pos = 0; pos < NC; ++pos, ++g) {
@@ -394,59 +429,64 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live = cq * 16 < n1;
-        const bool tr = warp == TM_FIRST_EPI_WARP && lane == 0;
         if (tr) tm_stamp(p, 1, g, 0);
-        mbar_wait(&z_full[zb], (g >> 1) & 1);
-        if (tr) tm_stamp(p, 1, g, 1);
-        tc_fence_after();
-        uint32_t v[16];
-        if (live && !(p.flags & 16)) {
-          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, v);
-          tmem_ld_wait();
+        if (!have) {                                      // first chunk, or the producer side was not ahead: load now
+          mbar_wait(&z_full[zb], (g >> 1) & 1);
+          tc_fence_after();
+          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vn);
         }
+        tmem_ld_wait16(vn);
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = vn[i];
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&z_empty[zb], is_leader);
+        if (tr) tm_stamp(p, 1, g, 1);
+        // probes whose latency the math hides: is the hidden-tile buffer free; is the next chunk's accumulator complete
+        const int hb = p.nhb == 2 ? zb : 0;
+        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        const uint32_t free_ok = mbar_test(&h_free[hb], hph);
+        have = false;
+        if (g + 1 < total && mbar_test(&z_full[zb ^ 1], ((g + 1) >> 1) & 1)) {
+          tc_fence_after();
+          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + (zb ^ 1) * TM_CH + cq * 16 + lane_addr, vn);
+          have = true;
+        }
         if (tr) tm_stamp(p, 1, g, 2);
         uint32_t o[8];
         if (live && (p.flags & 1)) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
         } else if (live) {
-          const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = bp[e4];
+            const float4 bv = lds_f4(s_b1 + (j * TM_CH + cq * 16 + 4 * e4) * 4);
             f32x2 gl, dg;
-            gelu_erf_pair<false>(pack2(__uint_as_float(v[4 * e4]) + bv.x, __uint_as_float(v[4 * e4 + 1]) + bv.y), gl, dg);
+            gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4]) + bv.x, __uint_as_float(v[4 * e4 + 1]) + bv.y), gl, dg);
             o[2 * e4] = pack_bf16x2_f2(gl);
-            gelu_erf_pair<false>(pack2(__uint_as_float(v[4 * e4 + 2]) + bv.z, __uint_as_float(v[4 * e4 + 3]) + bv.w), gl, dg);
+            gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4 + 2]) + bv.z, __uint_as_float(v[4 * e4 + 3]) + bv.w), gl, dg);
             o[2 * e4 + 1] = pack_bf16x2_f2(gl);
           }
         }
-        const int hb = p.nhb == 2 ? zb : 0;                          // hidden tile buffer (one when two do not fit)
-        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
         if (tr) tm_stamp(p, 1, g, 3);
-        mbar_wait(&h_empty[hb], hph);                                // G2 of the previous user of this buffer has read it
+        if (!free_ok) mbar_wait(&h_free[hb], hph);        // G2 and the TMA store of this buffer's previous user are done
         if (tr) tm_stamp(p, 1, g, 4);
-        mbar_wait(&hs_empty[hb], hph);                               // ... and so has its TMA store
-        if (tr) tm_stamp(p, 1, g, 5);
         if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
-        if (tr) tm_stamp(p, 1, g, 6);
+        if (tr) tm_stamp(p, 1, g, 5);
         if (lane == 0) {
           tm_arrive_leader(&h_full[hb], is_leader);
           mbar_arrive(&h_done[hb]);
         }
-        if (tr) tm_stamp(p, 1, g, 7);
+        if (tr) tm_stamp(p, 1, g, 6);
       }
       // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
       // tokens per tcgen05.ld; the [token][channel] transposition goes through the shared residual/output tile: 2-byte
       // accesses at [n * 256 + ch * 2] -- the 32 lanes of a warp touch 64 consecutive bytes, conflict-free -- updated in
       // place, then ONE TMA store per tile (issued by warp 3) writes it out and clips rows >= N / channels >= C.
-      mbar_wait(ro_full, it & 1);
-      mbar_wait(u_full, it & 1);
+      mbar_wait2<0>(ro_full, it & 1, u_full, it & 1);
       tc_fence_after();
       const uint32_t ro_col = s_ro + row * 2;
 #pragma unroll 1
@@ -456,7 +496,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         uint32_t v[16];
         if (has) {
           tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + grp * 16 + lane_addr, v);
-          tmem_ld_wait();
+          tmem_ld_wait();                                 // (also completes a pending prefetch of the next item's chunk 0)
         }
         if (last) {
           tc_fence_before();
@@ -465,10 +505,9 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         }
         if (has) {
           const uint32_t a0 = ro_col + grp * 16 * 256;
-          const float4* bp = reinterpret_cast<const float4*>(sb2 + grp * 16);
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 bv = bp[i4];
+            const float4 bv = lds_f4(s_b2 + (grp * 16 + 4 * i4) * 4);
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -497,14 +536,14 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Backward (data-gradient chain).  SMEM: [barriers][Xh^T tile][dU^T tile][W1 ring][W2^T ring][W1^T ring][dZ tiles 2 x 16 KB][b1]
+// Backward (data-gradient chain).  SMEM: [barriers][Xh^T tile][dU^T tile][W1 ring][W2^T ring][W1^T ring][dZ tile(s)][b1][d b1 sums]
 // TMEM: Z double buffer [0, 128), dH double buffer [128, 256), dXh accumulator [256, 256 + NT).
 // Per hidden chunk: G1 Z^T = Xh^T * W1chunk^T (recomputed, never stored), G2 dH^T = dU^T * W2[:, chunk],
 // epilogue dZ^T = dH^T .* gelu'(Z^T + b1) -> bf16 SMEM tile (+ TMA store into dZ^T [B, C, Ds] for the weight gradient),
 // G3 dXh^T += dZ^T * W1[chunk, :].  The weight operands are all K-major copies prepared once per step by
 // vmlp_tokmix_prepare: W1 [Ds, Np], W2^T [Ds, Np], W1^T [N, Ds].
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TM_THREADS, 1)
+__global__ void __launch_bounds__(TM_BWD_THREADS, 1)
 tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C]   box (64 c, NT rows)
                  const __grid_constant__ CUtensorMap tmDU,     // dU    [B, N, C]   box (64 c, NT rows)
                  const __grid_constant__ CUtensorMap tmW1,     // W1    [Ds, NT]    box (64 k, 32 rows)
@@ -523,8 +562,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   uint64_t* in_full = bars + 0;     uint64_t* in_empty = bars + 1;
   uint64_t* dx_full = bars + 2;     uint64_t* dx_empty = bars + 3;
   uint64_t* zd_full = bars + 4;     uint64_t* zd_empty = bars + 6;     // [2] each
-  uint64_t* dz_full = bars + 8;     uint64_t* dz_empty = bars + 10;
-  uint64_t* dz_done = bars + 12;    uint64_t* dzs_empty = bars + 14;
+  uint64_t* dz_full = bars + 8;     uint64_t* dz_free = bars + 10;     // dz_free: G3 + TMA store + column sums have read the tile
+  uint64_t* dz_done = bars + 12;
   uint64_t* w1_full = bars + 16;    uint64_t* w1_empty = bars + 20;    // up to 4 stages each
   uint64_t* w2_full = bars + 24;    uint64_t* w2_empty = bars + 28;
   uint64_t* w3_full = bars + 32;    uint64_t* w3_empty = bars + 36;
@@ -536,18 +575,19 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t s_w2 = s_w1 + p.s_wa * p.wa_stage;
   const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
   const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
-  float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + p.nhb * TM_HTILE);
+  const uint32_t s_b1 = s_dz + p.nhb * TM_HTILE;
+  float* sb1 = reinterpret_cast<float*>(smem + (s_b1 - s_base));
   float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
-    mbar_init(in_full, 1); mbar_init(in_empty, 1);
+    mbar_init(in_full, 1); mbar_init(in_empty, 2);
     mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * TM_EPI_WARPS);
-      mbar_init(&dz_full[i], 2 * TM_EPI_WARPS);  mbar_init(&dz_empty[i], 1);
-      mbar_init(&dz_done[i], TM_EPI_WARPS);      mbar_init(&dzs_empty[i], 2);   // store warp + column-sum warp
+      mbar_init(&zd_full[i], 2);  mbar_init(&zd_empty[i], 2 * TM_EPI_WARPS);
+      mbar_init(&dz_full[i], 2 * TM_EPI_WARPS);  mbar_init(&dz_free[i], 5);   // G3 commit + the four store / column-sum warps
+      mbar_init(&dz_done[i], TM_EPI_WARPS);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1);
@@ -556,7 +596,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_THREADS) {
+  for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_BWD_THREADS) {
     sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
     sdb[i] = 0.f;
   }
@@ -567,6 +607,9 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t tmem_base = *tmem_slot;
   const int NC = p.n_chunks;
   const int rot = (p.flags & 64) ? 0 : cluster_id % NC;
+  int my_items = 0;
+  for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
+  const int total = my_items * NC;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -579,20 +622,15 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       const int j = tm_chunk(pos, rot, NC);
       const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
       const int row = j * TM_CH + cta_rank * (n1 >> 1);
-      mbar_wait<128>(&w1_empty[sa], pa ^ 1);
+      mbar_wait2<128>(&w1_empty[sa], pa ^ 1, &w2_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
-        if (p.flags & 32) { if (is_leader) mbar_arrive(&w1_full[sa]); }
+        if (p.flags & 32) { if (is_leader) { mbar_arrive(&w1_full[sa]); mbar_arrive(&w2_full[sa]); } }
         else {
-          if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
+          if (is_leader) {
+            mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
+            mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
+          }
           tm_load_wa(s_w1 + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
-        }
-      }
-      __syncwarp();
-      mbar_wait<128>(&w2_empty[sa], pa ^ 1);
-      if (elect_one_sync()) {
-        if (p.flags & 32) { if (is_leader) mbar_arrive(&w2_full[sa]); }
-        else {
-          if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
           tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
         }
       }
@@ -632,119 +670,121 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       if (NC >= 2) load_w3(NC - 2);
       load_w3(NC - 1);
     }
-  } else if (warp == 1) {
-    // ================================================================ MMA issuer (leader CTA)
+  } else if (warp == 1 || warp == 2) {
+    // ================================================================ issuers (leader CTA): warp 1 of Z^T = Xh^T W1chunk^T,
+    // warp 2 of dH^T = dU^T W2[:, chunk].  zd_full collects both commits (count 2), either warp frees its own ring stage;
+    // the activation tiles are released by the later of the two last commits of an item (in_empty, count 2).
     if (is_leader) {
-      const uint32_t idesc_g3 = umma_idesc_bf16(256, p.NT, 0, 0);
-      int my_items = 0;
-      for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
-      const int total = my_items * NC;
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-      int j1 = 0, it1 = 0, j3 = 0, it3 = 0;
-      int t1 = 0, t3 = 0;
-      auto do_g12 = [&]() {       // ---- Z^T = Xh^T * W1chunk^T and dH^T = dU^T * W2[:, chunk]
+      const bool zrole = warp == 1;
+      uint64_t* wfull = zrole ? w1_full : w2_full;
+      uint64_t* wempty = zrole ? w1_empty : w2_empty;
+      const uint32_t s_act = zrole ? s_xt : s_dut, s_w = zrole ? s_w1 : s_w2;
+      const uint32_t d_off = zrole ? 0 : 2 * TM_CH;
+      uint32_t sa = 0, pa = 0;
+      int j1 = 0, it1 = 0;
+      for (int t1 = 0; t1 < total; ++t1) {
         const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
-        if (j1 == 0) mbar_wait<32>(in_full, it1 & 1);
         const int zb = t1 & 1;
-        mbar_wait<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
-        mbar_wait<32>(&w1_full[sa], pa);
+        if (j1 == 0) mbar_wait<32>(in_full, it1 & 1);
+        mbar_wait2<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1, &wfull[sa], pa);
         tc_fence_after();
         if (elect_one_sync()) {
-          tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_w1 + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
-          umma_commit_2cta_mc(&w1_empty[sa]);
-        }
-        __syncwarp();
-        mbar_wait<32>(&w2_full[sa], pa);
-        tc_fence_after();
-        if (elect_one_sync()) {
-          tm_mma_over_tokens(tmem_base + 2 * TM_CH + zb * TM_CH, s_dut, s_w2 + sa * p.wa_stage,
-                             umma_idesc_bf16(256, n1, 1, 0), p);
-          umma_commit_2cta_mc(&w2_empty[sa]);
+          tm_mma_over_tokens(tmem_base + d_off + zb * TM_CH, s_act, s_w + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
+          umma_commit_2cta_mc(&wempty[sa]);
           umma_commit_2cta_mc(&zd_full[zb]);
           if (j1 == NC - 1) umma_commit_2cta_mc(in_empty);
         }
         __syncwarp();
         if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
         if (++j1 == NC) { j1 = 0; ++it1; }
-        ++t1;
-      };
-      auto do_g3 = [&]() {        // ---- dXh^T (+)= dZ^T * W1[chunk, :]
+      }
+    }
+  } else if (warp == 3) {
+    // ================================================================ issuer of G3: dXh^T (+)= dZ^T * W1[chunk, :]
+    if (is_leader) {
+      const uint32_t idesc_g3 = umma_idesc_bf16(256, p.NT, 0, 0);
+      uint32_t sb = 0, pb = 0;
+      int j3 = 0, it3 = 0;
+      for (int t3 = 0; t3 < total; ++t3) {
         const int hb = p.nhb == 2 ? (t3 & 1) : 0;
-        mbar_wait<32>(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1);
-        mbar_wait<32>(&w3_full[sb], pb);
         if (j3 == 0) mbar_wait<32>(dx_empty, (it3 & 1) ^ 1);
+        mbar_wait2<32>(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1, &w3_full[sb], pb);
         tc_fence_after();
         if (elect_one_sync()) {
           const int ksteps = (tm_chunk(j3, rot, NC) == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
           tm_mma_over_hidden(tmem_base + 4 * TM_CH, s_dz + hb * TM_HTILE, s_w3 + sb * p.wb_stage, idesc_g3, ksteps, j3 == 0);
           umma_commit_2cta_mc(&w3_empty[sb]);
-          umma_commit_2cta_mc(&dz_empty[hb]);
+          umma_commit_2cta_mc(&dz_free[hb]);
           if (j3 == NC - 1) umma_commit_2cta_mc(dx_full);
         }
         __syncwarp();
         if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
         if (++j3 == NC) { j3 = 0; ++it3; }
-        ++t3;
-      };
-      for (int t = 0; t < total + 2; ++t) {      // same issue order as the forward kernel
-        const bool g1 = t < total, g3 = t >= 2;
-        const bool g3_first = g3 && (!g1 || j1 < 2);
-        if (g3 && g3_first) do_g3();
-        if (g1) do_g12();
-        if (g3 && !g3_first) do_g3();
       }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ================================================================ helper warps: warp 2 stores the dZ^T tile by TMA;
-    // both sum the tile's columns over their 64 channel rows (d b1[m] = sum over (b, c) of dZ): lane l owns hidden
-    // columns 2l, 2l+1 of the chunk and reads one 32-bit word per row (the 16-byte chunk index is un-swizzled per row).
-    const int r0 = (warp - 2) * 64;
-    const uint32_t kq = lane >> 2, wofs = (lane & 3) * 4;
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================ helper warps 4..7: warp 4 stores the dZ^T tile by TMA;
+    // all four sum the tile's columns over 32 channel rows each (d b1[m] = sum over (b, c) of dZ).  Lane l reads the
+    // 16-byte chunk (l & 7) -- eight hidden columns -- of rows r0 + (l >> 3) + 4 i: one LDS.128 per row, eight independent
+    // fp32 accumulators, then two shuffle steps fold the four row phases.
+    const int r0 = (warp - 4) * 32;
+    const uint32_t kc = lane & 7;
+    const int rs = lane >> 3;
     int g = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
       const TokTile t = tm_tile(p, pair, cta_rank);
       for (int pos = 0; pos < NC; ++pos, ++g) {
         const int j = tm_chunk(pos, rot, NC);
         const int hb = p.nhb == 2 ? (g & 1) : 0;
-        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
-        if (warp == 2 && elect_one_sync()) {
+        mbar_wait<32>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        if (warp == 4 && elect_one_sync()) {
           if (t.valid && !(p.flags & 2)) {
             tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
             tma_store_commit();
           }
         }
         __syncwarp();
-        float s0 = 0.f, s1 = 0.f;
-        if (t.valid && 2 * lane < n1 && !(p.flags & 4)) {
+        if (t.valid && !(p.flags & 4)) {
           const uint32_t tb = s_dz + hb * TM_HTILE;
-#pragma unroll 8
-          for (int r = r0; r < r0 + 64; ++r) {
-            uint32_t w;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tb + r * 128 + ((kq ^ (r & 7)) << 4) + wofs) : "memory");
-            s0 += bf16lo(w);
-            s1 += bf16hi(w);
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + rs + 4 * i;
+            const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
+            acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
+            acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
           }
-          atomicAdd(&sdb[j * TM_CH + 2 * lane], s0);
-          atomicAdd(&sdb[j * TM_CH + 2 * lane + 1], s1);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+          }
+          if (rs == 0) {           // columns beyond Ds hold zeros (zero weights, zero-padded bias table)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&sdb[j * TM_CH + kc * 8 + e], acc[e]);
+          }
         }
         __syncwarp();
         if (elect_one_sync()) {
-          if (warp == 2) tma_store_wait_read<0>();
-          mbar_arrive(&dzs_empty[hb]);
+          if (warp == 4) tma_store_wait_read<0>();
+          mbar_arrive(&dz_free[hb]);
         }
         __syncwarp();
       }
     }
-    if (warp == 2 && elect_one_sync()) tma_store_wait_all<0>();
+    if (warp == 4 && elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
-  } else if (warp >= TM_FIRST_EPI_WARP) {
-    // ================================================================ epilogue warps
+  } else if (warp >= TM_BWD_EPI0) {
+    // ================================================================ epilogue warps (software-pipelined over chunks)
     const int q = warp & 3;
-    const int cq = (warp - TM_FIRST_EPI_WARP) >> 2;
+    const int cq = (warp - TM_BWD_EPI0) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
+    uint32_t vn[16];                                      // Z columns of the NEXT chunk (in flight or landed)
+    bool have = false;
     int g = 0, it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
@@ -755,37 +795,49 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live = cq * 16 < n1;
-        mbar_wait(&zd_full[zb], (g >> 1) & 1);
-        tc_fence_after();
-        uint32_t vz[16], vh[16];
-        if (live && !(p.flags & 16)) {
-          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vz);
-          tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
-          tmem_ld_wait();
+        if (!have) {
+          mbar_wait(&zd_full[zb], (g >> 1) & 1);
+          tc_fence_after();
+          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vn);
         }
+        tmem_ld_wait16(vn);
+        uint32_t vz[16], vh[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) vz[i] = vn[i];
+        // dH of this chunk (needed only after gelu' is known) and, if already complete, Z of the next chunk: both loads fly
+        // while the math runs
+        if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
+        const int hb = p.nhb == 2 ? zb : 0;
+        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        const uint32_t free_ok = mbar_test(&dz_free[hb], hph);
+        have = false;
+        if (g + 1 < total && mbar_test(&zd_full[zb ^ 1], ((g + 1) >> 1) & 1)) {
+          tc_fence_after();
+          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + (zb ^ 1) * TM_CH + cq * 16 + lane_addr, vn);
+          have = true;
+        }
+        f32x2 dgp[8];
+        if (live && !(p.flags & 1)) {
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bv = lds_f4(s_b1 + (j * TM_CH + cq * 16 + 4 * e4) * 4);
+            f32x2 gl;
+            gelu_rcp16_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dgp[2 * e4]);
+            gelu_rcp16_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dgp[2 * e4 + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dgp[e] = pack2(1.f, 1.f);
+        }
+        tmem_ld_wait16(vh);                               // dH(g) has landed (and so has a prefetched Z(g + 1))
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
         uint32_t o[8];
-        if (live && (p.flags & 1)) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(vz[2 * e]) + __uint_as_float(vh[2 * e]), __uint_as_float(vz[2 * e + 1]) + __uint_as_float(vh[2 * e + 1]));
-        } else if (live) {
-          const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = bp[e4];
-            f32x2 gl, dg;
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dg);
-            o[2 * e4] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4]), __uint_as_float(vh[4 * e4 + 1]))));
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dg);
-            o[2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
-          }
-        }
-        const int hb = p.nhb == 2 ? zb : 0;                        // dZ tile buffer (single-buffered when two do not fit)
-        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
-        mbar_wait(&dz_empty[hb], hph);                             // G3 of the previous user of this buffer has read it
-        mbar_wait(&dzs_empty[hb], hph);                            // ... and so have its TMA store and column sums
+        for (int e = 0; e < 8; ++e)
+          o[e] = pack_bf16x2_f2(mul2(dgp[e], pack2(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1]))));
+        if (!free_ok) mbar_wait(&dz_free[hb], hph);       // G3, TMA store and column sums of the previous user are done
         if (live && !(p.flags & 8)) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
         __syncwarp();
@@ -835,7 +887,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     tmem_dealloc_2cta(tmem_base, 512);
   }
   if (p.db1 != nullptr)
-    for (int i = threadIdx.x; i < p.Ds; i += TM_THREADS) red_add_f32(p.db1 + i, sdb[i]);
+    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i]);
 }
 
 // W [rows, cols] -> padded copy [rows, ld] (zero fill) and/or transposed copy [cols, ldt] (zero fill): the K-major weight
