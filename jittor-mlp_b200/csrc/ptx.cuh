@@ -240,6 +240,10 @@ __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n, int a_mn_major
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// non-blocking arrival on a named barrier (the warps that only produce; the consumer warp calls named_bar_sync)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -416,10 +420,10 @@ __device__ __forceinline__ void gelu_rcp16_pair(f32x2 z, f32x2& gelu, f32x2& dge
     const f32x2 u = fma2(t, VMLP_P2(8.0f), VMLP_P2(-0.5f));
     const f32x2 w = fma2(r16, u, VMLP_P2(0.5f));                          // Phi(a) + a phi(a) - 0.5  (>= 0)
     f32x2 ws;
-    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xf8;" : "=r"(*reinterpret_cast<uint32_t*>(&ws)) : "r"((uint32_t)z), "r"((uint32_t)w));
-    uint32_t hi;
-    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xf8;" : "=r"(hi) : "r"((uint32_t)(z >> 32)), "r"((uint32_t)(w >> 32)));
-    ws = (ws & 0xffffffffull) | (static_cast<f32x2>(hi) << 32);            // copysign(w, z) per half: (z & sign) | w
+    uint32_t lo, hi;                                                      // copysign(w, z) per half: (z & sign) | w, immLut 0xEA
+    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xea;" : "=r"(lo) : "r"((uint32_t)z), "r"((uint32_t)w));
+    asm("lop3.b32 %0, %1, 0x80000000, %2, 0xea;" : "=r"(hi) : "r"((uint32_t)(z >> 32)), "r"((uint32_t)(w >> 32)));
+    ws = static_cast<f32x2>(lo) | (static_cast<f32x2>(hi) << 32);
     dgelu = add2(ws, VMLP_P2(0.5f));
     gelu = z;   // not needed by the callers of the gradient form
   }

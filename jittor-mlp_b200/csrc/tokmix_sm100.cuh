@@ -43,6 +43,7 @@ constexpr int TM_EPI_WARPS = 16;
 // Registers are allocated to warps in groups of four: 20 warps leave 96 registers per thread, 21..24 warps leave 80.
 constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 16 epilogue warps
 constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_EPI_WARPS);   // 640
+constexpr int TM_NB_START = 1, TM_NB_ZE = 2, TM_NB_HW = 4;          // named (hardware) barrier ids, see the epilogue
 constexpr int TM_BWD_EPI0 = 8;                                   // backward: 8 service warps + 16 epilogue warps
 constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 768
 constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
@@ -218,8 +219,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   uint64_t* xt_full = bars + 0;     uint64_t* xt_empty = bars + 1;
   uint64_t* u_full = bars + 2;      uint64_t* u_empty = bars + 3;
   uint64_t* z_full = bars + 4;      uint64_t* z_empty = bars + 6;      // [2] each
-  uint64_t* h_full = bars + 8;      uint64_t* h_free = bars + 10;      // h_free: G2 has read the tile AND its TMA store has
-  uint64_t* h_done = bars + 12;                                        // h_done: this CTA's 16 epilogue warps have written it
+  uint64_t* h_full = bars + 8;      uint64_t* h_free = bars + 10;      // h_free: G2 and the TMA store have both read the tile
   uint64_t* wa_full = bars + 16;    uint64_t* wa_empty = bars + 24;    // up to 8 stages each
   uint64_t* wb_full = bars + 32;    uint64_t* wb_empty = bars + 40;
   uint64_t* ro_full = bars + 48;    uint64_t* ro_done = bars + 49;
@@ -242,9 +242,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     mbar_init(ro_full, 1); mbar_init(ro_done, TM_EPI_WARPS);
     mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2 * TM_EPI_WARPS);
-      mbar_init(&h_full[i], 2 * TM_EPI_WARPS);  mbar_init(&h_free[i], 2);
-      mbar_init(&h_done[i], TM_EPI_WARPS);
+      mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2);      // one forwarded arrival per CTA (warp 2)
+      mbar_init(&h_full[i], 2);  mbar_init(&h_free[i], 2);
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&wa_full[i], 1); mbar_init(&wa_empty[i], 1);
@@ -387,9 +386,16 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       const TokTile t = tm_tile(p, pair, cta_rank);
       for (int j = 0; j < NC; ++j, ++g) {
-        const int hb = p.nhb == 2 ? (g & 1) : 0;
-        mbar_wait<64>(&h_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        const int zb = g & 1;
+        const int hb = p.nhb == 2 ? zb : 0;
+        // the 16 epilogue warps of this CTA have read Z(g): forward ONE arrival to the leader's barrier
+        named_bar_sync(TM_NB_ZE + zb, 32 * (TM_EPI_WARPS + 1));
+        if (elect_one_sync()) tm_arrive_leader(&z_empty[zb], is_leader);
+        __syncwarp();
+        // ... have written (and proxy-fenced) the hidden tile H(g): tell the G2 issuer, store the tile, release the buffer
+        named_bar_sync(TM_NB_HW + zb, 32 * (TM_EPI_WARPS + 1));
         if (elect_one_sync()) {
+          tm_arrive_leader(&h_full[hb], is_leader);
           if (save_hidden && t.valid && !(p.flags & 2)) {
             tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
             tma_store_commit();
@@ -420,39 +426,30 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
     const bool tr = warp == TM_FWD_EPI0 && lane == 0;
-    uint32_t vn[16];                                      // accumulator columns of the NEXT chunk (in flight or landed)
-    bool have = false;                                    // vn holds (a pending load of) chunk g
     int g = 0, it = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
       for (int pos = 0; pos < NC; ++pos, ++g) {
         const int j = tm_chunk(pos, rot, NC);
         const int zb = g & 1;
+        const int hb = p.nhb == 2 ? zb : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live = cq * 16 < n1;
         if (tr) tm_stamp(p, 1, g, 0);
-        if (!have) {                                      // first chunk, or the producer side was not ahead: load now
-          mbar_wait(&z_full[zb], (g >> 1) & 1);
-          tc_fence_after();
-          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vn);
-        }
-        tmem_ld_wait16(vn);
-        uint32_t v[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = vn[i];
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tm_arrive_leader(&z_empty[zb], is_leader);
+        // ONE warp polls the mbarriers (Z(g) complete; hidden buffer free: G2 and the TMA store of its previous user done),
+        // the named barrier releases the other fifteen: an mbarrier operation costs a warp 100-200 cycles and the SM
+        // serialises them, 16 warps x 7 operations per chunk was the critical path of the first versions
+        if (warp == TM_FWD_EPI0)
+          mbar_wait2<0>(&z_full[zb], (g >> 1) & 1, &h_free[hb], ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1);
+        named_bar_sync(TM_NB_START, 32 * TM_EPI_WARPS);
+        tc_fence_after();
         if (tr) tm_stamp(p, 1, g, 1);
-        // probes whose latency the math hides: is the hidden-tile buffer free; is the next chunk's accumulator complete
-        const int hb = p.nhb == 2 ? zb : 0;
-        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
-        const uint32_t free_ok = mbar_test(&h_free[hb], hph);
-        have = false;
-        if (g + 1 < total && mbar_test(&z_full[zb ^ 1], ((g + 1) >> 1) & 1)) {
-          tc_fence_after();
-          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + (zb ^ 1) * TM_CH + cq * 16 + lane_addr, vn);
-          have = true;
+        uint32_t v[16];
+        if (live && !(p.flags & 16)) {
+          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, v);
+          tmem_ld_wait();
         }
+        tc_fence_before();
+        named_bar_arrive(TM_NB_ZE + zb, 32 * (TM_EPI_WARPS + 1));      // warp 2 forwards "Z(g) consumed" to the G1 issuer
         if (tr) tm_stamp(p, 1, g, 2);
         uint32_t o[8];
         if (live && (p.flags & 1)) {
@@ -470,17 +467,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           }
         }
         if (tr) tm_stamp(p, 1, g, 3);
-        if (!free_ok) mbar_wait(&h_free[hb], hph);        // G2 and the TMA store of this buffer's previous user are done
-        if (tr) tm_stamp(p, 1, g, 4);
         if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + hb * TM_HTILE, row, cq, o);
         fence_proxy_async_smem();
-        __syncwarp();
-        if (tr) tm_stamp(p, 1, g, 5);
-        if (lane == 0) {
-          tm_arrive_leader(&h_full[hb], is_leader);
-          mbar_arrive(&h_done[hb]);
-        }
-        if (tr) tm_stamp(p, 1, g, 6);
+        named_bar_arrive(TM_NB_HW + zb, 32 * (TM_EPI_WARPS + 1));      // warp 2 forwards "H(g) written", stores the tile
+        if (tr) tm_stamp(p, 1, g, 4);
       }
       // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
       // tokens per tcgen05.ld; the [token][channel] transposition goes through the shared residual/output tile: 2-byte
@@ -822,8 +812,10 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
           for (int e4 = 0; e4 < 4; ++e4) {
             const float4 bv = lds_f4(s_b1 + (j * TM_CH + cq * 16 + 4 * e4) * 4);
             f32x2 gl;
-            gelu_rcp16_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dgp[2 * e4]);
-            gelu_rcp16_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dgp[2 * e4 + 1]);
+            // rcp + ex2 form here: it is MUFU-bound at 1024 cycles per chunk and SM, the single-MUFU gradient form needs 22
+            // FMA-pipe lane operations per element = 1408 cycles (the forward value form needs 13 = 832)
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dgp[2 * e4]);
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dgp[2 * e4 + 1]);
           }
         } else {
 #pragma unroll

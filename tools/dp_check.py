@@ -45,5 +45,28 @@ dist.all_reduce(same, op=dist.ReduceOp.MIN)
 if rank == 0:
     print(f"dp_check world={world}: max rel-L2(dp grad, big-batch grad) = {float(t):.3e}; identical across ranks = {bool(same.item())}")
     assert float(t) < 2e-2 and bool(same.item())
+
+# CUDA-graph mode (what bench.py times for N > 1): the captured step holds this rank's compute only, ONE grouped NCCL
+# all-reduce of the static gradient buffers follows every replay (graph.GraphedStep(ddp=...), dp.reduce_static)
+model.zero_grad(set_to_none=True)
+gs = J.GraphedStep(model, xs[rank * per:(rank + 1) * per], loss_fn, ddp=ddp)
+for _ in range(2):
+    gs.run()
+torch.cuda.synchronize()
+worst_g = 0.0
+for k, p in model.named_parameters():
+    err = float((p.grad.float() - dp_grads[k]).norm() / dp_grads[k].norm().clamp_min(1e-20))
+    worst_g = max(worst_g, err)
+tg = torch.tensor([worst_g], device=dev)
+dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+flat = torch.cat([p.grad.float().flatten() for p in model.parameters()])
+ref0 = flat.clone()
+dist.broadcast(ref0, src=0)
+same = torch.tensor([float(torch.equal(flat, ref0))], device=dev)
+dist.all_reduce(same, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print(f"dp_check world={world} (graph + one grouped all-reduce, {len(ddp._static)} buffers): max rel-L2 vs eager DP step = "
+          f"{float(tg):.3e}; identical across ranks = {bool(same.item())}")
+    assert float(tg) < 5e-3 and bool(same.item())
 dist.barrier()
 dist.destroy_process_group()
