@@ -471,7 +471,7 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   // as with it (the L2 -> SMEM stream is not the limiter), so a second hidden-tile buffer comes before ring depth.
   const int force_depth = [] { const char* e = getenv("VMLP_TM_DEPTH"); return e ? atoi(e) : 0; }();
   const int force_nhb = [] { const char* e = getenv("VMLP_TM_NHB"); return e ? atoi(e) : 0; }();
-  for (int nhb = 2; nhb >= 1; --nhb) {
+  for (int nhb = 2; nhb >= (backward ? 1 : 2); --nhb) {   // forward: one hidden-tile buffer per epilogue group
     if (force_nhb && nhb != force_nhb) continue;
     for (int depth = 4; depth >= 2; --depth) {
       if (force_depth && depth != force_depth) continue;

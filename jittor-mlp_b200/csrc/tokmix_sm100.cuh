@@ -43,7 +43,7 @@ constexpr int TM_EPI_WARPS = 16;
 // Registers are allocated to warps in groups of four: 20 warps leave 96 registers per thread, 21..24 warps leave 80.
 constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 16 epilogue warps
 constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_EPI_WARPS);   // 640
-constexpr int TM_NB_START = 1, TM_NB_ZE = 2, TM_NB_HW = 4;          // named (hardware) barrier ids, see the epilogue
+constexpr int TM_NB_START = 1, TM_NB_ZE = 3, TM_NB_HW = 5;          // named (hardware) barrier ids (+ group), see the epilogue
 constexpr int TM_BWD_EPI0 = 8;                                   // backward: 8 service warps + 16 epilogue warps
 constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 768
 constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
@@ -382,138 +382,159 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     };
     if (cluster_id < p.n_pairs && elect_one_sync()) load_residual(cluster_id);
     __syncwarp();
-    int g = 0, it = 0;
-    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
-      const TokTile t = tm_tile(p, pair, cta_rank);
-      for (int j = 0; j < NC; ++j, ++g) {
-        const int zb = g & 1;
-        const int hb = p.nhb == 2 ? zb : 0;
-        // the 16 epilogue warps of this CTA have read Z(g): forward ONE arrival to the leader's barrier
-        named_bar_sync(TM_NB_ZE + zb, 32 * (TM_EPI_WARPS + 1));
-        if (elect_one_sync()) tm_arrive_leader(&z_empty[zb], is_leader);
-        __syncwarp();
-        // ... have written (and proxy-fenced) the hidden tile H(g): tell the G2 issuer, store the tile, release the buffer
-        named_bar_sync(TM_NB_HW + zb, 32 * (TM_EPI_WARPS + 1));
-        if (elect_one_sync()) {
-          tm_arrive_leader(&h_full[hb], is_leader);
-          if (save_hidden && t.valid && !(p.flags & 2)) {
-            tma_store_3d(&tmH, smem + (s_h - s_base) + hb * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
-            tma_store_commit();
-            tma_store_wait_read<0>();
-          }
-          mbar_arrive(&h_free[hb]);
-        }
-        __syncwarp();
-      }
-      mbar_wait<64>(ro_done, it & 1);
+    // "Z(g) has been read by the 8 warps of group g & 1" is forwarded as ONE arrival to the leader's z_empty; "H(g) has been
+    // written" is forwarded to h_full, the tile is stored and the buffer released.  At the end of an item the output tile.
+    auto forward_hw = [&](int g) {
+      const int gi = g & 1;
+      const int item = g / NC, j = g - item * NC;
+      const TokTile t = tm_tile(p, cluster_id + item * num_clusters, cta_rank);
+      named_bar_sync(TM_NB_HW + gi, 32 * (TM_EPI_WARPS / 2 + 1));
       if (elect_one_sync()) {
-        if (t.valid) {
-          tma_store_3d(&tmU, smem + (s_ro - s_base), t.c0, 0, t.b);     // rows >= N and channels >= C are clipped
+        tm_arrive_leader(&h_full[gi], is_leader);
+        if (save_hidden && t.valid && !(p.flags & 2)) {
+          tma_store_3d(&tmH, smem + (s_h - s_base) + gi * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
           tma_store_commit();
           tma_store_wait_read<0>();
         }
-        if (pair + num_clusters < p.n_pairs) load_residual(pair + num_clusters);
+        mbar_arrive(&h_free[gi]);
       }
       __syncwarp();
+      if (j == NC - 1) {                                   // last chunk of an item: its output tile follows
+        mbar_wait<64>(ro_done, item & 1);
+        if (elect_one_sync()) {
+          if (t.valid) {
+            tma_store_3d(&tmU, smem + (s_ro - s_base), t.c0, 0, t.b);     // rows >= N and channels >= C are clipped
+            tma_store_commit();
+            tma_store_wait_read<0>();
+          }
+          if (item + 1 < my_items) load_residual(cluster_id + (item + 1) * num_clusters);
+        }
+        __syncwarp();
+      }
+    };
+    // H(g - 1) before Z(g): at an item boundary the group that owns chunk g first does its share of the previous item's
+    // output epilogue, which needs G2 of that item's last chunk, i.e. the forwarding of H(g - 1)
+    for (int g = 0; g <= total; ++g) {
+      if (g >= 1) forward_hw(g - 1);
+      if (g < total) {
+        named_bar_sync(TM_NB_ZE + (g & 1), 32 * (TM_EPI_WARPS / 2 + 1));
+        if (elect_one_sync()) tm_arrive_leader(&z_empty[g & 1], is_leader);
+        __syncwarp();
+      }
     }
     if (elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
   } else if (warp >= TM_FWD_EPI0) {
     // ================================================================ epilogue warps (software-pipelined over chunks)
+    // Two groups of 8 warps work on ALTERNATE chunks (group = chunk parity = Z buffer = hidden-tile buffer): while one group
+    // runs the GELU of chunk g, the other one is in the hand-off phases of chunk g + 1 (barrier, TMEM load, tile write,
+    // fence), which cost ~900 cycles per chunk and were serial with the ~1250 cycles of math when all 16 warps moved in
+    // lock step.  A warp owns TMEM lane quarter warp % 4 and 32 of the chunk's 64 columns.
     const int q = warp & 3;                               // TMEM lane quarter
-    const int cq = (warp - TM_FWD_EPI0) >> 2;       // 16-column group of the 64-column chunk
+    const int gi = (warp - TM_FWD_EPI0) >> 3;             // group: chunks with g % 2 == gi
+    const int half = ((warp - TM_FWD_EPI0) >> 2) & 1;     // columns [32 half, 32 half + 32) of the chunk
+    const int cq = gi * 2 + half;                         // token-group phase of this warp in the output epilogue
     const int row = q * 32 + lane;                        // channel within the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
-    const bool tr = warp == TM_FWD_EPI0 && lane == 0;
-    int g = 0, it = 0;
-    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
-      for (int pos = 0; pos < NC; ++pos, ++g) {
+    const bool tr = (warp - TM_FWD_EPI0) % 8 == 0 && lane == 0;
+    const bool poller = ((warp - TM_FWD_EPI0) & 7) == 0;   // the one warp of the group that polls the mbarriers
+    int it = 0;                                           // item whose output epilogue this warp does next
+    for (int g = gi; ; g += 2) {
+      // ---- output epilogues of every item that ends before chunk g (or all remaining ones once g runs out)
+      const int item_of_g = g < total ? g / NC : my_items;
+      for (; it < item_of_g; ++it) {
+        // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
+        // tokens per tcgen05.ld; the [token][channel] transposition goes through the shared residual/output tile: 2-byte
+        // accesses at [n * 256 + ch * 2] -- the 32 lanes of a warp touch 64 consecutive bytes, conflict-free -- updated in
+        // place, then ONE TMA store per tile (issued by warp 3) writes it out and clips rows >= N / channels >= C.
+        mbar_wait2<0>(ro_full, it & 1, u_full, it & 1);
+        tc_fence_after();
+        const uint32_t ro_col = s_ro + row * 2;
+  #pragma unroll 1
+        for (int grp = cq; grp < ngrp + 4; grp += 4) {
+          const bool has = grp < ngrp;
+          const bool last = grp + 4 >= ngrp;                // this warp's last visit (possibly an empty one)
+          uint32_t v[16];
+          if (has) {
+            tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + grp * 16 + lane_addr, v);
+            tmem_ld_wait();                                 // (also completes a pending prefetch of the next item's chunk 0)
+          }
+          if (last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tm_arrive_leader(u_empty, is_leader);
+          }
+          if (has) {
+            const uint32_t a0 = ro_col + grp * 16 * 256;
+  #pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bv = lds_f4(s_b2 + (grp * 16 + 4 * i4) * 4);
+              const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+  #pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 4 * i4 + e;
+                unsigned short r;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a0 + i * 256) : "memory");
+                const float f = __uint_as_float(v[i]) + bb[e] + __uint_as_float(static_cast<uint32_t>(r) << 16);
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a0 + i * 256), "h"(static_cast<unsigned short>(bf16_bits(f))) : "memory");
+              }
+            }
+          }
+          if (last) break;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ro_done);
+      }
+      if (g >= total) break;
+      // ---- chunk g
+      {
+        const int pos = g - item_of_g * NC;
         const int j = tm_chunk(pos, rot, NC);
-        const int zb = g & 1;
-        const int hb = p.nhb == 2 ? zb : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        const bool live = cq * 16 < n1;
         if (tr) tm_stamp(p, 1, g, 0);
-        // ONE warp polls the mbarriers (Z(g) complete; hidden buffer free: G2 and the TMA store of its previous user done),
-        // the named barrier releases the other fifteen: an mbarrier operation costs a warp 100-200 cycles and the SM
-        // serialises them, 16 warps x 7 operations per chunk was the critical path of the first versions
-        if (warp == TM_FWD_EPI0)
-          mbar_wait2<0>(&z_full[zb], (g >> 1) & 1, &h_free[hb], ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1);
-        named_bar_sync(TM_NB_START, 32 * TM_EPI_WARPS);
+        // ONE warp of the group polls the mbarriers (Z(g) complete; hidden buffer free: G2 and the TMA store of its previous
+        // user done), the named barrier releases the other seven: an mbarrier operation costs a warp 100-200 cycles
+        if (poller) mbar_wait2<0>(&z_full[gi], (g >> 1) & 1, &h_free[gi], ((g >> 1) & 1) ^ 1);
+        named_bar_sync(TM_NB_START + gi, 32 * (TM_EPI_WARPS / 2));
         tc_fence_after();
         if (tr) tm_stamp(p, 1, g, 1);
-        uint32_t v[16];
-        if (live && !(p.flags & 16)) {
-          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, v);
+        uint32_t v[32];
+        const bool live0 = half * 32 < n1, live1 = half * 32 + 16 < n1;
+        if (!(p.flags & 16)) {
+          if (live0) tmem_ld_32x32b_x16(tmem_base + gi * TM_CH + half * 32 + lane_addr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          if (live1) tmem_ld_32x32b_x16(tmem_base + gi * TM_CH + half * 32 + 16 + lane_addr, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
           tmem_ld_wait();
         }
         tc_fence_before();
-        named_bar_arrive(TM_NB_ZE + zb, 32 * (TM_EPI_WARPS + 1));      // warp 2 forwards "Z(g) consumed" to the G1 issuer
+        named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
         if (tr) tm_stamp(p, 1, g, 2);
-        uint32_t o[8];
-        if (live && (p.flags & 1)) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-        } else if (live) {
+        for (int hh = 0; hh < 2; ++hh) {
+          if (!(hh ? live1 : live0)) continue;
+          uint32_t o[8];
+          if (p.flags & 1) {
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = lds_f4(s_b1 + (j * TM_CH + cq * 16 + 4 * e4) * 4);
-            f32x2 gl, dg;
-            gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4]) + bv.x, __uint_as_float(v[4 * e4 + 1]) + bv.y), gl, dg);
-            o[2 * e4] = pack_bf16x2_f2(gl);
-            gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4 + 2]) + bv.z, __uint_as_float(v[4 * e4 + 3]) + bv.w), gl, dg);
-            o[2 * e4 + 1] = pack_bf16x2_f2(gl);
-          }
-        }
-        if (tr) tm_stamp(p, 1, g, 3);
-        if (live && !(p.flags & 8)) tm_store_hidden_row(s_h + hb * TM_HTILE, row, cq, o);
-        fence_proxy_async_smem();
-        named_bar_arrive(TM_NB_HW + zb, 32 * (TM_EPI_WARPS + 1));      // warp 2 forwards "H(g) written", stores the tile
-        if (tr) tm_stamp(p, 1, g, 4);
-      }
-      // ---- output: U[b, n, ch] = U^T[ch, n] + b2[n] + x[b, n, ch].  This thread owns one channel (TMEM lane) and gets 16
-      // tokens per tcgen05.ld; the [token][channel] transposition goes through the shared residual/output tile: 2-byte
-      // accesses at [n * 256 + ch * 2] -- the 32 lanes of a warp touch 64 consecutive bytes, conflict-free -- updated in
-      // place, then ONE TMA store per tile (issued by warp 3) writes it out and clips rows >= N / channels >= C.
-      mbar_wait2<0>(ro_full, it & 1, u_full, it & 1);
-      tc_fence_after();
-      const uint32_t ro_col = s_ro + row * 2;
-#pragma unroll 1
-      for (int grp = cq; grp < ngrp + 4; grp += 4) {
-        const bool has = grp < ngrp;
-        const bool last = grp + 4 >= ngrp;                // this warp's last visit (possibly an empty one)
-        uint32_t v[16];
-        if (has) {
-          tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + grp * 16 + lane_addr, v);
-          tmem_ld_wait();                                 // (also completes a pending prefetch of the next item's chunk 0)
-        }
-        if (last) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tm_arrive_leader(u_empty, is_leader);
-        }
-        if (has) {
-          const uint32_t a0 = ro_col + grp * 16 * 256;
+            for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[16 * hh + 2 * e]), __uint_as_float(v[16 * hh + 2 * e + 1]));
+          } else {
 #pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 bv = lds_f4(s_b2 + (grp * 16 + 4 * i4) * 4);
-            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int i = 4 * i4 + e;
-              unsigned short r;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a0 + i * 256) : "memory");
-              const float f = __uint_as_float(v[i]) + bb[e] + __uint_as_float(static_cast<uint32_t>(r) << 16);
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(a0 + i * 256), "h"(static_cast<unsigned short>(bf16_bits(f))) : "memory");
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 bv = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 4 * e4) * 4);
+              f32x2 gl, dg;
+              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[16 * hh + 4 * e4]) + bv.x, __uint_as_float(v[16 * hh + 4 * e4 + 1]) + bv.y), gl, dg);
+              o[2 * e4] = pack_bf16x2_f2(gl);
+              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[16 * hh + 4 * e4 + 2]) + bv.z, __uint_as_float(v[16 * hh + 4 * e4 + 3]) + bv.w), gl, dg);
+              o[2 * e4 + 1] = pack_bf16x2_f2(gl);
             }
           }
+          if (!(p.flags & 8)) tm_store_hidden_row(s_h + gi * TM_HTILE, row, half * 2 + hh, o);
         }
-        if (last) break;
+        if (tr) tm_stamp(p, 1, g, 3);
+        fence_proxy_async_smem();
+        named_bar_arrive(TM_NB_HW + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "H(g) written", stores the tile
+        if (tr) tm_stamp(p, 1, g, 4);
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ro_done);
     }
   }
 
