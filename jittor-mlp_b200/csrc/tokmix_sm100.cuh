@@ -44,6 +44,7 @@ constexpr int TM_EPI_WARPS = 16;
 constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 16 epilogue warps
 constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_EPI_WARPS);   // 640
 constexpr int TM_NB_START = 1, TM_NB_ZE = 3, TM_NB_HW = 5;          // named (hardware) barrier ids (+ group), see the epilogue
+constexpr int TM_NB_BSTART = 1, TM_NB_BWR = 3, TM_NB_BZE = 5, TM_NB_BHW = 7;   // backward kernel's named barriers (+ group)
 constexpr int TM_BWD_EPI0 = 8;                                   // backward: 8 service warps + 16 epilogue warps
 constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 768
 constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
@@ -500,12 +501,11 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         named_bar_sync(TM_NB_START + gi, 32 * (TM_EPI_WARPS / 2));
         tc_fence_after();
         if (tr) tm_stamp(p, 1, g, 1);
-        uint32_t v[32];
+        uint32_t va[16], vb[16];
         const bool live0 = half * 32 < n1, live1 = half * 32 + 16 < n1;
         if (!(p.flags & 16)) {
-          if (live0) tmem_ld_32x32b_x16(tmem_base + gi * TM_CH + half * 32 + lane_addr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-          if (live1) tmem_ld_32x32b_x16(tmem_base + gi * TM_CH + half * 32 + 16 + lane_addr, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-          tmem_ld_wait();
+          if (live1) tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + half * 32 + lane_addr, tmem_base + gi * TM_CH + half * 32 + 16 + lane_addr, va, vb);
+          else if (live0) tmem_ld_x16_wait(tmem_base + gi * TM_CH + half * 32 + lane_addr, va);
         }
         tc_fence_before();
         named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
@@ -513,18 +513,19 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           if (!(hh ? live1 : live0)) continue;
+          const uint32_t (&v)[16] = hh ? vb : va;
           uint32_t o[8];
           if (p.flags & 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[16 * hh + 2 * e]), __uint_as_float(v[16 * hh + 2 * e + 1]));
+            for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
           } else {
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
               const float4 bv = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 4 * e4) * 4);
               f32x2 gl, dg;
-              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[16 * hh + 4 * e4]) + bv.x, __uint_as_float(v[16 * hh + 4 * e4 + 1]) + bv.y), gl, dg);
+              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4]) + bv.x, __uint_as_float(v[4 * e4 + 1]) + bv.y), gl, dg);
               o[2 * e4] = pack_bf16x2_f2(gl);
-              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[16 * hh + 4 * e4 + 2]) + bv.z, __uint_as_float(v[16 * hh + 4 * e4 + 3]) + bv.w), gl, dg);
+              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4 + 2]) + bv.z, __uint_as_float(v[4 * e4 + 3]) + bv.w), gl, dg);
               o[2 * e4 + 1] = pack_bf16x2_f2(gl);
             }
           }
@@ -574,7 +575,6 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   uint64_t* dx_full = bars + 2;     uint64_t* dx_empty = bars + 3;
   uint64_t* zd_full = bars + 4;     uint64_t* zd_empty = bars + 6;     // [2] each
   uint64_t* dz_full = bars + 8;     uint64_t* dz_free = bars + 10;     // dz_free: G3 + TMA store + column sums have read the tile
-  uint64_t* dz_done = bars + 12;
   uint64_t* w1_full = bars + 16;    uint64_t* w1_empty = bars + 20;    // up to 4 stages each
   uint64_t* w2_full = bars + 24;    uint64_t* w2_empty = bars + 28;
   uint64_t* w3_full = bars + 32;    uint64_t* w3_empty = bars + 36;
@@ -596,9 +596,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     mbar_init(in_full, 1); mbar_init(in_empty, 2);
     mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&zd_full[i], 2);  mbar_init(&zd_empty[i], 2 * TM_EPI_WARPS);
-      mbar_init(&dz_full[i], 2 * TM_EPI_WARPS);  mbar_init(&dz_free[i], 5);   // G3 commit + the four store / column-sum warps
-      mbar_init(&dz_done[i], TM_EPI_WARPS);
+      mbar_init(&zd_full[i], 2);  mbar_init(&zd_empty[i], 2);                // one forwarded arrival per CTA (warp 7)
+      mbar_init(&dz_full[i], 2);  mbar_init(&dz_free[i], 5);                 // G3 commit + the four store / column-sum warps
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1);
@@ -734,162 +733,167 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ================================================================ helper warps 4..7: warp 4 stores the dZ^T tile by TMA;
-    // all four sum the tile's columns over 32 channel rows each (d b1[m] = sum over (b, c) of dZ).  Lane l reads the
-    // 16-byte chunk (l & 7) -- eight hidden columns -- of rows r0 + (l >> 3) + 4 i: one LDS.128 per row, eight independent
-    // fp32 accumulators, then two shuffle steps fold the four row phases.
+    // ================================================================ helper warps 4..7.  All four wait (named barrier) until
+    // the 8 epilogue warps of group g & 1 have written dZ(g), then sum the tile's columns over 32 channel rows each
+    // (d b1[m] = sum over (b, c) of dZ): lane l reads the 16-byte chunk (l & 7) -- eight hidden columns -- of rows
+    // r0 + (l >> 3) + 4 i, eight independent fp32 accumulators, two shuffle steps fold the four row phases.  Warp 4 also
+    // forwards "dZ(g) written" to the G3 issuer (one arrival per CTA) and stores the tile by TMA; warp 7 also forwards
+    // "Z(g), dH(g) read" to the Z / dH issuers.
     const int r0 = (warp - 4) * 32;
     const uint32_t kc = lane & 7;
     const int rs = lane >> 3;
-    int g = 0;
-    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
-      const TokTile t = tm_tile(p, pair, cta_rank);
-      for (int pos = 0; pos < NC; ++pos, ++g) {
-        const int j = tm_chunk(pos, rot, NC);
-        const int hb = p.nhb == 2 ? (g & 1) : 0;
-        mbar_wait<32>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
-        if (warp == 4 && elect_one_sync()) {
-          if (t.valid && !(p.flags & 2)) {
-            tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
-            tma_store_commit();
-          }
+    auto consume_dz = [&](int g) {
+      const int gi = g & 1;
+      const int item = g / NC, j = tm_chunk(g - item * NC, rot, NC);
+      const TokTile t = tm_tile(p, cluster_id + item * num_clusters, cta_rank);
+      const int hb = p.nhb == 2 ? gi : 0;
+      named_bar_sync(TM_NB_BHW + gi, 32 * (TM_EPI_WARPS / 2 + 4));
+      if (warp == 4 && elect_one_sync()) {
+        tm_arrive_leader(&dz_full[hb], is_leader);
+        if (t.valid && !(p.flags & 2)) {
+          tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
+          tma_store_commit();
         }
-        __syncwarp();
-        if (t.valid && !(p.flags & 4)) {
-          const uint32_t tb = s_dz + hb * TM_HTILE;
-          float acc[8];
+      }
+      __syncwarp();
+      if (t.valid && !(p.flags & 4)) {
+        const uint32_t tb = s_dz + hb * TM_HTILE;
+        float acc[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = r0 + rs + 4 * i;
-            const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
-            acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
-            acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
-          }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-          }
-          if (rs == 0) {           // columns beyond Ds hold zeros (zero weights, zero-padded bias table)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&sdb[j * TM_CH + kc * 8 + e], acc[e]);
-          }
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + rs + 4 * i;
+          const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
+          acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
+          acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
         }
-        __syncwarp();
-        if (elect_one_sync()) {
-          if (warp == 4) tma_store_wait_read<0>();
-          mbar_arrive(&dz_free[hb]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
         }
+        if (rs == 0) {           // columns beyond Ds hold zeros (zero weights, zero-padded bias table)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) atomicAdd(&sdb[j * TM_CH + kc * 8 + e], acc[e]);
+        }
+      }
+      __syncwarp();
+      if (elect_one_sync()) {
+        if (warp == 4) tma_store_wait_read<0>();
+        mbar_arrive(&dz_free[hb]);
+      }
+      __syncwarp();
+    };
+    // dZ(g - 1) before "Z(g) read": same order (and the same reason) as in the forward kernel's forwarding warp
+    for (int g = 0; g <= total; ++g) {
+      if (g >= 1) consume_dz(g - 1);
+      if (g < total && warp == 7) {
+        named_bar_sync(TM_NB_BZE + (g & 1), 32 * (TM_EPI_WARPS / 2 + 1));
+        if (elect_one_sync()) tm_arrive_leader(&zd_empty[g & 1], is_leader);
         __syncwarp();
       }
     }
     if (warp == 4 && elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
   } else if (warp >= TM_BWD_EPI0) {
-    // ================================================================ epilogue warps (software-pipelined over chunks)
+    // ================================================================ epilogue warps: two groups of 8 on ALTERNATE chunks (see
+    // the forward kernel).  A warp owns TMEM lane quarter warp % 4 and 32 of the chunk's 64 columns, worked in two halves
+    // of 16 (Z and dH of a half = 32 registers; 24 warps leave 80 registers per thread).
     const int q = warp & 3;
-    const int cq = (warp - TM_BWD_EPI0) >> 2;
+    const int gi = (warp - TM_BWD_EPI0) >> 3;
+    const int half = ((warp - TM_BWD_EPI0) >> 2) & 1;
+    const int cq = gi * 2 + half;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
-    uint32_t vn[16];                                      // Z columns of the NEXT chunk (in flight or landed)
-    bool have = false;
-    int g = 0, it = 0;
-    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
-      const TokTile t = tm_tile(p, pair, cta_rank);
-      const int ch = t.c0 + row;
-      const bool ch_ok = t.valid && ch < p.C;
-      for (int pos = 0; pos < NC; ++pos, ++g) {
-        const int j = tm_chunk(pos, rot, NC);
-        const int zb = g & 1;
-        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        const bool live = cq * 16 < n1;
-        if (!have) {
-          mbar_wait(&zd_full[zb], (g >> 1) & 1);
-          tc_fence_after();
-          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vn);
-        }
-        tmem_ld_wait16(vn);
-        uint32_t vz[16], vh[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) vz[i] = vn[i];
-        // dH of this chunk (needed only after gelu' is known) and, if already complete, Z of the next chunk: both loads fly
-        // while the math runs
-        if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
-        const int hb = p.nhb == 2 ? zb : 0;
-        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
-        const uint32_t free_ok = mbar_test(&dz_free[hb], hph);
-        have = false;
-        if (g + 1 < total && mbar_test(&zd_full[zb ^ 1], ((g + 1) >> 1) & 1)) {
-          tc_fence_after();
-          if (!(p.flags & 16)) tmem_ld_32x32b_x16(tmem_base + (zb ^ 1) * TM_CH + cq * 16 + lane_addr, vn);
-          have = true;
-        }
-        f32x2 dgp[8];
-        if (live && !(p.flags & 1)) {
-#pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = lds_f4(s_b1 + (j * TM_CH + cq * 16 + 4 * e4) * 4);
-            f32x2 gl;
-            // rcp + ex2 form here: it is MUFU-bound at 1024 cycles per chunk and SM, the single-MUFU gradient form needs 22
-            // FMA-pipe lane operations per element = 1408 cycles (the forward value form needs 13 = 832)
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dgp[2 * e4]);
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dgp[2 * e4 + 1]);
+    const bool poller = ((warp - TM_BWD_EPI0) & 7) == 0;
+    int it = 0;
+    for (int g = gi; ; g += 2) {
+      const int item_of_g = g < total ? g / NC : my_items;
+      for (; it < item_of_g; ++it) {
+        // ---- output of item `it`: dXh[b, n, ch] = dXh^T[ch, n]   (this thread = one channel; 16 tokens per tcgen05.ld)
+        const TokTile t = tm_tile(p, cluster_id + it * num_clusters, cta_rank);
+        const int ch = t.c0 + row;
+        const bool ch_ok = t.valid && ch < p.C;
+        __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
+        mbar_wait(dx_full, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int grp = cq; grp < ngrp + 4; grp += 4) {
+          const bool has = grp < ngrp;
+          const bool last = grp + 4 >= ngrp;
+          uint32_t v[16];
+          if (has) {
+            tmem_ld_32x32b_x16(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);
+            tmem_ld_wait();
           }
+          if (last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
+          }
+          if (has && ch_ok) {
+            __nv_bfloat16* po = obase + (long long)(grp * 16) * p.C;
+            if (grp * 16 + 16 <= p.N) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i, po += p.C) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i, po += p.C)
+                if (grp * 16 + i < p.N) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+            }
+          }
+          if (last) break;
+        }
+      }
+      if (g >= total) break;
+      // ---- chunk g
+      const int j = tm_chunk(g - item_of_g * NC, rot, NC);
+      const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+      const int hb = p.nhb == 2 ? gi : 0;
+      if (poller) mbar_wait(&zd_full[gi], (g >> 1) & 1);               // Z(g) and dH(g) complete
+      named_bar_sync(TM_NB_BSTART + gi, 32 * (TM_EPI_WARPS / 2));
+      tc_fence_after();
+      uint32_t o[2][8];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int c0 = half * 32 + hh * 16;
+        const bool live = c0 < n1;
+        uint32_t vz[16], vh[16];
+        if (live && !(p.flags & 16))
+          tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + c0 + lane_addr, tmem_base + 2 * TM_CH + gi * TM_CH + c0 + lane_addr, vz, vh);
+        if (hh == 1) {                                                  // both halves are in registers: release the TMEM buffers
+          tc_fence_before();
+          named_bar_arrive(TM_NB_BZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));
+        }
+        if (!live) continue;
+        if (p.flags & 1) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[hh][e] = pack_bf16x2(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1]));
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dgp[e] = pack2(1.f, 1.f);
-        }
-        tmem_ld_wait16(vh);                               // dH(g) has landed (and so has a prefetched Z(g + 1))
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
-        uint32_t o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          o[e] = pack_bf16x2_f2(mul2(dgp[e], pack2(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1]))));
-        if (!free_ok) mbar_wait(&dz_free[hb], hph);       // G3, TMA store and column sums of the previous user are done
-        if (live && !(p.flags & 8)) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tm_arrive_leader(&dz_full[hb], is_leader);
-          mbar_arrive(&dz_done[hb]);
-        }
-      }
-      // ---- output: dXh[b, n, ch] = dXh^T[ch, n]
-      __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
-      mbar_wait(dx_full, it & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int grp = cq; grp < ngrp + 4; grp += 4) {
-        const bool has = grp < ngrp;
-        const bool last = grp + 4 >= ngrp;
-        uint32_t v[16];
-        if (has) {
-          tmem_ld_32x32b_x16(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);
-          tmem_ld_wait();
-        }
-        if (last) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
-        }
-        if (has && ch_ok) {
-          __nv_bfloat16* po = obase + (long long)(grp * 16) * p.C;
-          if (grp * 16 + 16 <= p.N) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i, po += p.C) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i, po += p.C)
-              if (grp * 16 + i < p.N) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const float4 bv = lds_f4(s_b1 + (j * TM_CH + c0 + 4 * e4) * 4);
+            f32x2 gl, d0, d1;
+            // rcp + ex2 form: MUFU-bound at 1024 cycles per chunk and SM; the single-MUFU gradient form needs 22 FMA-pipe
+            // lane operations per element = 1408 cycles (the forward value form needs 13 = 832)
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, d0);
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, d1);
+            o[hh][2 * e4] = pack_bf16x2_f2(mul2(d0, pack2(__uint_as_float(vh[4 * e4]), __uint_as_float(vh[4 * e4 + 1]))));
+            o[hh][2 * e4 + 1] = pack_bf16x2_f2(mul2(d1, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
           }
         }
-        if (last) break;
       }
+      // the dZ tile buffer must be free: G3, the TMA store and the column sums of its previous user are done
+      if (poller) mbar_wait(&dz_free[hb], ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1);
+      named_bar_sync(TM_NB_BWR + gi, 32 * (TM_EPI_WARPS / 2));
+      if (!(p.flags & 8)) {
+        if (half * 32 < n1) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, half * 2, o[0]);
+        if (half * 32 + 16 < n1) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, half * 2 + 1, o[1]);
+      }
+      fence_proxy_async_smem();
+      named_bar_arrive(TM_NB_BHW + gi, 32 * (TM_EPI_WARPS / 2 + 4));   // the helper warps take over
     }
   }
 
