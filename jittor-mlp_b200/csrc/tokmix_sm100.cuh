@@ -44,9 +44,8 @@ constexpr int TM_EPI_WARPS = 16;
 constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 16 epilogue warps
 constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_EPI_WARPS);   // 640
 constexpr int TM_NB_START = 1, TM_NB_ZE = 3, TM_NB_HW = 5;          // named (hardware) barrier ids (+ group), see the epilogue
-constexpr int TM_NB_BSTART = 1, TM_NB_BWR = 3, TM_NB_BZE = 5, TM_NB_BHW = 7;   // backward kernel's named barriers (+ group)
-constexpr int TM_BWD_EPI0 = 8;                                   // backward: 8 service warps + 16 epilogue warps
-constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 768
+constexpr int TM_BWD_EPI0 = 4;                                   // backward: 4 service warps + 16 epilogue warps
+constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 640
 constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
 constexpr int TM_MAX_DS = 1024;
 constexpr int TM_BAR_BYTES = 1024;
@@ -548,7 +547,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Backward (data-gradient chain).  SMEM: [barriers][Xh^T tile][dU^T tile][W1 ring][W2^T ring][W1^T ring][dZ tile(s)][b1][d b1 sums]
+// Backward (data-gradient chain).  SMEM: [barriers][Xh^T tile][dU^T tile][W1 ring][W2^T ring][W1^T ring][dZ tiles 2 x 16 KB][b1]
 // TMEM: Z double buffer [0, 128), dH double buffer [128, 256), dXh accumulator [256, 256 + NT).
 // Per hidden chunk: G1 Z^T = Xh^T * W1chunk^T (recomputed, never stored), G2 dH^T = dU^T * W2[:, chunk],
 // epilogue dZ^T = dH^T .* gelu'(Z^T + b1) -> bf16 SMEM tile (+ TMA store into dZ^T [B, C, Ds] for the weight gradient),
@@ -574,7 +573,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   uint64_t* in_full = bars + 0;     uint64_t* in_empty = bars + 1;
   uint64_t* dx_full = bars + 2;     uint64_t* dx_empty = bars + 3;
   uint64_t* zd_full = bars + 4;     uint64_t* zd_empty = bars + 6;     // [2] each
-  uint64_t* dz_full = bars + 8;     uint64_t* dz_free = bars + 10;     // dz_free: G3 + TMA store + column sums have read the tile
+  uint64_t* dz_full = bars + 8;     uint64_t* dz_empty = bars + 10;
+  uint64_t* dz_done = bars + 12;    uint64_t* dzs_empty = bars + 14;
   uint64_t* w1_full = bars + 16;    uint64_t* w1_empty = bars + 20;    // up to 4 stages each
   uint64_t* w2_full = bars + 24;    uint64_t* w2_empty = bars + 28;
   uint64_t* w3_full = bars + 32;    uint64_t* w3_empty = bars + 36;
@@ -586,18 +586,18 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t s_w2 = s_w1 + p.s_wa * p.wa_stage;
   const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
   const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
-  const uint32_t s_b1 = s_dz + p.nhb * TM_HTILE;
-  float* sb1 = reinterpret_cast<float*>(smem + (s_b1 - s_base));
+  float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + p.nhb * TM_HTILE);
   float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
-    mbar_init(in_full, 1); mbar_init(in_empty, 2);
+    mbar_init(in_full, 1); mbar_init(in_empty, 1);
     mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&zd_full[i], 2);  mbar_init(&zd_empty[i], 2);                // one forwarded arrival per CTA (warp 7)
-      mbar_init(&dz_full[i], 2);  mbar_init(&dz_free[i], 5);                 // G3 commit + the four store / column-sum warps
+      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * TM_EPI_WARPS);
+      mbar_init(&dz_full[i], 2 * TM_EPI_WARPS);  mbar_init(&dz_empty[i], 1);
+      mbar_init(&dz_done[i], TM_EPI_WARPS);      mbar_init(&dzs_empty[i], 2);   // store warp + column-sum warp
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1);
@@ -617,9 +617,6 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t tmem_base = *tmem_slot;
   const int NC = p.n_chunks;
   const int rot = (p.flags & 64) ? 0 : cluster_id % NC;
-  int my_items = 0;
-  for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
-  const int total = my_items * NC;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -632,15 +629,20 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       const int j = tm_chunk(pos, rot, NC);
       const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
       const int row = j * TM_CH + cta_rank * (n1 >> 1);
-      mbar_wait2<128>(&w1_empty[sa], pa ^ 1, &w2_empty[sa], pa ^ 1);
+      mbar_wait<128>(&w1_empty[sa], pa ^ 1);
       if (elect_one_sync()) {
-        if (p.flags & 32) { if (is_leader) { mbar_arrive(&w1_full[sa]); mbar_arrive(&w2_full[sa]); } }
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&w1_full[sa]); }
         else {
-          if (is_leader) {
-            mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
-            mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
-          }
+          if (is_leader) mbar_arrive_expect_tx(&w1_full[sa], 2 * p.wa_stage);
           tm_load_wa(s_w1 + sa * p.wa_stage, mW1, leader_cta_addr(smem_u32(&w1_full[sa])), row, p);
+        }
+      }
+      __syncwarp();
+      mbar_wait<128>(&w2_empty[sa], pa ^ 1);
+      if (elect_one_sync()) {
+        if (p.flags & 32) { if (is_leader) mbar_arrive(&w2_full[sa]); }
+        else {
+          if (is_leader) mbar_arrive_expect_tx(&w2_full[sa], 2 * p.wa_stage);
           tm_load_wa(s_w2 + sa * p.wa_stage, mW2T, leader_cta_addr(smem_u32(&w2_full[sa])), row, p);
         }
       }
@@ -680,220 +682,212 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       if (NC >= 2) load_w3(NC - 2);
       load_w3(NC - 1);
     }
-  } else if (warp == 1 || warp == 2) {
-    // ================================================================ issuers (leader CTA): warp 1 of Z^T = Xh^T W1chunk^T,
-    // warp 2 of dH^T = dU^T W2[:, chunk].  zd_full collects both commits (count 2), either warp frees its own ring stage;
-    // the activation tiles are released by the later of the two last commits of an item (in_empty, count 2).
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA)
     if (is_leader) {
-      const bool zrole = warp == 1;
-      uint64_t* wfull = zrole ? w1_full : w2_full;
-      uint64_t* wempty = zrole ? w1_empty : w2_empty;
-      const uint32_t s_act = zrole ? s_xt : s_dut, s_w = zrole ? s_w1 : s_w2;
-      const uint32_t d_off = zrole ? 0 : 2 * TM_CH;
-      uint32_t sa = 0, pa = 0;
-      int j1 = 0, it1 = 0;
-      for (int t1 = 0; t1 < total; ++t1) {
+      const uint32_t idesc_g3 = umma_idesc_bf16(256, p.NT, 0, 0);
+      int my_items = 0;
+      for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
+      const int total = my_items * NC;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+      int j1 = 0, it1 = 0, j3 = 0, it3 = 0;
+      int t1 = 0, t3 = 0;
+      auto do_g12 = [&]() {       // ---- Z^T = Xh^T * W1chunk^T and dH^T = dU^T * W2[:, chunk]
         const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
-        const int zb = t1 & 1;
         if (j1 == 0) mbar_wait<32>(in_full, it1 & 1);
-        mbar_wait2<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1, &wfull[sa], pa);
+        const int zb = t1 & 1;
+        mbar_wait<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        mbar_wait<32>(&w1_full[sa], pa);
         tc_fence_after();
         if (elect_one_sync()) {
-          tm_mma_over_tokens(tmem_base + d_off + zb * TM_CH, s_act, s_w + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
-          umma_commit_2cta_mc(&wempty[sa]);
+          tm_mma_over_tokens(tmem_base + zb * TM_CH, s_xt, s_w1 + sa * p.wa_stage, umma_idesc_bf16(256, n1, 1, 0), p);
+          umma_commit_2cta_mc(&w1_empty[sa]);
+        }
+        __syncwarp();
+        mbar_wait<32>(&w2_full[sa], pa);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          tm_mma_over_tokens(tmem_base + 2 * TM_CH + zb * TM_CH, s_dut, s_w2 + sa * p.wa_stage,
+                             umma_idesc_bf16(256, n1, 1, 0), p);
+          umma_commit_2cta_mc(&w2_empty[sa]);
           umma_commit_2cta_mc(&zd_full[zb]);
           if (j1 == NC - 1) umma_commit_2cta_mc(in_empty);
         }
         __syncwarp();
         if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
         if (++j1 == NC) { j1 = 0; ++it1; }
-      }
-    }
-  } else if (warp == 3) {
-    // ================================================================ issuer of G3: dXh^T (+)= dZ^T * W1[chunk, :]
-    if (is_leader) {
-      const uint32_t idesc_g3 = umma_idesc_bf16(256, p.NT, 0, 0);
-      uint32_t sb = 0, pb = 0;
-      int j3 = 0, it3 = 0;
-      for (int t3 = 0; t3 < total; ++t3) {
+        ++t1;
+      };
+      auto do_g3 = [&]() {        // ---- dXh^T (+)= dZ^T * W1[chunk, :]
         const int hb = p.nhb == 2 ? (t3 & 1) : 0;
+        mbar_wait<32>(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1);
+        mbar_wait<32>(&w3_full[sb], pb);
         if (j3 == 0) mbar_wait<32>(dx_empty, (it3 & 1) ^ 1);
-        mbar_wait2<32>(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1, &w3_full[sb], pb);
         tc_fence_after();
         if (elect_one_sync()) {
           const int ksteps = (tm_chunk(j3, rot, NC) == NC - 1) ? (p.last_n1 >> 4) : (TM_CH >> 4);
           tm_mma_over_hidden(tmem_base + 4 * TM_CH, s_dz + hb * TM_HTILE, s_w3 + sb * p.wb_stage, idesc_g3, ksteps, j3 == 0);
           umma_commit_2cta_mc(&w3_empty[sb]);
-          umma_commit_2cta_mc(&dz_free[hb]);
+          umma_commit_2cta_mc(&dz_empty[hb]);
           if (j3 == NC - 1) umma_commit_2cta_mc(dx_full);
         }
         __syncwarp();
         if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
         if (++j3 == NC) { j3 = 0; ++it3; }
+        ++t3;
+      };
+      for (int t = 0; t < total + 2; ++t) {      // same issue order as the forward kernel
+        const bool g1 = t < total, g3 = t >= 2;
+        const bool g3_first = g3 && (!g1 || j1 < 2);
+        if (g3 && g3_first) do_g3();
+        if (g1) do_g12();
+        if (g3 && !g3_first) do_g3();
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================================================ helper warps 4..7.  All four wait (named barrier) until
-    // the 8 epilogue warps of group g & 1 have written dZ(g), then sum the tile's columns over 32 channel rows each
-    // (d b1[m] = sum over (b, c) of dZ): lane l reads the 16-byte chunk (l & 7) -- eight hidden columns -- of rows
-    // r0 + (l >> 3) + 4 i, eight independent fp32 accumulators, two shuffle steps fold the four row phases.  Warp 4 also
-    // forwards "dZ(g) written" to the G3 issuer (one arrival per CTA) and stores the tile by TMA; warp 7 also forwards
-    // "Z(g), dH(g) read" to the Z / dH issuers.
-    const int r0 = (warp - 4) * 32;
-    const uint32_t kc = lane & 7;
-    const int rs = lane >> 3;
-    auto consume_dz = [&](int g) {
-      const int gi = g & 1;
-      const int item = g / NC, j = tm_chunk(g - item * NC, rot, NC);
-      const TokTile t = tm_tile(p, cluster_id + item * num_clusters, cta_rank);
-      const int hb = p.nhb == 2 ? gi : 0;
-      named_bar_sync(TM_NB_BHW + gi, 32 * (TM_EPI_WARPS / 2 + 4));
-      if (warp == 4 && elect_one_sync()) {
-        tm_arrive_leader(&dz_full[hb], is_leader);
-        if (t.valid && !(p.flags & 2)) {
-          tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
-          tma_store_commit();
+  } else if (warp == 2 || warp == 3) {
+    // ================================================================ helper warps: warp 2 stores the dZ^T tile by TMA;
+    // both sum the tile's columns over their 64 channel rows (d b1[m] = sum over (b, c) of dZ): lane l owns hidden
+    // columns 2l, 2l+1 of the chunk and reads one 32-bit word per row (the 16-byte chunk index is un-swizzled per row).
+    const int r0 = (warp - 2) * 64;
+    const uint32_t kc = lane & 7;            // 16-byte chunk = eight hidden columns
+    const int rs = lane >> 3;                // row phase: rows r0 + rs + 4 i
+    int g = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      for (int pos = 0; pos < NC; ++pos, ++g) {
+        const int j = tm_chunk(pos, rot, NC);
+        const int hb = p.nhb == 2 ? (g & 1) : 0;
+        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+        mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        if (warp == 2 && elect_one_sync()) {
+          if (t.valid && !(p.flags & 2)) {
+            tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
+            tma_store_commit();
+          }
         }
-      }
-      __syncwarp();
-      if (t.valid && !(p.flags & 4)) {
-        const uint32_t tb = s_dz + hb * TM_HTILE;
-        float acc[8];
+        __syncwarp();
+        if (t.valid && !(p.flags & 4)) {
+          // one LDS.128 per row, eight independent fp32 accumulators, two shuffle steps fold the four row phases (the first
+          // version -- one 32-bit word per row and lane, two serial 64-term chains -- cost 60 us of the kernel's 316: with a
+          // single dZ buffer the epilogue's next write waits for these sums)
+          const uint32_t tb = s_dz + hb * TM_HTILE;
+          float acc[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 16; ++i) {
+            const int r = r0 + rs + 4 * i;
+            const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
+            acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
+            acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
+          }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + rs + 4 * i;
-          const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
-          acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
-          acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
+          for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+          }
+          if (rs == 0) {           // columns beyond Ds hold stale or zero data and are never flushed
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&sdb[j * TM_CH + kc * 8 + e], acc[e]);
+          }
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-          acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+        __syncwarp();
+        if (elect_one_sync()) {
+          if (warp == 2) tma_store_wait_read<0>();
+          mbar_arrive(&dzs_empty[hb]);
         }
-        if (rs == 0) {           // columns beyond Ds hold zeros (zero weights, zero-padded bias table)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) atomicAdd(&sdb[j * TM_CH + kc * 8 + e], acc[e]);
-        }
-      }
-      __syncwarp();
-      if (elect_one_sync()) {
-        if (warp == 4) tma_store_wait_read<0>();
-        mbar_arrive(&dz_free[hb]);
-      }
-      __syncwarp();
-    };
-    // dZ(g - 1) before "Z(g) read": same order (and the same reason) as in the forward kernel's forwarding warp
-    for (int g = 0; g <= total; ++g) {
-      if (g >= 1) consume_dz(g - 1);
-      if (g < total && warp == 7) {
-        named_bar_sync(TM_NB_BZE + (g & 1), 32 * (TM_EPI_WARPS / 2 + 1));
-        if (elect_one_sync()) tm_arrive_leader(&zd_empty[g & 1], is_leader);
         __syncwarp();
       }
     }
-    if (warp == 4 && elect_one_sync()) tma_store_wait_all<0>();
+    if (warp == 2 && elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
   } else if (warp >= TM_BWD_EPI0) {
-    // ================================================================ epilogue warps: two groups of 8 on ALTERNATE chunks (see
-    // the forward kernel).  A warp owns TMEM lane quarter warp % 4 and 32 of the chunk's 64 columns, worked in two halves
-    // of 16 (Z and dH of a half = 32 registers; 24 warps leave 80 registers per thread).
+    // ================================================================ epilogue warps
     const int q = warp & 3;
-    const int gi = (warp - TM_BWD_EPI0) >> 3;
-    const int half = ((warp - TM_BWD_EPI0) >> 2) & 1;
-    const int cq = gi * 2 + half;
+    const int cq = (warp - TM_BWD_EPI0) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
-    const bool poller = ((warp - TM_BWD_EPI0) & 7) == 0;
-    int it = 0;
-    for (int g = gi; ; g += 2) {
-      const int item_of_g = g < total ? g / NC : my_items;
-      for (; it < item_of_g; ++it) {
-        // ---- output of item `it`: dXh[b, n, ch] = dXh^T[ch, n]   (this thread = one channel; 16 tokens per tcgen05.ld)
-        const TokTile t = tm_tile(p, cluster_id + it * num_clusters, cta_rank);
-        const int ch = t.c0 + row;
-        const bool ch_ok = t.valid && ch < p.C;
-        __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
-        mbar_wait(dx_full, it & 1);
+    int g = 0, it = 0;
+    for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters, ++it) {
+      const TokTile t = tm_tile(p, pair, cta_rank);
+      const int ch = t.c0 + row;
+      const bool ch_ok = t.valid && ch < p.C;
+      for (int pos = 0; pos < NC; ++pos, ++g) {
+        const int j = tm_chunk(pos, rot, NC);
+        const int zb = g & 1;
+        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+        const bool live = cq * 16 < n1;
+        mbar_wait(&zd_full[zb], (g >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int grp = cq; grp < ngrp + 4; grp += 4) {
-          const bool has = grp < ngrp;
-          const bool last = grp + 4 >= ngrp;
-          uint32_t v[16];
-          if (has) {
-            tmem_ld_32x32b_x16(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);
-            tmem_ld_wait();
-          }
-          if (last) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
-          }
-          if (has && ch_ok) {
-            __nv_bfloat16* po = obase + (long long)(grp * 16) * p.C;
-            if (grp * 16 + 16 <= p.N) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i, po += p.C) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i, po += p.C)
-                if (grp * 16 + i < p.N) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
-            }
-          }
-          if (last) break;
-        }
-      }
-      if (g >= total) break;
-      // ---- chunk g
-      const int j = tm_chunk(g - item_of_g * NC, rot, NC);
-      const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-      const int hb = p.nhb == 2 ? gi : 0;
-      if (poller) mbar_wait(&zd_full[gi], (g >> 1) & 1);               // Z(g) and dH(g) complete
-      named_bar_sync(TM_NB_BSTART + gi, 32 * (TM_EPI_WARPS / 2));
-      tc_fence_after();
-      uint32_t o[2][8];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int c0 = half * 32 + hh * 16;
-        const bool live = c0 < n1;
         uint32_t vz[16], vh[16];
-        if (live && !(p.flags & 16))
-          tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + c0 + lane_addr, tmem_base + 2 * TM_CH + gi * TM_CH + c0 + lane_addr, vz, vh);
-        if (hh == 1) {                                                  // both halves are in registers: release the TMEM buffers
-          tc_fence_before();
-          named_bar_arrive(TM_NB_BZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));
+        if (live && !(p.flags & 16)) {
+          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vz);
+          tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
+          tmem_ld_wait();
         }
-        if (!live) continue;
-        if (p.flags & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
+        uint32_t o[8];
+        if (live && (p.flags & 1)) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[hh][e] = pack_bf16x2(__uint_as_float(vh[2 * e]), __uint_as_float(vh[2 * e + 1]));
-        } else {
+          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(vz[2 * e]) + __uint_as_float(vh[2 * e]), __uint_as_float(vz[2 * e + 1]) + __uint_as_float(vh[2 * e + 1]));
+        } else if (live) {
+          const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
 #pragma unroll
           for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = lds_f4(s_b1 + (j * TM_CH + c0 + 4 * e4) * 4);
-            f32x2 gl, d0, d1;
-            // rcp + ex2 form: MUFU-bound at 1024 cycles per chunk and SM; the single-MUFU gradient form needs 22 FMA-pipe
-            // lane operations per element = 1408 cycles (the forward value form needs 13 = 832)
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, d0);
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, d1);
-            o[hh][2 * e4] = pack_bf16x2_f2(mul2(d0, pack2(__uint_as_float(vh[4 * e4]), __uint_as_float(vh[4 * e4 + 1]))));
-            o[hh][2 * e4 + 1] = pack_bf16x2_f2(mul2(d1, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
+            const float4 bv = bp[e4];
+            f32x2 gl, dg;
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dg);
+            o[2 * e4] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4]), __uint_as_float(vh[4 * e4 + 1]))));
+            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dg);
+            o[2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
           }
         }
+        const int hb = p.nhb == 2 ? zb : 0;                        // dZ tile buffer (single-buffered when two do not fit)
+        const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        mbar_wait(&dz_empty[hb], hph);                             // G3 of the previous user of this buffer has read it
+        mbar_wait(&dzs_empty[hb], hph);                            // ... and so have its TMA store and column sums
+        if (live && !(p.flags & 8)) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tm_arrive_leader(&dz_full[hb], is_leader);
+          mbar_arrive(&dz_done[hb]);
+        }
       }
-      // the dZ tile buffer must be free: G3, the TMA store and the column sums of its previous user are done
-      if (poller) mbar_wait(&dz_free[hb], ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1);
-      named_bar_sync(TM_NB_BWR + gi, 32 * (TM_EPI_WARPS / 2));
-      if (!(p.flags & 8)) {
-        if (half * 32 < n1) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, half * 2, o[0]);
-        if (half * 32 + 16 < n1) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, half * 2 + 1, o[1]);
+      // ---- output: dXh[b, n, ch] = dXh^T[ch, n]
+      __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
+      mbar_wait(dx_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int grp = cq; grp < ngrp + 4; grp += 4) {
+        const bool has = grp < ngrp;
+        const bool last = grp + 4 >= ngrp;
+        uint32_t v[16];
+        if (has) {
+          tmem_ld_32x32b_x16(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);
+          tmem_ld_wait();
+        }
+        if (last) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
+        }
+        if (has && ch_ok) {
+          __nv_bfloat16* po = obase + (long long)(grp * 16) * p.C;
+          if (grp * 16 + 16 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i, po += p.C) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i, po += p.C)
+              if (grp * 16 + i < p.N) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+          }
+        }
+        if (last) break;
       }
-      fence_proxy_async_smem();
-      named_bar_arrive(TM_NB_BHW + gi, 32 * (TM_EPI_WARPS / 2 + 4));   // the helper warps take over
     }
   }
 
