@@ -19,6 +19,7 @@ for _ in range(reps):
     m.zero_grad(set_to_none=True)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.cudart().cudaProfilerStart()          # ncu --profile-from-start off: exactly `reps` blocks are captured
 e0.record()
 for _ in range(reps):
     y = m(x)
@@ -26,4 +27,5 @@ for _ in range(reps):
     m.zero_grad(set_to_none=True)
 e1.record()
 torch.cuda.synchronize()
-print(f"block fwd+bwd: {e0.elapsed_time(e1) / reps:.3f} ms  (roofline 1.239 ms, 65% target 1.91 ms)")
+torch.cuda.cudart().cudaProfilerStop()
+print(f"block fwd+bwd: {e0.elapsed_time(e1) / reps:.3f} ms  (tensor roofline 1.277 ms at the measured sustained peak)")
