@@ -42,7 +42,7 @@ enum {
 /* Library / device introspection.  VMLP_ABI_VERSION changes whenever a struct or a signature below changes; a binding
  * checks it together with vmlp_abi_struct_bytes (0 operand, 1 gemm_args, 2 mixer_params, 3 mixer_saved, 4 hire_dims)
  * before the first call.  vmlp_source_hash: digest of the sources the library was built from (stale-build detection). */
-#define VMLP_ABI_VERSION 2
+#define VMLP_ABI_VERSION 3
 int vmlp_abi_version(void);
 const char* vmlp_source_hash(void);
 int vmlp_abi_struct_bytes(int32_t which);
@@ -179,22 +179,57 @@ int vmlp_bn_bwd_coef(const float* sdy, const float* sdya, const void* gamma, con
                      float* A, float* Bq, float* Cc, float* dgamma, float* dbeta, int64_t R, int32_t C,
                      vmlp_stream_t stream);
 
-/* S2-MLPv2 split attention (s2_mlp_v2.py:31-69).  t: [B,H,W,3C] (mlp1 output); branch k = t[..., kC:(k+1)C] read through
- * spatial_shift1 (k=0), spatial_shift2 (k=1) or unshifted (k=2) as load-time clamp offsets.
+/* Split attention of S2-MLPv2 (s2_mlp_v2.py:31-69) and Vision Permutator (vip.py:37-57).  t: [B,H,W,3C]; branch k =
+ * t[..., kC:(k+1)C].  plain = 0: S2-MLPv2 -- branch 0 / 1 are read through spatial_shift1 / spatial_shift2 as load-time
+ * clamp offsets, branch 2 unshifted.  plain = 1: ViP -- three unshifted branches (the stacked H / W / C permute-MLP outputs).
  *   sum      : a_f32[b,c] += sum_pos (x_0 + x_1 + x_2)                        (caller zero-fills a_f32)
  *   combine  : out[b,pos,c] = sum_k softmax_k(hat[b,:,c]) * x_k[b,pos,c]      (hat: bf16 [B,3C])
  *   combine_bwd : dt (bf16 [B,H,W,3C]) and dhat (bf16 [B,3C]) from dout; dbar_f32 is a zero-filled fp32 [B,3C] scratch
  *   sum_bwd  : dt from da (bf16 [B,C]) */
-int vmlp_s2v2_sum(const void* t, float* a_f32, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
+int vmlp_s2v2_sum(const void* t, float* a_f32, int32_t B, int32_t H, int32_t W, int32_t C, int32_t plain,
+                  vmlp_stream_t stream);
 int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
-                      vmlp_stream_t stream);
+                      int32_t plain, vmlp_stream_t stream);
 int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, float* dbar_f32, void* dhat, void* dt,
-                          int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
-int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream);
+                          int32_t B, int32_t H, int32_t W, int32_t C, int32_t plain, vmlp_stream_t stream);
+int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, int32_t plain,
+                      vmlp_stream_t stream);
 /* the whole split-attention backward w.r.t. t in one write: dt = softmax_k(hat) * adjoint_k(dout) + da * read_count_k.
    Pair with vmlp_s2v2_combine_bwd(..., dt = NULL, ...), which then only produces dbar / dhat. */
 int vmlp_s2v2_dt_fused(const void* dout, const void* hat, const void* da, void* dt, int32_t B, int32_t H, int32_t W,
-                       int32_t C, vmlp_stream_t stream);
+                       int32_t C, int32_t plain, vmlp_stream_t stream);
+
+/* Strided 5-D copy with a contiguous inner run: out[i0*os0 + i1*os1 + i2*os2 + i3*os3 + j] (+)= in[i0*is0 + ... + j],
+ * 0 <= j < dims[4].  Vision Permutator's `b h w (c s) -> b w c (h s)` / `b h w (c s) -> b h c (w s)` rearrangements and
+ * their inverses (vip.py:68-70,73-75) are this copy with the inner run = one segment; the destination may be a channel
+ * slot of a wider buffer (row stride in os).  dims[4] and every stride must be multiples of 8 elements, both pointers
+ * 16-byte aligned, dims[1]*dims[2]*dims[3]*dims[4]/8 < 2^22.  accumulate != 0: out += in (bf16, fp32 add). */
+int vmlp_permute5(const void* in, void* out, const int32_t dims[5], const int64_t in_strides[4],
+                  const int64_t out_strides[4], int32_t accumulate, vmlp_stream_t stream);
+
+/* Multi-tensor optimizer step (the reference has no optimizer -- compare.py:141-145 only
+ * interchanges state_dicts -- so the semantics are torch.optim.AdamW / torch.optim.SGD(momentum) on fp32 master weights).
+ * table: DEVICE array of n_chunks entries, each a run of <= 32768 elements of one bf16 parameter tensor and its bf16
+ * gradient; state_off = offset of the run in the flat fp32 buffers master / mom / var (var unused for SGD).
+ * One launch updates master, moments and the bf16 parameter copy of every run. */
+typedef struct {
+  void* param;           /* bf16, updated in place */
+  const void* grad;      /* bf16 */
+  int64_t state_off;
+  int32_t n;
+  int32_t reserved;
+} vmlp_optim_chunk;
+typedef struct {
+  int32_t kind;          /* 0 = AdamW, 1 = SGD with momentum */
+  int32_t first_step;    /* SGD: momentum buffer := gradient on the first step (torch.optim.SGD) */
+  float lr, beta1, beta2, eps, weight_decay;
+  float bias_c1;         /* 1 - beta1^t */
+  float bias_c2_sqrt;    /* sqrt(1 - beta2^t) */
+  float grad_scale;      /* gradients are multiplied by this first (1/world for SUM all-reduces, loss-scale inverse) */
+  float momentum;
+} vmlp_optim_hyper;
+int vmlp_optim_step(const vmlp_optim_chunk* table_dev, int32_t n_chunks, float* master, float* mom, float* var,
+                    const vmlp_optim_hyper* hyper, vmlp_stream_t stream);
 
 /* Hire-MLP region rearrangement (hire_mlp.py:44-152) as load-time index arithmetic on channels-last tensors.
  * Padding is circular with Hp = H + (h - H % h), Wp = W + (w - W % w); step = cross_region_step or 0.

@@ -8,4 +8,6 @@ from .s2_mlp import S2MLPv1, S2MLPv1_deep, S2MLPv1_wide, S2MLPv2  # noqa: F401
 from .as_mlp import AS_MLP  # noqa: F401
 from .hire_mlp import HireMLP  # noqa: F401
 from .conv_mixer import ConvMixer  # noqa: F401
+from .vip import ViP  # noqa: F401
+from .optim import FusedAdamW, FusedSGD  # noqa: F401
 from .graph import GraphedStep  # noqa: F401

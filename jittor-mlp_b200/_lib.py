@@ -28,7 +28,7 @@ def _sources():
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
 
 
-ABI_VERSION = 2          # == VMLP_ABI_VERSION in include/vmlp_b200.h
+ABI_VERSION = 3          # == VMLP_ABI_VERSION in include/vmlp_b200.h
 
 
 def source_hash():
@@ -102,6 +102,15 @@ class HireDims(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in ("B", "H", "W", "C", "h", "w", "step_h", "step_w")]
 
 
+class OptimChunk(ctypes.Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state_off", c_int64), ("n", c_int32), ("reserved", c_int32)]
+
+
+class OptimHyper(ctypes.Structure):
+    _fields_ = [("kind", c_int32), ("first_step", c_int32)] + [(n, ctypes.c_float) for n in (
+        "lr", "beta1", "beta2", "eps", "weight_decay", "bias_c1", "bias_c2_sqrt", "grad_scale", "momentum")]
+
+
 class MixerSaved(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("xhat1", "z1", "h1", "u", "xhat2", "z2", "h2", "stats", "w1t_pad")]
 
@@ -150,12 +159,15 @@ SYMBOLS = [
                                    c_void_p, c_void_p, c_int64, c_float, c_float, c_int32, c_void_p]),
     ("vmlp_bn_bwd_coef", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
-    ("vmlp_s2v2_sum", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
-    ("vmlp_s2v2_combine", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_sum", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_combine", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_s2v2_combine_bwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
-                                        c_int32, c_int32, c_void_p]),
-    ("vmlp_s2v2_sum_bwd", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
-    ("vmlp_s2v2_dt_fused", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+                                        c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_sum_bwd", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_s2v2_dt_fused", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_void_p]),
+    ("vmlp_permute5", c_int32, [c_void_p, c_void_p, _P(c_int32), _P(c_int64), _P(c_int64), c_int32, c_void_p]),
+    ("vmlp_optim_step", c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, _P(OptimHyper), c_void_p]),
     ("vmlp_hire_build", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
     ("vmlp_hire_build_adj", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
     ("vmlp_hire_combine", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
@@ -214,7 +226,7 @@ def lib():
         fn.argtypes = argtypes
     if handle.vmlp_abi_version() != ABI_VERSION:
         raise VmlpError(f"{LIB_PATH}: ABI version {handle.vmlp_abi_version()} != binding {ABI_VERSION}")
-    for which, struct in enumerate((Operand, GemmArgs, MixerParams, MixerSaved, HireDims)):
+    for which, struct in enumerate((Operand, GemmArgs, MixerParams, MixerSaved, HireDims, OptimChunk, OptimHyper)):
         if handle.vmlp_abi_struct_bytes(which) != ctypes.sizeof(struct):
             raise VmlpError(f"{LIB_PATH}: sizeof({struct.__name__}) = {ctypes.sizeof(struct)} here, "
                             f"{handle.vmlp_abi_struct_bytes(which)} in the library")

@@ -6,6 +6,7 @@
 #include "spatial.cuh"
 #include "spatial2.cuh"
 #include "tokmix_sm100.cuh"
+#include "aux_sm100.cuh"
 
 #include <cstdarg>
 #include <cstdlib>
@@ -602,6 +603,8 @@ int vmlp_abi_struct_bytes(int32_t which) {
     case 2: return (int)sizeof(vmlp_mixer_params);
     case 3: return (int)sizeof(vmlp_mixer_saved);
     case 4: return (int)sizeof(vmlp_hire_dims);
+    case 5: return (int)sizeof(vmlp_optim_chunk);
+    case 6: return (int)sizeof(vmlp_optim_hyper);
   }
   return -1;
 }
@@ -949,35 +952,35 @@ static dim3 s2v2_reduce_grid(int B, int H, int W, int C) {
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)B);
 }
-int vmlp_s2v2_sum(const void* t, float* a_f32, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
+int vmlp_s2v2_sum(const void* t, float* a_f32, int32_t B, int32_t H, int32_t W, int32_t C, int32_t plain, vmlp_stream_t stream) {
   int rc = s2v2_check(t, a_f32, B, H, W, C);
   if (rc) return rc;
   s2v2_reduce_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, RW_THREADS * 8 * sizeof(float),
-                          static_cast<cudaStream_t>(stream)>>>((cbf)t, nullptr, a_f32, H, W, C);
+                          static_cast<cudaStream_t>(stream)>>>((cbf)t, nullptr, a_f32, H, W, C, plain);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
 }
 int vmlp_s2v2_combine(const void* t, const void* hat, void* out, int32_t B, int32_t H, int32_t W, int32_t C,
-                      vmlp_stream_t stream) {
+                      int32_t plain, vmlp_stream_t stream) {
   int rc = s2v2_check(t, out, B, H, W, C);
   if (rc) return rc;
   if (!hat || !aligned16(hat)) return fail(VMLP_EALIGN, "s2v2 hat");
   s2v2_combine_kernel<<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      (cbf)t, (cbf)hat, (bf)out, B, H, W, C);
+      (cbf)t, (cbf)hat, (bf)out, B, H, W, C, plain);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
 }
 int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, float* dbar_f32, void* dhat, void* dt,
-                          int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
+                          int32_t B, int32_t H, int32_t W, int32_t C, int32_t plain, vmlp_stream_t stream) {
   int rc = s2v2_check(t, dhat, B, H, W, C);
   if (rc) return rc;
   if (!hat || !dout || !dbar_f32 || !dhat || !aligned16(hat) || !aligned16(dout) || !aligned16(dhat) || (dt && !aligned16(dt)))
     return fail(VMLP_EALIGN, "s2v2 bwd");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   s2v2_reduce_kernel<1><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, RW_THREADS * 24 * sizeof(float), st>>>(
-      (cbf)t, (cbf)dout, dbar_f32, H, W, C);
+      (cbf)t, (cbf)dout, dbar_f32, H, W, C, plain);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   const long long nv = (long long)B * (C / 8);
@@ -985,28 +988,72 @@ int vmlp_s2v2_combine_bwd(const void* t, const void* hat, const void* dout, floa
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   if (dt) {     // dt == NULL: the caller finishes with vmlp_s2v2_dt_fused once d(a) is known
-    s2v2_dt_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, nullptr, (bf)dt, B, H, W, C);
+    s2v2_dt_kernel<0><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, st>>>((cbf)dout, (cbf)hat, nullptr, (bf)dt, B, H, W, C, plain);
     CUDA_OK(cudaGetLastError());
     ++g_launches;
   }
   return VMLP_OK;
 }
-int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, vmlp_stream_t stream) {
+int vmlp_s2v2_sum_bwd(const void* da, void* dt, int32_t B, int32_t H, int32_t W, int32_t C, int32_t plain, vmlp_stream_t stream) {
   int rc = s2v2_check(da, dt, B, H, W, C);
   if (rc) return rc;
   s2v2_dt_kernel<1><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, nullptr, (cbf)da, (bf)dt, B, H, W, C);
+      nullptr, nullptr, (cbf)da, (bf)dt, B, H, W, C, plain);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;
 }
 int vmlp_s2v2_dt_fused(const void* dout, const void* hat, const void* da, void* dt, int32_t B, int32_t H, int32_t W,
-                       int32_t C, vmlp_stream_t stream) {
+                       int32_t C, int32_t plain, vmlp_stream_t stream) {
   int rc = s2v2_check(dout, dt, B, H, W, C);
   if (rc) return rc;
   if (!hat || !da || !aligned16(hat) || !aligned16(da)) return fail(VMLP_EALIGN, "s2v2 dt_fused");
   s2v2_dt_kernel<2><<<s2v2_reduce_grid(B, H, W, C), RW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      (cbf)dout, (cbf)hat, (cbf)da, (bf)dt, B, H, W, C);
+      (cbf)dout, (cbf)hat, (cbf)da, (bf)dt, B, H, W, C, plain);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+int vmlp_permute5(const void* in, void* out, const int32_t dims[5], const int64_t in_strides[4],
+                  const int64_t out_strides[4], int32_t accumulate, vmlp_stream_t stream) {
+  if (!in || !out || !dims || !in_strides || !out_strides) return fail(VMLP_EINVAL, "permute5 args");
+  if (!aligned16(in) || !aligned16(out)) return fail(VMLP_EALIGN, "permute5 alignment");
+  for (int i = 0; i < 5; ++i)
+    if (dims[i] <= 0) return fail(VMLP_EINVAL, "permute5: dims[%d] = %d", i, dims[i]);
+  if (dims[4] % 8) return fail(VMLP_EINVAL, "permute5: inner run %d is not a multiple of 8 elements", dims[4]);
+  Permute5 p;
+  p.n1 = dims[1]; p.n2 = dims[2]; p.n3 = dims[3]; p.nv = dims[4] / 8;
+  const long long slab = (long long)p.n1 * p.n2 * p.n3 * p.nv;
+  if (slab >= (1 << 22)) return fail(VMLP_EINVAL, "permute5: dims[1..4] too large (%lld vectors per dims[0] step)", slab);
+  for (int i = 0; i < 4; ++i) {
+    if (in_strides[i] % 8 || out_strides[i] % 8) return fail(VMLP_EALIGN, "permute5: strides must be multiples of 8");
+    p.is[i] = in_strides[i]; p.os[i] = out_strides[i];
+  }
+  p.total = slab * dims[0];
+  long long blocks = (p.total + 255) / 256;
+  const long long cap = (long long)device_info().sms * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (accumulate) permute5_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((cbf)in, (bf)out, p);
+  else permute5_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((cbf)in, (bf)out, p);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+static_assert(sizeof(vmlp_optim_chunk) == sizeof(OptimChunk), "optimizer table entry layout");
+static_assert(sizeof(vmlp_optim_hyper) == sizeof(OptimHyper), "optimizer hyper-parameter layout");
+int vmlp_optim_step(const vmlp_optim_chunk* table_dev, int32_t n_chunks, float* master, float* mom, float* var,
+                    const vmlp_optim_hyper* hyper, vmlp_stream_t stream) {
+  if (!table_dev || n_chunks <= 0 || !master || !mom || !hyper) return fail(VMLP_EINVAL, "optim_step args");
+  if (hyper->kind != 0 && hyper->kind != 1) return fail(VMLP_EINVAL, "optim_step: kind %d", hyper->kind);
+  if (hyper->kind == 0 && !var) return fail(VMLP_EINVAL, "optim_step: AdamW needs the second-moment buffer");
+  if (!aligned16(master) || !aligned16(mom) || (var && !aligned16(var))) return fail(VMLP_EALIGN, "optim_step state");
+  OptimHyper h;
+  memcpy(&h, hyper, sizeof(h));
+  optim_step_kernel<<<n_chunks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const OptimChunk*>(table_dev), master, mom, var, h);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

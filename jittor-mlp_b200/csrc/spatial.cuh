@@ -389,6 +389,8 @@ __global__ void bn_bwd_coef_kernel(const float* __restrict__ sdy, const float* _
 // --------------------------------------------------------------------------- S2-MLPv2 split attention (s2_mlp_v2.py:31-69)
 // t: [B, H, W, 3C] = mlp1 output;  x_k = shift_k(t[..., kC:(k+1)C]) for k = 0 (plan 1), 1 (plan 2), 2 (identity).
 // The shifts are never materialised: every kernel below reads t at clamp(position + offset_k(channel quarter)).
+// `plain` != 0: no shifts at all -- the same SplitAttention as Vision Permutator uses it on its stacked H / W / C branch
+// outputs (vip.py:37-57), which the branch kernels write side by side into one [B, H, W, 3C] buffer.
 __device__ __forceinline__ void s2_plan_offset(int k, int quarter, int& dh, int& dw) {
   // `x[:,1:] = x[:,:-1]` => out[i] = in[i-1] => offset -1 (s2_mlp_v2.py:15-29)
   // plan 1: quarters (0, 1) move along h by (-1, +1), quarters (2, 3) along w; plan 2 swaps the axes; k = 2 is identity
@@ -399,19 +401,19 @@ __device__ __forceinline__ void s2_plan_offset(int k, int quarter, int& dh, int&
 }
 // value of x_k[b, h, w, c0 .. c0+7] (forward gather, clamp) as 8 floats
 __device__ __forceinline__ void s2_gather8(const __nv_bfloat16* __restrict__ t, long long img, int h, int w, int k,
-                                           int c0, int H, int W, int C, float (&o)[8]) {
+                                           int c0, int H, int W, int C, float (&o)[8], int plain = 0) {
   const int qs = C >> 2;
   const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
   if (q0 == q1) {
     int dh, dw;
-    s2_plan_offset(k, q0, dh, dw);
+    s2_plan_offset(plain ? 2 : k, q0, dh, dw);
     const int hs = min(max(h + dh, 0), H - 1), ws = min(max(w + dw, 0), W - 1);
     unpack8(ldg_nc_v4(t + img + ((long long)hs * W + ws) * 3 * C + k * C + c0), o);
   } else {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       int dh, dw;
-      s2_plan_offset(k, min((c0 + e) / qs, 3), dh, dw);
+      s2_plan_offset(plain ? 2 : k, min((c0 + e) / qs, 3), dh, dw);
       const int hs = min(max(h + dh, 0), H - 1), ws = min(max(w + dw, 0), W - 1);
       o[e] = __bfloat162float(t[img + ((long long)hs * W + ws) * 3 * C + k * C + c0 + e]);
     }
@@ -421,12 +423,12 @@ __device__ __forceinline__ void s2_gather8(const __nv_bfloat16* __restrict__ t, 
 // A vector that lies inside one channel quarter (always, when C/4 is a multiple of 8) costs at most two 16-byte loads:
 // the shifted neighbour and, on the clamped edge, the position itself.
 __device__ __forceinline__ void s2_adjoint8(const __nv_bfloat16* __restrict__ g, long long img, int h, int w, int k,
-                                            int c0, int H, int W, int C, float (&o)[8]) {
+                                            int c0, int H, int W, int C, float (&o)[8], int plain = 0) {
   const int qs = C >> 2;
   const int q0 = min(c0 / qs, 3), q1 = min((c0 + 7) / qs, 3);
   if (q0 == q1) {
     int dh, dw;
-    s2_plan_offset(k, q0, dh, dw);
+    s2_plan_offset(plain ? 2 : k, q0, dh, dw);
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[e] = 0.f;
     const int hs = h - dh, ws = w - dw;
@@ -443,7 +445,7 @@ __device__ __forceinline__ void s2_adjoint8(const __nv_bfloat16* __restrict__ g,
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     int dh, dw;
-    s2_plan_offset(k, min((c0 + e) / qs, 3), dh, dw);
+    s2_plan_offset(plain ? 2 : k, min((c0 + e) / qs, 3), dh, dw);
     o[e] = shift_fetch<2>(g, img, h, w, c0 + e, H, W, C, dh, dw);
   }
 }
@@ -461,7 +463,7 @@ __device__ __forceinline__ float s2_read_count(int h, int w, int H, int W, int d
 template <int MODE>
 __global__ void __launch_bounds__(RW_THREADS)
 s2v2_reduce_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ g, float* __restrict__ out,
-                   int H, int W, int C) {
+                   int H, int W, int C, int plain) {
   extern __shared__ float sh[];     // [plane][nvec*8*(MODE?3:1)]
   const int nvec = C >> 3;
   const int plane = RW_THREADS / nvec;
@@ -485,7 +487,7 @@ s2v2_reduce_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __r
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         float xv[8];
-        s2_gather8(t, img, h, w, k, v * 8, H, W, C, xv);
+        s2_gather8(t, img, h, w, k, v * 8, H, W, C, xv, plain);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           if (MODE) acc[k][e] += gv[e] * xv[e];
@@ -526,7 +528,7 @@ __device__ __forceinline__ void s2_softmax3(const __nv_bfloat16* __restrict__ ha
 // channels (24 exp) is evaluated once per thread, not once per position.
 __global__ void __launch_bounds__(RW_THREADS)
 s2v2_combine_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ hat,
-                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, int plain) {
   const int nvec = C >> 3;
   const int plane = RW_THREADS / nvec;
   const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
@@ -548,7 +550,7 @@ s2v2_combine_kernel(const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       float xv[8];
-      s2_gather8(t, img, h, w, k, c0, H, W, C, xv);
+      s2_gather8(t, img, h, w, k, c0, H, W, C, xv, plain);
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] += bar[k][e] * xv[e];
     }
@@ -582,7 +584,8 @@ __global__ void s2v2_softmax_bwd_kernel(const __nv_bfloat16* __restrict__ hat, c
 template <int MODE>
 __global__ void __launch_bounds__(RW_THREADS)
 s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __restrict__ hat,
-               const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dt, int B, int H, int W, int C) {
+               const __nv_bfloat16* __restrict__ da, __nv_bfloat16* __restrict__ dt, int B, int H, int W, int C,
+               int plain) {
   const int nvec = C >> 3;
   const int qs = C >> 2;
   const int plane = RW_THREADS / nvec;
@@ -609,7 +612,7 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
       for (int e = 0; e < 8; ++e) o[e] = 0.f;
       if (MODE != 1) {
         float gv[8];
-        if (k < 2) s2_adjoint8(src, simg, h, w, k, c0, H, W, C, gv);
+        if (k < 2) s2_adjoint8(src, simg, h, w, k, c0, H, W, C, gv, plain);
         else unpack8(ldg_nc_v4(src + simg + (long long)pos * C + c0), gv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = bar[k][e] * gv[e];
@@ -617,7 +620,7 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
       if (MODE != 0) {
         if (k == 2 || q0 == q1) {
           int dh = 0, dw = 0;
-          if (k < 2) s2_plan_offset(k, q0, dh, dw);
+          if (k < 2) s2_plan_offset(plain ? 2 : k, q0, dh, dw);
           const float cnt = (k < 2) ? s2_read_count(h, w, H, W, dh, dw) : 1.f;
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] += dav[e] * cnt;
@@ -625,7 +628,7 @@ s2v2_dt_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* __res
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             int dh, dw;
-            s2_plan_offset(k, min((c0 + e) / qs, 3), dh, dw);
+            s2_plan_offset(plain ? 2 : k, min((c0 + e) / qs, 3), dh, dw);
             o[e] += dav[e] * s2_read_count(h, w, H, W, dh, dw);
           }
         }

@@ -500,32 +500,37 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         named_bar_sync(TM_NB_START + gi, 32 * (TM_EPI_WARPS / 2));
         tc_fence_after();
         if (tr) tm_stamp(p, 1, g, 1);
-        uint32_t va[16], vb[16];
         const bool live0 = half * 32 < n1, live1 = half * 32 + 16 < n1;
-        if (!(p.flags & 16)) {
-          if (live1) tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + half * 32 + lane_addr, tmem_base + gi * TM_CH + half * 32 + 16 + lane_addr, va, vb);
-          else if (live0) tmem_ld_x16_wait(tmem_base + gi * TM_CH + half * 32 + lane_addr, va);
-        }
-        tc_fence_before();
-        named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
-        if (tr) tm_stamp(p, 1, g, 2);
+        // 16 columns at a time: with all 32 accumulator values of the warp live, ptxas has no registers left to overlap the
+        // GELU chains of different element pairs (gelu_rcp16_x4) and the warp stalls on every dependent instruction
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          if (!(hh ? live1 : live0)) continue;
-          const uint32_t (&v)[16] = hh ? vb : va;
+          const bool live = hh ? live1 : live0;
+          uint32_t v[16];
+          if (live && !(p.flags & 16)) tmem_ld_x16_wait(tmem_base + gi * TM_CH + half * 32 + 16 * hh + lane_addr, v);
+          if (hh == 1) {
+            tc_fence_before();
+            named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
+            if (tr) tm_stamp(p, 1, g, 2);
+          }
+          if (!live) continue;
           uint32_t o[8];
           if (p.flags & 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
           } else {
 #pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const float4 bv = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 4 * e4) * 4);
-              f32x2 gl, dg;
-              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4]) + bv.x, __uint_as_float(v[4 * e4 + 1]) + bv.y), gl, dg);
-              o[2 * e4] = pack_bf16x2_f2(gl);
-              gelu_rcp16_pair<false>(pack2(__uint_as_float(v[4 * e4 + 2]) + bv.z, __uint_as_float(v[4 * e4 + 3]) + bv.w), gl, dg);
-              o[2 * e4 + 1] = pack_bf16x2_f2(gl);
+            for (int e8 = 0; e8 < 2; ++e8) {                       // 8 columns = 4 pairs in flight (gelu_rcp16_x4)
+              const float4 b0 = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 8 * e8) * 4);
+              const float4 b1v = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 8 * e8 + 4) * 4);
+              const f32x2 zz[4] = {pack2(__uint_as_float(v[8 * e8]) + b0.x, __uint_as_float(v[8 * e8 + 1]) + b0.y),
+                                   pack2(__uint_as_float(v[8 * e8 + 2]) + b0.z, __uint_as_float(v[8 * e8 + 3]) + b0.w),
+                                   pack2(__uint_as_float(v[8 * e8 + 4]) + b1v.x, __uint_as_float(v[8 * e8 + 5]) + b1v.y),
+                                   pack2(__uint_as_float(v[8 * e8 + 6]) + b1v.z, __uint_as_float(v[8 * e8 + 7]) + b1v.w)};
+              f32x2 gl[4];
+              gelu_rcp16_x4(zz, gl);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o[4 * e8 + q] = pack_bf16x2_f2(gl[q]);
             }
           }
           if (!(p.flags & 8)) tm_store_hidden_row(s_h + gi * TM_HTILE, row, half * 2 + hh, o);

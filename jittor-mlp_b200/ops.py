@@ -45,13 +45,17 @@ def operand(t, major, batched=None):
 
 def gemm(M, N, K, A, B, epilogue=L.EPI_STORE, batch=1, contract_batch=False, D=None, D2=None, bias=None,
          bias_mode=0, colscale=None, aux=None, out_f32=None, split_k=0, block_n=0, cta_group=0, red_out=None, red_mode=0,
-         out_trans=False):
-    """Generic fused GEMM, see vmlp_gemm_bf16 in include/vmlp_b200.h.  A/B are L.Operand."""
+         out_trans=False, strided_d=False):
+    """Generic fused GEMM, see vmlp_gemm_bf16 in include/vmlp_b200.h.  A/B are L.Operand.  strided_d: D may be a column
+    slice of a wider row-major buffer (its row pitch goes into d_ld)."""
     g = L.GemmArgs()
     g.M, g.N, g.K, g.batch, g.contract_batch = M, N, K, batch, int(contract_batch)
     g.A, g.B, g.epilogue = A, B, epilogue
     if D is not None:
-        _chk(D, "D")
+        if strided_d and D.dim() == 2 and D.stride(1) == 1 and D.is_cuda and D.dtype == BF16:
+            pass
+        else:
+            _chk(D, "D")
         g.D, g.d_ld, g.d_bs = D.data_ptr(), D.stride(-2), (D.stride(0) if D.dim() == 3 else 0)
     if D2 is not None:
         _chk(D2, "D2")

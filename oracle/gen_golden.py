@@ -38,6 +38,10 @@ CASES = {
                                              depth=[2, 2], num_classes=10), (2, 3, 40, 32)),
     "convmixer_tiny": ("conv_mixer", "ConvMixer", dict(dim=32, depth=2, kernel_size=5, patch_size=4, n_classes=10),
                        (4, 3, 32, 32)),
+    "vip_tiny": ("vip", "ViP", dict(image_size=(32, 48), patch_size=(8, 8), d_model=32, depth=2, segments=8, num_classes=10,
+                                    expansion_factor=3, weighted=True), (2, 3, 32, 48), {"split_attention": 0.15}),
+    "vip_sum_tiny": ("vip", "ViP", dict(image_size=(32, 32), patch_size=(8, 4), d_model=48, depth=1, segments=16,
+                                        num_classes=10, weighted=False), (3, 3, 32, 32)),
     "gmlp_tiny": ("g_mlp", "gMLPForImageClassification",
                   dict(image_size=32, patch_size=8, num_classes=10, d_model=64, d_ffn=128, depth=2), (2, 3, 32, 32)),
 }

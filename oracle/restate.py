@@ -319,3 +319,57 @@ def convmixer_forward(sd, x, kw):
         pw = F.conv2d(t, sd[p + "1.weight"], sd[p + "1.bias"])
         t = batch_norm_train(gelu(pw), sd[p + "3.weight"], sd[p + "3.bias"])
     return linear(t.mean((2, 3)), sd["classifier.2.weight"], sd["classifier.2.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- ViP
+def vip_forward(sd, x, kw):
+    """ViP.forward (vip.py:166-171); WeightedPermutator / Permutator blocks (vip.py:59-128), ParallelWeightedSum
+    (vip.py:24-35), SplitAttention (vip.py:37-57).  The einops rearrangements are written as explicit reshapes:
+    `b h w (c s) -> b w c (h s)` = [B,H,W,c,S] -> permute(0,2,3,1,4) -> [B,W,c,H*S]."""
+    ps = kw.get("patch_size", 16)
+    ps = (ps, ps) if isinstance(ps, int) else tuple(ps)
+    S, depth, weighted = kw.get("segments", 14), kw.get("depth", 30), kw.get("weighted", True)
+    t = F.conv2d(x, sd["patcher.0.weight"], sd["patcher.0.bias"], stride=ps).permute(0, 2, 3, 1)
+    B, H, W, C = t.shape
+    c = C // S
+    for i in range(depth):
+        p = f"blocks.model.{i}."
+        q = p + "0.fn.0."
+        u = layer_norm(t, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"])
+        u5 = u.reshape(B, H, W, c, S)
+        xh = linear(u5.permute(0, 2, 3, 1, 4).reshape(B, W, c, H * S), sd[q + "fns.0.1.weight"], sd[q + "fns.0.1.bias"])
+        xh = xh.reshape(B, W, c, H, S).permute(0, 3, 1, 2, 4).reshape(B, H, W, C)
+        xw = linear(u5.permute(0, 1, 3, 2, 4).reshape(B, H, c, W * S), sd[q + "fns.1.1.weight"], sd[q + "fns.1.1.bias"])
+        xw = xw.reshape(B, H, c, W, S).permute(0, 1, 3, 2, 4).reshape(B, H, W, C)
+        xc = linear(u, sd[q + "fns.2.weight"], sd[q + "fns.2.bias"])
+        if weighted:
+            a = (xh + xw + xc).sum((1, 2))                                            # [B, C]
+            hat = linear(gelu(linear(a, sd[q + "split_attention.mlp1.weight"])), sd[q + "split_attention.mlp2.weight"])
+            bar = torch.softmax(hat.reshape(B, 3, C), 1)
+            o = bar[:, 0, None, None, :] * xh + bar[:, 1, None, None, :] * xw + bar[:, 2, None, None, :] * xc
+        else:
+            o = xh + xw + xc
+        t = t + linear(o, sd[p + "0.fn.1.weight"], sd[p + "0.fn.1.bias"])
+        h = gelu(linear(layer_norm(t, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"]), sd[p + "1.fn.0.weight"], sd[p + "1.fn.0.bias"]))
+        t = t + linear(h, sd[p + "1.fn.3.weight"], sd[p + "1.fn.3.bias"])
+    t = layer_norm(t, sd["mlp_head.0.weight"], sd["mlp_head.0.bias"])
+    return linear(t.mean((1, 2)), sd["mlp_head.2.weight"], sd["mlp_head.2.bias"])
+
+
+# ----------------------------------------------------------------------------------------------- optimizer step (f4)
+def adamw_step(w, g, m, v, t, lr, b1, b2, eps, wd):
+    """One torch.optim.AdamW step on fp32 tensors (decoupled weight decay, bias-corrected moments); t = step count
+    AFTER this step.  The reference has no optimizer (compare.py:141-145): this restates the library's documented
+    algorithm, and tests pin it against torch.optim.AdamW itself."""
+    w = w * (1 - lr * wd)
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    w = w - (lr / (1 - b1 ** t)) * m / (v.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+    return w, m, v
+
+
+def sgd_step(w, g, buf, t, lr, momentum, wd):
+    """One torch.optim.SGD(momentum, dampening=0) step; the buffer starts as the first gradient."""
+    g = g + wd * w
+    buf = g.clone() if t == 1 else momentum * buf + g
+    return w - lr * buf, buf

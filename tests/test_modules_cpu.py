@@ -9,7 +9,7 @@ import jittor_mlp_b200 as J
 from oracle import ref_loader
 
 CASES = {"mixer_tiny": 1, "mixer_ragged": 1, "resmlp_tiny": 1, "gmlp_tiny": 1, "s2v1_tiny": 1, "s2v2_tiny": 1,
-         "asmlp_tiny": 1, "hire_tiny": 1, "convmixer_tiny": 1}
+         "asmlp_tiny": 1, "hire_tiny": 1, "convmixer_tiny": 1, "vip_tiny": 1, "vip_sum_tiny": 1}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -28,10 +28,44 @@ def test_state_dict_roundtrip_strict(golden, name):
                                      ("res_mlp", "MLPblock"), ("g_mlp", "gMLPForImageClassification"),
                                      ("g_mlp", "gMLP"), ("g_mlp", "gMLPBlock"),
                                      ("s2_mlp_v1", "S2MLPv1"), ("s2_mlp_v1", "S2MLPv1_deep"), ("s2_mlp_v2", "S2MLPv2"),
-                                     ("as_mlp", "AS_MLP"), ("hire_mlp", "HireMLP"), ("conv_mixer", "ConvMixer")])
+                                     ("as_mlp", "AS_MLP"), ("hire_mlp", "HireMLP"), ("conv_mixer", "ConvMixer"),
+                                     ("vip", "ViP")])
 def test_constructor_signature_matches_reference(mod, cls):
     ref = getattr(ref_loader.load(mod), cls)
 
     def sig(f):   # parameter names + defaults (function-object defaults compared by name)
         return [(n, getattr(p.default, "__name__", p.default)) for n, p in inspect.signature(f).parameters.items()]
     assert sig(getattr(J, cls).__init__ if inspect.isclass(ref) else getattr(J, cls)) == sig(ref.__init__ if inspect.isclass(ref) else ref)
+
+
+def test_optimizer_chunk_table_covers_every_element_once():
+    from jittor_mlp_b200 import optim
+    tab = optim.build_table([(4096, 8192, 0, 70000), (1 << 20, 2 << 20, 70000, 5), (3 << 20, 4 << 20, 70008, 32768)])
+    assert [int(n) for n in tab["n"]] == [32768, 32768, 70000 - 65536, 5, 32768]
+    assert int(tab["param"][1]) == 4096 + 2 * 32768 and int(tab["grad"][2]) == 8192 + 2 * 65536
+    assert [int(o) for o in tab["state_off"]] == [0, 32768, 65536, 70000, 70008]
+    assert tab.dtype.itemsize == 32           # == sizeof(vmlp_optim_chunk)
+
+
+def test_fused_optimizer_state_dict_interchanges_with_torch_adamw():
+    """Weight / optimizer-state interchange: torch's AdamW state loads into FusedAdamW and back."""
+    ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    ref = torch.optim.AdamW(ps, lr=1e-3, weight_decay=0.1)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    ref.step()
+    mine_ps = [torch.nn.Parameter(p.detach().bfloat16()) for p in ps]
+    mine = J.FusedAdamW(mine_ps, lr=5e-4)
+    mine.load_state_dict(ref.state_dict())
+    assert mine.param_groups[0]["lr"] == 1e-3 and mine.param_groups[0]["weight_decay"] == 0.1
+    for p, q in zip(ps, mine_ps):
+        assert torch.equal(mine.state[q]["exp_avg"], ref.state[p]["exp_avg"])
+        assert torch.equal(mine.state[q]["exp_avg_sq"], ref.state[p]["exp_avg_sq"])
+        assert float(mine.state[q]["step"]) == 1.0
+    back = torch.optim.AdamW([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1.0)
+    back.load_state_dict(mine.state_dict())
+    assert back.param_groups[0]["lr"] == 1e-3
+    with pytest.raises(NotImplementedError):
+        for q in mine_ps:
+            q.grad = torch.zeros_like(q)
+        mine.step()                           # CPU tensors: refuse, never fall back

@@ -6,7 +6,7 @@ import torch
 from oracle import models, ref_loader, restate
 
 GOLDEN = ["mixer_tiny", "mixer_ragged", "resmlp_tiny", "gmlp_tiny", "s2v1_tiny", "s2v2_tiny", "asmlp_tiny", "hire_tiny",
-          "convmixer_tiny"]
+          "convmixer_tiny", "vip_tiny", "vip_sum_tiny"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -65,3 +65,26 @@ def test_aten_fast_path_of_the_port_equals_the_elementary_restatement(golden):
     finally:
         restate.USE_ATEN = False
     assert restate.rel_l2(b, a) < 1e-5
+
+
+def test_optimizer_restatements_match_torch_optim():
+    """the reference has no optimizer, so the oracle is pinned against torch.optim itself."""
+    g0 = torch.Generator().manual_seed(5)
+    w0 = torch.randn(37, 11, generator=g0)
+    grads = [torch.randn(37, 11, generator=g0) for _ in range(4)]
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.AdamW([p], lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    w, m, v = w0.clone(), torch.zeros_like(w0), torch.zeros_like(w0)
+    for t, g in enumerate(grads, 1):
+        p.grad = g.clone()
+        opt.step()
+        w, m, v = restate.adamw_step(w, g, m, v, t, 3e-3, 0.9, 0.95, 1e-8, 0.05)
+        assert float((w - p.detach()).abs().max()) < 1e-6
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.SGD([p], lr=1e-2, momentum=0.9, weight_decay=1e-3)
+    w, buf = w0.clone(), torch.zeros_like(w0)
+    for t, g in enumerate(grads, 1):
+        p.grad = g.clone()
+        opt.step()
+        w, buf = restate.sgd_step(w, g, buf, t, 1e-2, 0.9, 1e-3)
+        assert float((w - p.detach()).abs().max()) < 1e-6
