@@ -217,14 +217,15 @@ typedef struct {
   const void* grad;      /* bf16 */
   int64_t state_off;
   int32_t n;
-  int32_t reserved;
+  int32_t step;          /* > 0: step count t of THIS parameter (AdamW bias corrections 1 - beta^t are per tensor in
+                            torch.optim: a parameter that skipped a step lags behind); 0: use vmlp_optim_hyper's */
 } vmlp_optim_chunk;
 typedef struct {
   int32_t kind;          /* 0 = AdamW, 1 = SGD with momentum */
   int32_t first_step;    /* SGD: momentum buffer := gradient on the first step (torch.optim.SGD) */
   float lr, beta1, beta2, eps, weight_decay;
-  float bias_c1;         /* 1 - beta1^t */
-  float bias_c2_sqrt;    /* sqrt(1 - beta2^t) */
+  float bias_c1;         /* 1 - beta1^t       } used by chunks whose own `step` is 0 */
+  float bias_c2_sqrt;    /* sqrt(1 - beta2^t) } */
   float grad_scale;      /* gradients are multiplied by this first (1/world for SUM all-reduces, loss-scale inverse) */
   float momentum;
 } vmlp_optim_hyper;

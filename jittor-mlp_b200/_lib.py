@@ -103,7 +103,7 @@ class HireDims(ctypes.Structure):
 
 
 class OptimChunk(ctypes.Structure):
-    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state_off", c_int64), ("n", c_int32), ("reserved", c_int32)]
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("state_off", c_int64), ("n", c_int32), ("step", c_int32)]
 
 
 class OptimHyper(ctypes.Structure):

@@ -57,7 +57,8 @@ struct OptimChunk {                 // one run of <= OPT_CHUNK elements of one p
   const __nv_bfloat16* grad;
   long long state_off;              // offset of the run in the flat fp32 state buffers
   int n;
-  int pad;
+  int step;                         // > 0: this parameter's own step count t (bias corrections 1 - beta^t per tensor, like
+                                    // torch.optim.AdamW); 0: use the corrections in OptimHyper
 };
 struct OptimHyper {
   int kind;                         // 0 = AdamW (decoupled weight decay), 1 = SGD with momentum (torch.optim.SGD)
@@ -85,8 +86,13 @@ __device__ __forceinline__ float optim_update(const OptimHyper& h, float g, floa
 // start on any 2-byte boundary)
 __global__ void __launch_bounds__(256)
 optim_step_kernel(const OptimChunk* __restrict__ table, float* __restrict__ master, float* __restrict__ mom,
-                  float* __restrict__ var, const OptimHyper h) {
+                  float* __restrict__ var, const OptimHyper h_in) {
   const OptimChunk c = table[blockIdx.x];
+  OptimHyper h = h_in;
+  if (h.kind == 0 && c.step > 0) {
+    h.bias_c1 = 1.f - exp2f(static_cast<float>(c.step) * log2f(h.beta1));
+    h.bias_c2_sqrt = sqrtf(1.f - exp2f(static_cast<float>(c.step) * log2f(h.beta2)));
+  }
   float* w = master + c.state_off;
   float* m = mom + c.state_off;
   float* v = (h.kind == 0) ? var + c.state_off : nullptr;

@@ -18,34 +18,39 @@
 // Hidden chunks of 64 divide Ds = 784 with 16 left over (UMMA N = 16 for the tail chunk): no padded MMA work along Ds;
 // the token axis N = 196 is padded to NT = 208 by TMA zero fill (13 k-steps of 16).
 //
-// Warp roles, forward (640 threads): warp 0 = TMA producer of the weight rings and the activation tile, warp 1 = issuer of
-// G1 + TMEM owner, warp 3 = issuer of G2, warp 2 = TMA store of the hidden tile + the residual-in / output-out tile,
-// warps 4..19 = epilogue (TMEM lane quarter = warp % 4, 16 of the chunk's 64 columns each).  Backward (768 threads): warp
-// 0 = producer, warps 1 / 2 / 3 = issuers of Z / dH / G3, warp 4 = TMA store of the dZ tile, warps 4..7 = column sums,
-// warps 8..23 = epilogue.  All hand-offs are mbarriers (multicast tcgen05.commit towards both CTAs, remote arrives
-// towards the leader).
+// Warp roles, forward (384 threads): warp 0 = TMA producer of the weight rings and the activation tile, warp 1 = issuer of
+// G1 + TMEM owner, warp 3 = issuer of G2, warp 2 = forwarder of the epilogue's hand-offs + TMA stores (hidden tile,
+// residual-in / output-out tile), warps 4..11 = epilogue in two ping-pong groups of 4 (TMEM lane quarter = warp % 4, all
+// 64 columns of every other chunk).  Backward (384 threads): warp 0 = producer, warp 1 = the MMA issuer (G1, G2 and, two
+// chunks behind, G3), warp 2 = TMA store of the dZ tile, warps 2..3 = its column sums (d b1), warps 4..11 = epilogue
+// (lane quarter = warp % 4, 32 of the chunk's 64 columns).  All hand-offs between roles are mbarriers (multicast
+// tcgen05.commit towards both CTAs, remote arrives towards the leader); inside an epilogue group, hardware named barriers.
 //
-// What the first versions taught (clock64 timeline of CTA 0, tools/tokmix_trace.py; ncu source page): every mbarrier
-// operation costs a warp 100-200 cycles of latency even when it succeeds at once, so ONE issuer warp that waits on five
-// barriers and issues 17 MMAs per chunk needs ~1900 cycles for 832 cycles of tensor work, and an epilogue warp that does
-// wait / load / arrive / math / wait / wait / write / fence / arrive / arrive strictly in sequence needs ~1100 cycles of
-// pure hand-off latency per chunk on top of a MUFU-bound GELU (rcp + ex2 per element: 1024 cycles per chunk and SM).
-// Hence: two issuer warps; barrier probes issued back to back (test_wait) so their latencies overlap; the "buffer is
-// free" conditions merged into one barrier; the NEXT chunk's accumulator prefetched into registers before the math of
-// the current one; erf-GELU (and its derivative) with a single MUFU per element (ptx.cuh: gelu_rcp16_pair).
+// What the versions taught (clock64 timeline of CTA 0, tools/tokmix_trace.py; ncu stall reasons and source page):
+//  * every mbarrier operation costs a warp 100-200 cycles even when it succeeds at once: ONE issuer warp that waits on
+//    five barriers and issues 17 MMAs per chunk needs ~1900 cycles for 832 cycles of tensor work, and 16 epilogue warps
+//    that each wait / load / arrive / compute / wait / write / fence / arrive in lock step need ~1100 cycles of pure
+//    hand-off latency per chunk -> forward: two issuer warps, one polling warp per group + named barriers, one forwarding
+//    warp, two groups on alternate chunks;
+//  * the GELU is a 14-deep (gelu': ~20-deep) dependent chain per element pair; with 640 threads ptxas had 96 registers
+//    and serialised the pairs (ncu: fixed-latency "wait" the top stall, FMA pipe 41 % busy, issue slots 50 % used)
+//    -> 8 epilogue warps with 168 registers instead of 16 with 96: same lanes, several pairs in flight per warp;
+//  * erf-GELU with a single MUFU per element (ptx.cuh: gelu_rcp16_x4) -- rcp + ex2 per element is 1024 MUFU cycles per
+//    chunk and SM, more than the chunk's 832 MMA cycles.
 #pragma once
 #include "ptx.cuh"
 
 namespace vmlp {
 
 constexpr int TM_CH = 64;                              // hidden chunk (UMMA N of G1, K of G2 per chunk)
-constexpr int TM_EPI_WARPS = 16;
 // Registers are allocated to warps in groups of four: 20 warps leave 96 registers per thread, 21..24 warps leave 80.
-constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 16 epilogue warps
-constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_EPI_WARPS);   // 640
+constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 8 epilogue warps
+constexpr int TM_FWD_EPI_WARPS = 8;                              // 384 threads -> up to 168 registers each (see the epilogue)
+constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_FWD_EPI_WARPS);
 constexpr int TM_NB_START = 1, TM_NB_ZE = 3, TM_NB_HW = 5;          // named (hardware) barrier ids (+ group), see the epilogue
-constexpr int TM_BWD_EPI0 = 4;                                   // backward: 4 service warps + 16 epilogue warps
-constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_EPI_WARPS);   // 640
+constexpr int TM_BWD_EPI0 = 4;                                   // backward: 4 service warps + 8 epilogue warps
+constexpr int TM_BWD_EPI_WARPS = 8;
+constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_BWD_EPI_WARPS);
 constexpr int TM_HTILE = 128 * TM_CH * 2;              // 16 KB: [128 channels x 64 hidden] bf16, K-major SWIZZLE_128B
 constexpr int TM_MAX_DS = 1024;
 constexpr int TM_BAR_BYTES = 1024;
@@ -239,8 +244,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmR); tma_prefetch_desc(&tmU);
     mbar_init(xt_full, 1); mbar_init(xt_empty, 1);
-    mbar_init(ro_full, 1); mbar_init(ro_done, TM_EPI_WARPS);
-    mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_EPI_WARPS);
+    mbar_init(ro_full, 1); mbar_init(ro_done, TM_FWD_EPI_WARPS);
+    mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_FWD_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2);      // one forwarded arrival per CTA (warp 2)
       mbar_init(&h_full[i], 2);  mbar_init(&h_free[i], 2);
@@ -371,7 +376,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     }
   } else if (warp == 2) {
     // ================================================================ TMA stores (each CTA its own tiles): the saved hidden
-    // tile of every chunk, and per item the residual-in / output-out tile: once the 16 epilogue warps have turned the
+    // tile of every chunk, and per item the residual-in / output-out tile: once the epilogue warps have turned the
     // residual into the output in place (ro_done) it is stored and the NEXT item's residual is loaded behind it.  (While
     // this warp waits for ro_done the epilogue is in its output phase and writes no hidden tile; the first hidden tiles of
     // the next item are stored a little late, which the double buffer absorbs.)
@@ -382,13 +387,14 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     };
     if (cluster_id < p.n_pairs && elect_one_sync()) load_residual(cluster_id);
     __syncwarp();
-    // "Z(g) has been read by the 8 warps of group g & 1" is forwarded as ONE arrival to the leader's z_empty; "H(g) has been
+    // "Z(g) has been read by the 4 warps of group g & 1" is forwarded as ONE arrival to the leader's z_empty; "H(g) has been
     // written" is forwarded to h_full, the tile is stored and the buffer released.  At the end of an item the output tile.
     auto forward_hw = [&](int g) {
       const int gi = g & 1;
       const int item = g / NC, j = g - item * NC;
       const TokTile t = tm_tile(p, cluster_id + item * num_clusters, cta_rank);
-      named_bar_sync(TM_NB_HW + gi, 32 * (TM_EPI_WARPS / 2 + 1));
+      named_bar_sync(TM_NB_HW + gi, 32 * (TM_FWD_EPI_WARPS / 2 + 1));
+      if (lane == 0) tm_stamp(p, 2, g, 0);
       if (elect_one_sync()) {
         tm_arrive_leader(&h_full[gi], is_leader);
         if (save_hidden && t.valid && !(p.flags & 2)) {
@@ -399,6 +405,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         mbar_arrive(&h_free[gi]);
       }
       __syncwarp();
+      if (lane == 0) tm_stamp(p, 2, g, 1);
       if (j == NC - 1) {                                   // last chunk of an item: its output tile follows
         mbar_wait<64>(ro_done, item & 1);
         if (elect_one_sync()) {
@@ -417,7 +424,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     for (int g = 0; g <= total; ++g) {
       if (g >= 1) forward_hw(g - 1);
       if (g < total) {
-        named_bar_sync(TM_NB_ZE + (g & 1), 32 * (TM_EPI_WARPS / 2 + 1));
+        named_bar_sync(TM_NB_ZE + (g & 1), 32 * (TM_FWD_EPI_WARPS / 2 + 1));
+        if (lane == 0) tm_stamp(p, 2, g, 2);
         if (elect_one_sync()) tm_arrive_leader(&z_empty[g & 1], is_leader);
         __syncwarp();
       }
@@ -426,19 +434,20 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     __syncwarp();
   } else if (warp >= TM_FWD_EPI0) {
     // ================================================================ epilogue warps (software-pipelined over chunks)
-    // Two groups of 8 warps work on ALTERNATE chunks (group = chunk parity = Z buffer = hidden-tile buffer): while one group
+    // Two groups of 4 warps work on ALTERNATE chunks (group = chunk parity = Z buffer = hidden-tile buffer): while one group
     // runs the GELU of chunk g, the other one is in the hand-off phases of chunk g + 1 (barrier, TMEM load, tile write,
-    // fence), which cost ~900 cycles per chunk and were serial with the ~1250 cycles of math when all 16 warps moved in
-    // lock step.  A warp owns TMEM lane quarter warp % 4 and 32 of the chunk's 64 columns.
+    // fence).  A warp owns TMEM lane quarter warp % 4 and ALL 64 columns of its chunk: 8 fat warps instead of 16 thin ones,
+    // because the GELU is a 14-deep dependent chain per element pair and at 96 registers per thread (640 threads) ptxas
+    // serialised the pairs -- ncu: "wait" (fixed-latency dependency) the top stall, 2.4 warps per issue, the FMA pipe 41 %
+    // busy; with 384 threads it has 168 registers and overlaps the chains of many pairs.
     const int q = warp & 3;                               // TMEM lane quarter
-    const int gi = (warp - TM_FWD_EPI0) >> 3;             // group: chunks with g % 2 == gi
-    const int half = ((warp - TM_FWD_EPI0) >> 2) & 1;     // columns [32 half, 32 half + 32) of the chunk
-    const int cq = gi * 2 + half;                         // token-group phase of this warp in the output epilogue
+    const int gi = (warp - TM_FWD_EPI0) >> 2;             // group: chunks with g % 2 == gi
+    const int cq = gi;                                    // token-group phase of this warp in the output epilogue
     const int row = q * 32 + lane;                        // channel within the tile
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
-    const bool tr = (warp - TM_FWD_EPI0) % 8 == 0 && lane == 0;
-    const bool poller = ((warp - TM_FWD_EPI0) & 7) == 0;   // the one warp of the group that polls the mbarriers
+    const bool tr = (warp - TM_FWD_EPI0) % 4 == 0 && lane == 0;
+    const bool poller = ((warp - TM_FWD_EPI0) & 3) == 0;   // the one warp of the group that polls the mbarriers
     int it = 0;                                           // item whose output epilogue this warp does next
     for (int g = gi; ; g += 2) {
       // ---- output epilogues of every item that ends before chunk g (or all remaining ones once g runs out)
@@ -452,9 +461,9 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         tc_fence_after();
         const uint32_t ro_col = s_ro + row * 2;
   #pragma unroll 1
-        for (int grp = cq; grp < ngrp + 4; grp += 4) {
+        for (int grp = cq; grp < ngrp + 2; grp += 2) {
           const bool has = grp < ngrp;
-          const bool last = grp + 4 >= ngrp;                // this warp's last visit (possibly an empty one)
+          const bool last = grp + 2 >= ngrp;                // this warp's last visit (possibly an empty one)
           uint32_t v[16];
           if (has) {
             tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + grp * 16 + lane_addr, v);
@@ -497,47 +506,46 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         // ONE warp of the group polls the mbarriers (Z(g) complete; hidden buffer free: G2 and the TMA store of its previous
         // user done), the named barrier releases the other seven: an mbarrier operation costs a warp 100-200 cycles
         if (poller) mbar_wait2<0>(&z_full[gi], (g >> 1) & 1, &h_free[gi], ((g >> 1) & 1) ^ 1);
-        named_bar_sync(TM_NB_START + gi, 32 * (TM_EPI_WARPS / 2));
+        named_bar_sync(TM_NB_START + gi, 32 * (TM_FWD_EPI_WARPS / 2));
         tc_fence_after();
         if (tr) tm_stamp(p, 1, g, 1);
-        const bool live0 = half * 32 < n1, live1 = half * 32 + 16 < n1;
-        // 16 columns at a time: with all 32 accumulator values of the warp live, ptxas has no registers left to overlap the
-        // GELU chains of different element pairs (gelu_rcp16_x4) and the warp stalls on every dependent instruction
+        // all 64 accumulator columns of the chunk first (the Z buffer goes back to the G1 issuer at once), then the math
+        uint32_t v[4][16];
+        if (!(p.flags & 16)) {
+          if (n1 > 16) tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + lane_addr, tmem_base + gi * TM_CH + 16 + lane_addr, v[0], v[1]);
+          else tmem_ld_x16_wait(tmem_base + gi * TM_CH + lane_addr, v[0]);
+          if (n1 > 32) tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + 32 + lane_addr, tmem_base + gi * TM_CH + 48 + lane_addr, v[2], v[3]);
+        }
+        tc_fence_before();
+        named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_FWD_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
+        if (tr) tm_stamp(p, 1, g, 2);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const bool live = hh ? live1 : live0;
-          uint32_t v[16];
-          if (live && !(p.flags & 16)) tmem_ld_x16_wait(tmem_base + gi * TM_CH + half * 32 + 16 * hh + lane_addr, v);
-          if (hh == 1) {
-            tc_fence_before();
-            named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
-            if (tr) tm_stamp(p, 1, g, 2);
-          }
-          if (!live) continue;
+        for (int hh = 0; hh < 4; ++hh) {
+          if (16 * hh >= n1) continue;
           uint32_t o[8];
           if (p.flags & 1) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+            for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[hh][2 * e]), __uint_as_float(v[hh][2 * e + 1]));
           } else {
 #pragma unroll
-            for (int e8 = 0; e8 < 2; ++e8) {                       // 8 columns = 4 pairs in flight (gelu_rcp16_x4)
-              const float4 b0 = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 8 * e8) * 4);
-              const float4 b1v = lds_f4(s_b1 + (j * TM_CH + half * 32 + 16 * hh + 8 * e8 + 4) * 4);
-              const f32x2 zz[4] = {pack2(__uint_as_float(v[8 * e8]) + b0.x, __uint_as_float(v[8 * e8 + 1]) + b0.y),
-                                   pack2(__uint_as_float(v[8 * e8 + 2]) + b0.z, __uint_as_float(v[8 * e8 + 3]) + b0.w),
-                                   pack2(__uint_as_float(v[8 * e8 + 4]) + b1v.x, __uint_as_float(v[8 * e8 + 5]) + b1v.y),
-                                   pack2(__uint_as_float(v[8 * e8 + 6]) + b1v.z, __uint_as_float(v[8 * e8 + 7]) + b1v.w)};
+            for (int e8 = 0; e8 < 2; ++e8) {                       // 8 columns = 4 pairs per call (gelu_rcp16_x4)
+              const float4 b0 = lds_f4(s_b1 + (j * TM_CH + 16 * hh + 8 * e8) * 4);
+              const float4 b1v = lds_f4(s_b1 + (j * TM_CH + 16 * hh + 8 * e8 + 4) * 4);
+              const f32x2 zz[4] = {pack2(__uint_as_float(v[hh][8 * e8]) + b0.x, __uint_as_float(v[hh][8 * e8 + 1]) + b0.y),
+                                   pack2(__uint_as_float(v[hh][8 * e8 + 2]) + b0.z, __uint_as_float(v[hh][8 * e8 + 3]) + b0.w),
+                                   pack2(__uint_as_float(v[hh][8 * e8 + 4]) + b1v.x, __uint_as_float(v[hh][8 * e8 + 5]) + b1v.y),
+                                   pack2(__uint_as_float(v[hh][8 * e8 + 6]) + b1v.z, __uint_as_float(v[hh][8 * e8 + 7]) + b1v.w)};
               f32x2 gl[4];
               gelu_rcp16_x4(zz, gl);
 #pragma unroll
-              for (int q = 0; q < 4; ++q) o[4 * e8 + q] = pack_bf16x2_f2(gl[q]);
+              for (int qq = 0; qq < 4; ++qq) o[4 * e8 + qq] = pack_bf16x2_f2(gl[qq]);
             }
           }
-          if (!(p.flags & 8)) tm_store_hidden_row(s_h + gi * TM_HTILE, row, half * 2 + hh, o);
+          if (!(p.flags & 8)) tm_store_hidden_row(s_h + gi * TM_HTILE, row, hh, o);
         }
         if (tr) tm_stamp(p, 1, g, 3);
         fence_proxy_async_smem();
-        named_bar_arrive(TM_NB_HW + gi, 32 * (TM_EPI_WARPS / 2 + 1));   // warp 2 forwards "H(g) written", stores the tile
+        named_bar_arrive(TM_NB_HW + gi, 32 * (TM_FWD_EPI_WARPS / 2 + 1));   // warp 2 forwards "H(g) written", stores the tile
         if (tr) tm_stamp(p, 1, g, 4);
       }
     }
@@ -598,11 +606,11 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
     mbar_init(in_full, 1); mbar_init(in_empty, 1);
-    mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_EPI_WARPS);
+    mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_BWD_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * TM_EPI_WARPS);
-      mbar_init(&dz_full[i], 2 * TM_EPI_WARPS);  mbar_init(&dz_empty[i], 1);
-      mbar_init(&dz_done[i], TM_EPI_WARPS);      mbar_init(&dzs_empty[i], 2);   // store warp + column-sum warp
+      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * TM_BWD_EPI_WARPS);
+      mbar_init(&dz_full[i], 2 * TM_BWD_EPI_WARPS);  mbar_init(&dz_empty[i], 1);
+      mbar_init(&dz_done[i], TM_BWD_EPI_WARPS);      mbar_init(&dzs_empty[i], 2);   // store warp + column-sum warp
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&w1_full[i], 1); mbar_init(&w1_empty[i], 1);
@@ -807,9 +815,12 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     if (warp == 2 && elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
   } else if (warp >= TM_BWD_EPI0) {
-    // ================================================================ epilogue warps
+    // ================================================================ epilogue warps: 8 warps, each owns TMEM lane quarter
+    // warp % 4 and 32 of the chunk's 64 columns (two 16-column slices).  Eight fat warps instead of sixteen thin ones: gelu'
+    // is a ~20-deep dependent chain per element pair, and with 640 threads (96 registers) ptxas serialised the pairs; with
+    // 384 threads (168 registers) it overlaps them, and every chunk costs half as many mbarrier operations.
     const int q = warp & 3;
-    const int cq = (warp - TM_BWD_EPI0) >> 2;
+    const int cq = (warp - TM_BWD_EPI0) >> 2;             // columns [32 cq, 32 cq + 32) of the chunk
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     const int ngrp = p.NT >> 4;
@@ -822,39 +833,48 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const int j = tm_chunk(pos, rot, NC);
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        const bool live = cq * 16 < n1;
+        const bool live0 = cq * 32 < n1, live1 = cq * 32 + 16 < n1;
         mbar_wait(&zd_full[zb], (g >> 1) & 1);
         tc_fence_after();
-        uint32_t vz[16], vh[16];
-        if (live && !(p.flags & 16)) {
-          tmem_ld_32x32b_x16(tmem_base + zb * TM_CH + cq * 16 + lane_addr, vz);
-          tmem_ld_32x32b_x16(tmem_base + 2 * TM_CH + zb * TM_CH + cq * 16 + lane_addr, vh);
-          tmem_ld_wait();
+        uint32_t vz[2][16], vh[2][16];
+        if (!(p.flags & 16)) {
+          const uint32_t az = tmem_base + zb * TM_CH + cq * 32 + lane_addr, ah = az + 2 * TM_CH;
+          if (live1) { tmem_ld_x16_pair_wait(az, az + 16, vz[0], vz[1]); tmem_ld_x16_pair_wait(ah, ah + 16, vh[0], vh[1]); }
+          else if (live0) tmem_ld_x16_pair_wait(az, ah, vz[0], vh[0]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
-        uint32_t o[8];
-        if (live && (p.flags & 1)) {
+        uint32_t o[2][8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(vz[2 * e]) + __uint_as_float(vh[2 * e]), __uint_as_float(vz[2 * e + 1]) + __uint_as_float(vh[2 * e + 1]));
-        } else if (live) {
-          const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 16);
+        for (int hh = 0; hh < 2; ++hh) {
+          if (!(hh ? live1 : live0)) continue;
+          if (p.flags & 1) {
 #pragma unroll
-          for (int e4 = 0; e4 < 4; ++e4) {
-            const float4 bv = bp[e4];
-            f32x2 gl, dg;
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4]) + bv.x, __uint_as_float(vz[4 * e4 + 1]) + bv.y), gl, dg);
-            o[2 * e4] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4]), __uint_as_float(vh[4 * e4 + 1]))));
-            gelu_erf_pair<true>(pack2(__uint_as_float(vz[4 * e4 + 2]) + bv.z, __uint_as_float(vz[4 * e4 + 3]) + bv.w), gl, dg);
-            o[2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[4 * e4 + 2]), __uint_as_float(vh[4 * e4 + 3]))));
+            for (int e = 0; e < 8; ++e)
+              o[hh][e] = pack_bf16x2(__uint_as_float(vz[hh][2 * e]) + __uint_as_float(vh[hh][2 * e]),
+                                     __uint_as_float(vz[hh][2 * e + 1]) + __uint_as_float(vh[hh][2 * e + 1]));
+          } else {
+            const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + cq * 32 + 16 * hh);
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 bv = bp[e4];
+              f32x2 gl, dg;
+              gelu_erf_pair<true>(pack2(__uint_as_float(vz[hh][4 * e4]) + bv.x, __uint_as_float(vz[hh][4 * e4 + 1]) + bv.y), gl, dg);
+              o[hh][2 * e4] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[hh][4 * e4]), __uint_as_float(vh[hh][4 * e4 + 1]))));
+              gelu_erf_pair<true>(pack2(__uint_as_float(vz[hh][4 * e4 + 2]) + bv.z, __uint_as_float(vz[hh][4 * e4 + 3]) + bv.w), gl, dg);
+              o[hh][2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[hh][4 * e4 + 2]), __uint_as_float(vh[hh][4 * e4 + 3]))));
+            }
           }
         }
         const int hb = p.nhb == 2 ? zb : 0;                        // dZ tile buffer (single-buffered when two do not fit)
         const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
         mbar_wait(&dz_empty[hb], hph);                             // G3 of the previous user of this buffer has read it
         mbar_wait(&dzs_empty[hb], hph);                            // ... and so have its TMA store and column sums
-        if (live && !(p.flags & 8)) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, cq, o);
+        if (!(p.flags & 8)) {
+          if (live0) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, 2 * cq, o[0]);
+          if (live1) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, 2 * cq + 1, o[1]);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -867,9 +887,9 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       mbar_wait(dx_full, it & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int grp = cq; grp < ngrp + 4; grp += 4) {
+      for (int grp = cq; grp < ngrp + 2; grp += 2) {
         const bool has = grp < ngrp;
-        const bool last = grp + 4 >= ngrp;
+        const bool last = grp + 2 >= ngrp;
         uint32_t v[16];
         if (has) {
           tmem_ld_32x32b_x16(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);

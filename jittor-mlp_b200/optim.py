@@ -16,15 +16,15 @@ import torch
 from . import _lib as L
 
 CHUNK = 32768          # == OPT_CHUNK in csrc/aux_sm100.cuh
-_CHUNK_DTYPE = np.dtype([("param", "<u8"), ("grad", "<u8"), ("state_off", "<i8"), ("n", "<i4"), ("reserved", "<i4")])
+_CHUNK_DTYPE = np.dtype([("param", "<u8"), ("grad", "<u8"), ("state_off", "<i8"), ("n", "<i4"), ("step", "<i4")])
 
 
 def build_table(entries):
-    """entries: iterable of (param_ptr, grad_ptr, state_off, numel) -> numpy structured array of vmlp_optim_chunk."""
+    """entries: iterable of (param_ptr, grad_ptr, state_off, numel, step) -> numpy structured array of vmlp_optim_chunk."""
     rows = []
-    for pp, gp, off, n in entries:
+    for pp, gp, off, n, step in entries:
         for s in range(0, n, CHUNK):
-            rows.append((pp + 2 * s, gp + 2 * s, off + s, min(CHUNK, n - s), 0))
+            rows.append((pp + 2 * s, gp + 2 * s, off + s, min(CHUNK, n - s), step))
     return np.array(rows, dtype=_CHUNK_DTYPE)
 
 
@@ -67,9 +67,16 @@ class _FusedBase(torch.optim.Optimizer):
         for p, _ in live:
             if p.grad.dtype != torch.bfloat16 or not p.grad.is_contiguous():
                 raise TypeError("gradients must be contiguous bf16 tensors")
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p, _ in live)
+        # torch.optim keeps one step counter PER PARAMETER (a tensor without a gradient skips the step and its bias
+        # corrections lag behind): the counter travels in the table; when all live tensors agree it is left 0 and the
+        # corrections come from the hyper-parameter block, so the cached table stays valid from step to step
+        steps = {int(self.state[p]["step"].item()) + 1 for p, _ in live}
+        uniform = len(steps) <= 1
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), 0 if uniform else int(self.state[p]["step"].item()) + 1)
+                    for p, _ in live)
+        st["uniform_step"] = steps.pop() if uniform and steps else None
         if key != st["key"]:
-            tab = build_table((p.data_ptr(), p.grad.data_ptr(), o, p.numel()) for p, o in live)
+            tab = build_table((pp, gp, o, p.numel(), t) for (pp, gp, t), (p, o) in zip(key, live))
             host = torch.from_numpy(tab.view(np.uint8).copy())
             dev = st["master"].device
             st["table"] = host.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else host
@@ -137,7 +144,7 @@ class FusedAdamW(_FusedBase):
 
     def _hyper(self, g, st, grad_scale):
         b1, b2 = g["betas"]
-        t = st["step"]
+        t = st.get("uniform_step") or st["step"]
         return L.OptimHyper(0, 0, g["lr"], b1, b2, g["eps"], g["weight_decay"], 1.0 - b1 ** t, math.sqrt(1.0 - b2 ** t),
                             grad_scale, 0.0)
 

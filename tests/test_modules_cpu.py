@@ -40,10 +40,11 @@ def test_constructor_signature_matches_reference(mod, cls):
 
 def test_optimizer_chunk_table_covers_every_element_once():
     from jittor_mlp_b200 import optim
-    tab = optim.build_table([(4096, 8192, 0, 70000), (1 << 20, 2 << 20, 70000, 5), (3 << 20, 4 << 20, 70008, 32768)])
+    tab = optim.build_table([(4096, 8192, 0, 70000, 0), (1 << 20, 2 << 20, 70000, 5, 3), (3 << 20, 4 << 20, 70008, 32768, 0)])
     assert [int(n) for n in tab["n"]] == [32768, 32768, 70000 - 65536, 5, 32768]
     assert int(tab["param"][1]) == 4096 + 2 * 32768 and int(tab["grad"][2]) == 8192 + 2 * 65536
     assert [int(o) for o in tab["state_off"]] == [0, 32768, 65536, 70000, 70008]
+    assert [int(t) for t in tab["step"]] == [0, 0, 0, 3, 0]
     assert tab.dtype.itemsize == 32           # == sizeof(vmlp_optim_chunk)
 
 

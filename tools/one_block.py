@@ -17,6 +17,7 @@ for _ in range(reps):
     y = m(x)
     y.backward(dy)
     m.zero_grad(set_to_none=True)
+    x.grad = None
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.cudart().cudaProfilerStart()          # ncu --profile-from-start off: exactly `reps` blocks are captured
@@ -25,6 +26,7 @@ for _ in range(reps):
     y = m(x)
     y.backward(dy)
     m.zero_grad(set_to_none=True)
+    x.grad = None
 e1.record()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()

@@ -1,9 +1,10 @@
-"""clock64 timeline of CTA 0 of the fused forward token kernel (bring-up): prints per global chunk the cycle stamps of
-the MMA warp and of the first epilogue warp relative to the first stamp.
-MMA events: 0 iteration start, 1 after xt_full, 2 after z_empty, 3 after wa_full, 4 G1 issued + committed,
-            5 after h_full, 6 after wb_full/u_empty, 7 G2 issued + committed
-EPI events: 0 chunk start, 1 after z_full, 2 Z loaded + z_empty arrive, 3 math done, 4 after h_empty, 5 after hs_empty,
-            6 tile written + fence, 7 h_full arrive"""
+"""clock64 timeline of CTA 0 of the fused forward token kernel: per global chunk g the cycle stamps of the issuer warps,
+the polling warp of the epilogue group that owns g, and the forwarding / store warp, relative to the first stamp.
+ISSUE events: 0 G1 loop top, 1 after z_empty + wa_full, 2 G1 issued + committed; 4 G2 loop top, 5 after h_full + wb_full,
+              6 G2 issued + committed
+EPI events:   0 chunk start, 1 after z_full + h_free (+ group barrier), 2 Z loaded, "consumed" signalled, 3 GELU done and
+              tile written, 4 "written" signalled
+FWD events:   0 "H(g) written" received, 1 h_full forwarded, tile stored, h_free released; 2 "Z(g) consumed" received"""
 import os
 import sys
 
@@ -26,7 +27,7 @@ torch.cuda.synchronize()
 L.lib().vmlp_tokmix_set_trace(0)
 t = trace.cpu()
 t0 = int(t[t > 0].min())
-for role, name in ((0, "MMA"), (1, "EPI")):
+for role, name in ((0, "ISSUE"), (1, "EPI"), (2, "FWD")):
     print(name)
     for g in range(40):
         row = [int(v) - t0 if v > 0 else -1 for v in t[role, g]]
