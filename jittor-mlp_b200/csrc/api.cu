@@ -472,12 +472,13 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   // as with it (the L2 -> SMEM stream is not the limiter), so a second hidden-tile buffer comes before ring depth.
   const int force_depth = [] { const char* e = getenv("VMLP_TM_DEPTH"); return e ? atoi(e) : 0; }();
   const int force_nhb = [] { const char* e = getenv("VMLP_TM_NHB"); return e ? atoi(e) : 0; }();
-  for (int nhb = 2; nhb >= (backward ? 1 : 2); --nhb) {   // forward: one hidden-tile buffer per epilogue group
+  // forward: three hidden-tile buffers (a group never waits for G2 of its own previous chunk), at least two
+  for (int nhb = backward ? 2 : 3; nhb >= (backward ? 1 : 2); --nhb) {
     if (force_nhb && nhb != force_nhb) continue;
     for (int depth = 4; depth >= 2; --depth) {
       if (force_depth && depth != force_depth) continue;
       const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 +
-                        p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);
+                        p.n_chunks * TM_CH * 4 * (backward ? 3 : 1) + (backward ? 0 : p.NT * 4);
       const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
       if (fixed + rings <= TM_SMEM_MAX) {
         p.s_wa = p.s_wb = depth;
@@ -554,6 +555,7 @@ int tokmix_bwd_impl(const void* xhat, const void* du, const void* w1_pad, const 
   if (Np < p.NT || (Np % 8)) return fail(VMLP_EINVAL, "tokmix_bwd: padded weight pitch %d < ceil16(N) = %d", Np, p.NT);
   p.b1 = (cbf)b1; p.out = (bf)dxhat; p.db1 = db1;
   if (const char* e = getenv("VMLP_TM_FLAGS")) p.flags = atoi(e);     // profiling experiments only
+  p.trace = g_tokmix_trace;
   CUtensorMap tX, tDU, tW1, tW2T, tW1T, tDZ;
   int rc;
   if ((rc = make_map(&tX, xhat, C, N, B, C, (long long)N * C, 64, p.NT))) return rc;

@@ -473,31 +473,32 @@ __device__ __forceinline__ float rcp_approx_v(float x) {
   asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// Four independent element pairs through the forward form of gelu_rcp16_pair with every step issued for all four before
-// the next one: the chain is 14 dependent operations deep (6 Horner steps, the reciprocal, 4 squarings, 2 more), and left
+// NP independent element pairs through the forward form of gelu_rcp16_pair with every step issued for all four before
+// the next one (NP = 8 in the token kernel): the chain is 14 dependent operations deep (6 Horner steps, the reciprocal, 4 squarings, 2 more), and left
 // to itself ptxas serialises the pairs to stay inside the register budget -- the epilogue warps then sit in fixed-latency
 // dependency stalls (ncu "wait": 2.4 warps per issue) instead of filling the FMA pipe.
-__device__ __forceinline__ void gelu_rcp16_x4(const f32x2 (&z)[4], f32x2 (&gelu)[4]) {
+template <int NP>
+__device__ __forceinline__ void gelu_rcp16_xn(const f32x2 (&z)[NP], f32x2 (&gelu)[NP]) {
   constexpr float B1 = 0.0705230784f * 0.70710678118654752f, B2 = 0.0422820123f * 0.5f,
                   B3 = 0.0092705272f * 0.35355339059327376f, B4 = 0.0001520143f * 0.25f,
                   B5 = 0.0002765672f * 0.17677669529663688f, B6 = 0.0000430638f * 0.125f;
-  f32x2 a[4], pp[4];
+  f32x2 a[NP], pp[NP];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) a[i] = abs2(z[i]);
+  for (int i = 0; i < NP; ++i) a[i] = abs2(z[i]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(VMLP_P2(B6), a[i], VMLP_P2(B5));
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(VMLP_P2(B6), a[i], VMLP_P2(B5));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B4));
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B4));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B3));
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B3));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B2));
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B2));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B1));
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(B1));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(1.0f));
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(pp[i], a[i], VMLP_P2(1.0f));
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < NP; ++i) {
     float p0, p1;
     unpack2(pp[i], p0, p1);
     pp[i] = pack2(rcp_approx_v(p0), rcp_approx_v(p1));
@@ -505,11 +506,11 @@ __device__ __forceinline__ void gelu_rcp16_x4(const f32x2 (&z)[4], f32x2 (&gelu)
 #pragma unroll
   for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pp[i] = mul2v(pp[i], pp[i]);
+    for (int i = 0; i < NP; ++i) pp[i] = mul2v(pp[i], pp[i]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pp[i] = fma2v(pp[i], VMLP_P2(-0.5f), VMLP_P2(0.5f));      // Phi(a) - 0.5
+  for (int i = 0; i < NP; ++i) pp[i] = fma2v(pp[i], VMLP_P2(-0.5f), VMLP_P2(0.5f));      // Phi(a) - 0.5
 #pragma unroll
-  for (int i = 0; i < 4; ++i) gelu[i] = fma2v(a[i], pp[i], mul2v(z[i], VMLP_P2(0.5f)));
+  for (int i = 0; i < NP; ++i) gelu[i] = fma2v(a[i], pp[i], mul2v(z[i], VMLP_P2(0.5f)));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2_f2(f32x2 v) {

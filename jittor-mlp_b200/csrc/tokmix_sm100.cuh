@@ -35,7 +35,7 @@
 //  * the GELU is a 14-deep (gelu': ~20-deep) dependent chain per element pair; with 640 threads ptxas had 96 registers
 //    and serialised the pairs (ncu: fixed-latency "wait" the top stall, FMA pipe 41 % busy, issue slots 50 % used)
 //    -> 8 epilogue warps with 168 registers instead of 16 with 96: same lanes, several pairs in flight per warp;
-//  * erf-GELU with a single MUFU per element (ptx.cuh: gelu_rcp16_x4) -- rcp + ex2 per element is 1024 MUFU cycles per
+//  * erf-GELU with a single MUFU per element (ptx.cuh: gelu_rcp16_xn) -- rcp + ex2 per element is 1024 MUFU cycles per
 //    chunk and SM, more than the chunk's 832 MMA cycles.
 #pragma once
 #include "ptx.cuh"
@@ -224,7 +224,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
   uint64_t* xt_full = bars + 0;     uint64_t* xt_empty = bars + 1;
   uint64_t* u_full = bars + 2;      uint64_t* u_empty = bars + 3;
   uint64_t* z_full = bars + 4;      uint64_t* z_empty = bars + 6;      // [2] each
-  uint64_t* h_full = bars + 8;      uint64_t* h_free = bars + 10;      // h_free: G2 and the TMA store have both read the tile
+  uint64_t* h_full = bars + 8;      uint64_t* h_free = bars + 11;      // [3] each; h_free: G2 and the TMA store have read the tile
   uint64_t* wa_full = bars + 16;    uint64_t* wa_empty = bars + 24;    // up to 8 stages each
   uint64_t* wb_full = bars + 32;    uint64_t* wb_empty = bars + 40;
   uint64_t* ro_full = bars + 48;    uint64_t* ro_done = bars + 49;
@@ -247,8 +247,10 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     mbar_init(ro_full, 1); mbar_init(ro_done, TM_FWD_EPI_WARPS);
     mbar_init(u_full, 1);  mbar_init(u_empty, 2 * TM_FWD_EPI_WARPS);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], 2);      // one forwarded arrival per CTA (warp 2)
-      mbar_init(&h_full[i], 2);  mbar_init(&h_free[i], 2);
+      mbar_init(&z_full[i], 1);  mbar_init(&z_empty[i], TM_FWD_EPI_WARPS);   // 4 warps of the owning group x 2 CTAs
+    }
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&h_full[i], 2);  mbar_init(&h_free[i], 2);       // one forwarded arrival per CTA; G2 commit + TMA store
     }
     for (int i = 0; i < 8; ++i) {
       mbar_init(&wa_full[i], 1); mbar_init(&wa_empty[i], 1);
@@ -354,11 +356,12 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
       const uint32_t idesc_g2 = umma_idesc_bf16(256, p.NT, 0, 0);
       uint32_t sb = 0, pb = 0;
       int j2 = 0, it2 = 0;
+      int hb = 0;                 // hidden-tile buffer of chunk t2 = t2 % nhb, hph = (t2 / nhb) & 1
+      uint32_t hph = 0;
       for (int t2 = 0; t2 < total; ++t2) {
-        const int hb = p.nhb == 2 ? (t2 & 1) : 0;
         if (lane == 0) tm_stamp(p, 0, t2, 4);
         if (j2 == 0) mbar_wait<32>(u_empty, (it2 & 1) ^ 1);
-        mbar_wait2<32>(&h_full[hb], (p.nhb == 2 ? (t2 >> 1) : t2) & 1, &wb_full[sb], pb);
+        mbar_wait2<32>(&h_full[hb], hph, &wb_full[sb], pb);
         if (lane == 0) tm_stamp(p, 0, t2, 5);
         tc_fence_after();
         if (elect_one_sync()) {
@@ -372,6 +375,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         if (lane == 0) tm_stamp(p, 0, t2, 6);
         if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
         if (++j2 == NC) { j2 = 0; ++it2; }
+        if (++hb == p.nhb) { hb = 0; hph ^= 1; }
       }
     }
   } else if (warp == 2) {
@@ -387,27 +391,44 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     };
     if (cluster_id < p.n_pairs && elect_one_sync()) load_residual(cluster_id);
     __syncwarp();
-    // "Z(g) has been read by the 4 warps of group g & 1" is forwarded as ONE arrival to the leader's z_empty; "H(g) has been
-    // written" is forwarded to h_full, the tile is stored and the buffer released.  At the end of an item the output tile.
+    // "H(g) has been written by the 4 warps of group g & 1" is forwarded as ONE arrival per CTA to the leader's h_full; the
+    // tile is stored (saved activation) and the buffer released once the store has READ it -- checked one chunk later
+    // (wait_read<1>), so that this warp never sits in a TMA wait while the next hand-off is due.  With three hidden-tile
+    // buffers the late release costs nothing.  At the end of an item the output tile.
+    int pend_hb = -1;                                      // buffer whose store was committed last and is not yet released
+    auto release_pending = [&](int keep) {                 // keep = stores that may still be reading (0 or 1)
+      if (pend_hb >= 0 && elect_one_sync()) {
+        if (keep) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        mbar_arrive(&h_free[pend_hb]);
+      }
+      __syncwarp();
+      pend_hb = -1;
+    };
+    int hbf = 0;
     auto forward_hw = [&](int g) {
       const int gi = g & 1;
       const int item = g / NC, j = g - item * NC;
       const TokTile t = tm_tile(p, cluster_id + item * num_clusters, cta_rank);
       named_bar_sync(TM_NB_HW + gi, 32 * (TM_FWD_EPI_WARPS / 2 + 1));
       if (lane == 0) tm_stamp(p, 2, g, 0);
+      const bool store = save_hidden && t.valid && !(p.flags & 2);
       if (elect_one_sync()) {
-        tm_arrive_leader(&h_full[gi], is_leader);
-        if (save_hidden && t.valid && !(p.flags & 2)) {
-          tma_store_3d(&tmH, smem + (s_h - s_base) + gi * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
+        tm_arrive_leader(&h_full[hbf], is_leader);
+        if (store) {
+          tma_store_3d(&tmH, smem + (s_h - s_base) + hbf * TM_HTILE, tm_chunk(j, rot, NC) * TM_CH, t.c0, t.b);
           tma_store_commit();
-          tma_store_wait_read<0>();
         }
-        mbar_arrive(&h_free[gi]);
       }
       __syncwarp();
+      // The release of buffer g - 1 comes AFTER this warp has passed the named barrier of chunk g, also when nothing is
+      // stored: a group can therefore never signal "written" for chunk g + 2 before its signal for chunk g has been
+      // consumed (a named barrier must not collect two generations of arrivals).
+      release_pending(store ? 1 : 0);                      // the PREVIOUS store has long finished reading
+      pend_hb = hbf;
+      if (++hbf == p.nhb) hbf = 0;
       if (lane == 0) tm_stamp(p, 2, g, 1);
-      if (j == NC - 1) {                                   // last chunk of an item: its output tile follows
-        mbar_wait<64>(ro_done, item & 1);
+      if (j == NC - 1) {                                   // last chunk of an item: its output tile follows (the hidden
+        mbar_wait<64>(ro_done, item & 1);                  // buffer of this chunk stays pending like any other one)
         if (elect_one_sync()) {
           if (t.valid) {
             tma_store_3d(&tmU, smem + (s_ro - s_base), t.c0, 0, t.b);     // rows >= N and channels >= C are clipped
@@ -419,17 +440,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         __syncwarp();
       }
     };
-    // H(g - 1) before Z(g): at an item boundary the group that owns chunk g first does its share of the previous item's
-    // output epilogue, which needs G2 of that item's last chunk, i.e. the forwarding of H(g - 1)
-    for (int g = 0; g <= total; ++g) {
-      if (g >= 1) forward_hw(g - 1);
-      if (g < total) {
-        named_bar_sync(TM_NB_ZE + (g & 1), 32 * (TM_FWD_EPI_WARPS / 2 + 1));
-        if (lane == 0) tm_stamp(p, 2, g, 2);
-        if (elect_one_sync()) tm_arrive_leader(&z_empty[g & 1], is_leader);
-        __syncwarp();
-      }
-    }
+    for (int g = 0; g < total; ++g) forward_hw(g);
+    release_pending(0);
     if (elect_one_sync()) tma_store_wait_all<0>();
     __syncwarp();
   } else if (warp >= TM_FWD_EPI0) {
@@ -449,6 +461,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
     const bool tr = (warp - TM_FWD_EPI0) % 4 == 0 && lane == 0;
     const bool poller = ((warp - TM_FWD_EPI0) & 3) == 0;   // the one warp of the group that polls the mbarriers
     int it = 0;                                           // item whose output epilogue this warp does next
+    int hb = gi % p.nhb;                                  // hidden-tile buffer of chunk g = g % nhb, phase (g / nhb) & 1
+    uint32_t hph = (gi / p.nhb) & 1;
     for (int g = gi; ; g += 2) {
       // ---- output epilogues of every item that ends before chunk g (or all remaining ones once g runs out)
       const int item_of_g = g < total ? g / NC : my_items;
@@ -505,7 +519,7 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
         if (tr) tm_stamp(p, 1, g, 0);
         // ONE warp of the group polls the mbarriers (Z(g) complete; hidden buffer free: G2 and the TMA store of its previous
         // user done), the named barrier releases the other seven: an mbarrier operation costs a warp 100-200 cycles
-        if (poller) mbar_wait2<0>(&z_full[gi], (g >> 1) & 1, &h_free[gi], ((g >> 1) & 1) ^ 1);
+        if (poller) mbar_wait2<0>(&z_full[gi], (g >> 1) & 1, &h_free[hb], hph ^ 1);
         named_bar_sync(TM_NB_START + gi, 32 * (TM_FWD_EPI_WARPS / 2));
         tc_fence_after();
         if (tr) tm_stamp(p, 1, g, 1);
@@ -517,7 +531,8 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
           if (n1 > 32) tmem_ld_x16_pair_wait(tmem_base + gi * TM_CH + 32 + lane_addr, tmem_base + gi * TM_CH + 48 + lane_addr, v[2], v[3]);
         }
         tc_fence_before();
-        named_bar_arrive(TM_NB_ZE + gi, 32 * (TM_FWD_EPI_WARPS / 2 + 1));   // warp 2 forwards "Z(g) consumed" to the G1 issuer
+        __syncwarp();
+        if (lane == 0) tm_arrive_leader(&z_empty[gi], is_leader);           // "Z(g) consumed": the G1 issuer may overwrite it
         if (tr) tm_stamp(p, 1, g, 2);
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
@@ -527,26 +542,24 @@ tokmix_fwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh   [B, N, C]
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = pack_bf16x2(__uint_as_float(v[hh][2 * e]), __uint_as_float(v[hh][2 * e + 1]));
           } else {
+            f32x2 zz[8], gl[8];                                     // 16 columns = 8 pairs in flight (gelu_rcp16_xn)
 #pragma unroll
-            for (int e8 = 0; e8 < 2; ++e8) {                       // 8 columns = 4 pairs per call (gelu_rcp16_x4)
-              const float4 b0 = lds_f4(s_b1 + (j * TM_CH + 16 * hh + 8 * e8) * 4);
-              const float4 b1v = lds_f4(s_b1 + (j * TM_CH + 16 * hh + 8 * e8 + 4) * 4);
-              const f32x2 zz[4] = {pack2(__uint_as_float(v[hh][8 * e8]) + b0.x, __uint_as_float(v[hh][8 * e8 + 1]) + b0.y),
-                                   pack2(__uint_as_float(v[hh][8 * e8 + 2]) + b0.z, __uint_as_float(v[hh][8 * e8 + 3]) + b0.w),
-                                   pack2(__uint_as_float(v[hh][8 * e8 + 4]) + b1v.x, __uint_as_float(v[hh][8 * e8 + 5]) + b1v.y),
-                                   pack2(__uint_as_float(v[hh][8 * e8 + 6]) + b1v.z, __uint_as_float(v[hh][8 * e8 + 7]) + b1v.w)};
-              f32x2 gl[4];
-              gelu_rcp16_x4(zz, gl);
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) o[4 * e8 + qq] = pack_bf16x2_f2(gl[qq]);
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const float4 bv = lds_f4(s_b1 + (j * TM_CH + 16 * hh + 4 * e4) * 4);
+              zz[2 * e4] = pack2(__uint_as_float(v[hh][4 * e4]) + bv.x, __uint_as_float(v[hh][4 * e4 + 1]) + bv.y);
+              zz[2 * e4 + 1] = pack2(__uint_as_float(v[hh][4 * e4 + 2]) + bv.z, __uint_as_float(v[hh][4 * e4 + 3]) + bv.w);
             }
+            gelu_rcp16_xn<8>(zz, gl);
+#pragma unroll
+            for (int qq = 0; qq < 8; ++qq) o[qq] = pack_bf16x2_f2(gl[qq]);
           }
-          if (!(p.flags & 8)) tm_store_hidden_row(s_h + gi * TM_HTILE, row, hh, o);
+          if (!(p.flags & 8)) tm_store_hidden_row(s_h + hb * TM_HTILE, row, hh, o);
         }
         if (tr) tm_stamp(p, 1, g, 3);
         fence_proxy_async_smem();
         named_bar_arrive(TM_NB_HW + gi, 32 * (TM_FWD_EPI_WARPS / 2 + 1));   // warp 2 forwards "H(g) written", stores the tile
         if (tr) tm_stamp(p, 1, g, 4);
+        hb += 2; if (hb >= p.nhb) { hb -= p.nhb; hph ^= 1; }                // next chunk of this group is g + 2
       }
     }
   }
@@ -600,7 +613,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
   const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
   float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + p.nhb * TM_HTILE);
-  float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
+  float* sdb = sb1 + p.n_chunks * TM_CH;          // partial sums of d b1, one array per helper warp, flushed once at the end
+  const uint32_t s_db = s_dz + p.nhb * TM_HTILE + p.n_chunks * TM_CH * 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmDU); tma_prefetch_desc(&tmW1);
@@ -622,6 +636,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_BWD_THREADS) {
     sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
     sdb[i] = 0.f;
+    sdb[p.n_chunks * TM_CH + i] = 0.f;
   }
   if (warp == 1) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
   tc_fence_before();
@@ -707,9 +722,11 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       int t1 = 0, t3 = 0;
       auto do_g12 = [&]() {       // ---- Z^T = Xh^T * W1chunk^T and dH^T = dU^T * W2[:, chunk]
         const int n1 = (tm_chunk(j1, rot, NC) == NC - 1) ? p.last_n1 : TM_CH;
+        if (lane == 0) tm_stamp(p, 0, t1, 0);
         if (j1 == 0) mbar_wait<32>(in_full, it1 & 1);
         const int zb = t1 & 1;
         mbar_wait<32>(&zd_empty[zb], ((t1 >> 1) & 1) ^ 1);
+        if (lane == 0) tm_stamp(p, 0, t1, 1);
         mbar_wait<32>(&w1_full[sa], pa);
         tc_fence_after();
         if (elect_one_sync()) {
@@ -727,13 +744,16 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
           if (j1 == NC - 1) umma_commit_2cta_mc(in_empty);
         }
         __syncwarp();
+        if (lane == 0) tm_stamp(p, 0, t1, 2);
         if (++sa == (uint32_t)p.s_wa) { sa = 0; pa ^= 1; }
         if (++j1 == NC) { j1 = 0; ++it1; }
         ++t1;
       };
       auto do_g3 = [&]() {        // ---- dXh^T (+)= dZ^T * W1[chunk, :]
         const int hb = p.nhb == 2 ? (t3 & 1) : 0;
+        if (lane == 0) tm_stamp(p, 0, t3, 4);
         mbar_wait<32>(&dz_full[hb], (p.nhb == 2 ? (t3 >> 1) : t3) & 1);
+        if (lane == 0) tm_stamp(p, 0, t3, 5);
         mbar_wait<32>(&w3_full[sb], pb);
         if (j3 == 0) mbar_wait<32>(dx_empty, (it3 & 1) ^ 1);
         tc_fence_after();
@@ -745,6 +765,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
           if (j3 == NC - 1) umma_commit_2cta_mc(dx_full);
         }
         __syncwarp();
+        if (lane == 0) tm_stamp(p, 0, t3, 6);
         if (++sb == (uint32_t)p.s_wb) { sb = 0; pb ^= 1; }
         if (++j3 == NC) { j3 = 0; ++it3; }
         ++t3;
@@ -772,6 +793,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const int hb = p.nhb == 2 ? (g & 1) : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        if (warp == 2 && lane == 0) tm_stamp(p, 2, g, 0);
         if (warp == 2 && elect_one_sync()) {
           if (t.valid && !(p.flags & 2)) {
             tma_store_3d(&tmDZ, smem + (s_dz - s_base) + hb * TM_HTILE, j * TM_CH, t.c0, t.b);
@@ -800,16 +822,25 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
             acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
           }
           if (rs == 0) {           // columns beyond Ds hold stale or zero data and are never flushed
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&sdb[j * TM_CH + kc * 8 + e], acc[e]);
+            // each helper warp owns one partial-sum array and each lane 8 columns of it: a plain read-modify-write.  (Shared
+            // memory has no native fp32 add: atomicAdd / red.shared compile to an ATOMS.CAS spin loop -- the clock64
+            // timeline showed 3100 cycles per tile here, with the epilogue's next write waiting behind it.)
+            const uint32_t a = s_db + (((warp - 2) * p.n_chunks + j) * TM_CH + kc * 8) * 4;
+            float4 s0 = lds_f4(a), s1 = lds_f4(a + 16);
+            s0.x += acc[0]; s0.y += acc[1]; s0.z += acc[2]; s0.w += acc[3];
+            s1.x += acc[4]; s1.y += acc[5]; s1.z += acc[6]; s1.w += acc[7];
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a), "f"(s0.x), "f"(s0.y), "f"(s0.z), "f"(s0.w) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(a + 16), "f"(s1.x), "f"(s1.y), "f"(s1.z), "f"(s1.w) : "memory");
           }
         }
         __syncwarp();
+        if (warp == 2 && lane == 0) tm_stamp(p, 2, g, 1);
         if (elect_one_sync()) {
           if (warp == 2) tma_store_wait_read<0>();
           mbar_arrive(&dzs_empty[hb]);
         }
         __syncwarp();
+        if (warp == 2 && lane == 0) tm_stamp(p, 2, g, 2);
       }
     }
     if (warp == 2 && elect_one_sync()) tma_store_wait_all<0>();
@@ -834,8 +865,11 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const int zb = g & 1;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         const bool live0 = cq * 32 < n1, live1 = cq * 32 + 16 < n1;
+        const bool tr = warp == TM_BWD_EPI0 && lane == 0;
+        if (tr) tm_stamp(p, 1, g, 0);
         mbar_wait(&zd_full[zb], (g >> 1) & 1);
         tc_fence_after();
+        if (tr) tm_stamp(p, 1, g, 1);
         uint32_t vz[2][16], vh[2][16];
         if (!(p.flags & 16)) {
           const uint32_t az = tmem_base + zb * TM_CH + cq * 32 + lane_addr, ah = az + 2 * TM_CH;
@@ -845,6 +879,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         tc_fence_before();
         __syncwarp();
         if (lane == 0) tm_arrive_leader(&zd_empty[zb], is_leader);
+        if (tr) tm_stamp(p, 1, g, 2);
         uint32_t o[2][8];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -869,8 +904,10 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         }
         const int hb = p.nhb == 2 ? zb : 0;                        // dZ tile buffer (single-buffered when two do not fit)
         const uint32_t hph = ((p.nhb == 2 ? (g >> 1) : g) & 1) ^ 1;
+        if (tr) tm_stamp(p, 1, g, 3);
         mbar_wait(&dz_empty[hb], hph);                             // G3 of the previous user of this buffer has read it
         mbar_wait(&dzs_empty[hb], hph);                            // ... and so have its TMA store and column sums
+        if (tr) tm_stamp(p, 1, g, 4);
         if (!(p.flags & 8)) {
           if (live0) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, 2 * cq, o[0]);
           if (live1) tm_store_hidden_row(s_dz + hb * TM_HTILE, row, 2 * cq + 1, o[1]);
@@ -881,6 +918,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
           tm_arrive_leader(&dz_full[hb], is_leader);
           mbar_arrive(&dz_done[hb]);
         }
+        if (tr) tm_stamp(p, 1, g, 5);
       }
       // ---- output: dXh[b, n, ch] = dXh^T[ch, n]
       __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
@@ -923,7 +961,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     tmem_dealloc_2cta(tmem_base, 512);
   }
   if (p.db1 != nullptr)
-    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i]);
+    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i] + sdb[p.n_chunks * TM_CH + i]);
 }
 
 // W [rows, cols] -> padded copy [rows, ld] (zero fill) and/or transposed copy [cols, ldt] (zero fill): the K-major weight
