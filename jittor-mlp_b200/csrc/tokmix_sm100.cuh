@@ -47,7 +47,7 @@ constexpr int TM_CH = 64;                              // hidden chunk (UMMA N o
 constexpr int TM_FWD_EPI0 = 4;                                   // forward: 4 service warps + 8 epilogue warps
 constexpr int TM_FWD_EPI_WARPS = 8;                              // 384 threads -> up to 168 registers each (see the epilogue)
 constexpr int TM_FWD_THREADS = 32 * (TM_FWD_EPI0 + TM_FWD_EPI_WARPS);
-constexpr int TM_NB_START = 1, TM_NB_ZE = 3, TM_NB_HW = 5;          // named (hardware) barrier ids (+ group), see the epilogue
+constexpr int TM_NB_START = 1, TM_NB_ZE = 3, TM_NB_HW = 5, TM_NB_DZ = 7;          // named (hardware) barrier ids (+ group), see the epilogue
 constexpr int TM_BWD_EPI0 = 4;                                   // backward: 4 service warps + 8 epilogue warps
 constexpr int TM_BWD_EPI_WARPS = 8;
 constexpr int TM_BWD_THREADS = 32 * (TM_BWD_EPI0 + TM_BWD_EPI_WARPS);
@@ -792,7 +792,11 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         const int j = tm_chunk(pos, rot, NC);
         const int hb = p.nhb == 2 ? (g & 1) : 0;
         const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
-        mbar_wait<64>(&dz_done[hb], (p.nhb == 2 ? (g >> 1) : g) & 1);
+        // "tile written" comes over a hardware named barrier (8 epilogue warps arrive, the 2 helper warps sync): the
+        // helpers sit on the critical path while there is a single dZ buffer -- the epilogue's next write waits for them --
+        // and an mbarrier poll with back-off woke them ~1100 cycles late (clock64 timeline), without back-off it steals
+        // issue slots from the math warps
+        named_bar_sync(TM_NB_DZ + hb, 32 * (TM_BWD_EPI_WARPS + 2));
         if (warp == 2 && lane == 0) tm_stamp(p, 2, g, 0);
         if (warp == 2 && elect_one_sync()) {
           if (t.valid && !(p.flags & 2)) {
@@ -914,10 +918,8 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          tm_arrive_leader(&dz_full[hb], is_leader);
-          mbar_arrive(&dz_done[hb]);
-        }
+        if (lane == 0) tm_arrive_leader(&dz_full[hb], is_leader);
+        named_bar_arrive(TM_NB_DZ + hb, 32 * (TM_BWD_EPI_WARPS + 2));
         if (tr) tm_stamp(p, 1, g, 5);
       }
       // ---- output: dXh[b, n, ch] = dXh^T[ch, n]
