@@ -35,6 +35,10 @@ PRESETS = {
     "hire_t": ("HireMLP", dict(depth=[2, 2, 4, 2]), None, 2.832, 0.0590),
     "s2mlpv1_deep": ("S2MLPv1_deep", dict(), None, 20.93, 0.1156),
     "convmixer_768_32": ("ConvMixer", dict(dim=768, depth=32, kernel_size=7, patch_size=7), None, 41.24, 0.2312),
+    # SURVEY.md row f2, the geometry of compare.py:90-99: 14 x 28 positions, per block 2*448*224^2 + 2*224*448^2 (H / W
+    # permute-MLPs) + 2 * 2*392*256^2 (C branch, proj) + 4*392*256*1024 (channel MLP) = 648.7 MFLOP/img
+    "vip_s": ("ViP", dict(image_size=(224, 224), patch_size=(16, 8), d_model=256, depth=30, segments=16, weighted=True), None,
+              19.54, 0.0771),
 }
 METRIC = "images/sec fwd+bwd MLP-Mixer-B/16 224px"
 
@@ -260,6 +264,7 @@ STAGES = {
     "s2mlpv1_deep": [(14 * 14, 384, 36, None, 6)],
     "gmlp_s": [(196, 256, 30, 0.5804, 27)],
     "resmlp_24": [(196, 384, 24, 0.4919, 8)],
+    "vip_s": [(392, 256, 30, 0.6487, 12)],      # R x, W t[3C]=3, R t=3, W o, R o, R x, W x1, R x1, W y (hidden on chip)
 }
 
 

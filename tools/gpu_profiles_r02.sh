@@ -8,7 +8,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
 python tools/summarize_launches.py gpurun_out/r02_launches_mixer_b16.csv 16
 python tools/step_timeline.py mixer_b16 256 1 > gpurun_out/r02_timeline_mixer_b16.log 2>&1; head -16 gpurun_out/r02_timeline_mixer_b16.log
 : > gpurun_out/r02_bench_models.jsonl
-for m in ${MODELS:-mixer_l16 resmlp_24 gmlp_s as_mlp_t s2mlpv2 hire_t s2mlpv1_deep convmixer_768_32}; do
+for m in ${MODELS:-mixer_l16 resmlp_24 gmlp_s as_mlp_t s2mlpv2 hire_t s2mlpv1_deep convmixer_768_32 vip_s}; do
   python bench.py --model $m --no-cpu-baseline --steps 10 2>/dev/null | grep '^{' >> gpurun_out/r02_bench_models.jsonl
   tail -1 gpurun_out/r02_bench_models.jsonl | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$m', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'] if d.get('roofline') else None, d['clocks']['sm_mhz'])"
 done
