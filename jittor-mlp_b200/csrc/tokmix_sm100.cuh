@@ -791,7 +791,6 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
       for (int pos = 0; pos < NC; ++pos, ++g) {
         const int j = tm_chunk(pos, rot, NC);
         const int hb = p.nhb == 2 ? (g & 1) : 0;
-        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
         // "tile written" comes over a hardware named barrier (8 epilogue warps arrive, the 2 helper warps sync): the
         // helpers sit on the critical path while there is a single dZ buffer -- the epilogue's next write waits for them --
         // and an mbarrier poll with back-off woke them ~1100 cycles late (clock64 timeline), without back-off it steals
