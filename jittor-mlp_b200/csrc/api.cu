@@ -472,21 +472,27 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   // as with it (the L2 -> SMEM stream is not the limiter), so a second hidden-tile buffer comes before ring depth.
   const int force_depth = [] { const char* e = getenv("VMLP_TM_DEPTH"); return e ? atoi(e) : 0; }();
   const int force_nhb = [] { const char* e = getenv("VMLP_TM_NHB"); return e ? atoi(e) : 0; }();
+  const int bias_bytes = p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);   // b1 (+ d b1 sums | b2)
+  auto finish = [&](int nhb, int s_wa, int s_wb) -> int {
+    const int bytes = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 + bias_bytes +
+                      s_wa * p.wa_stage * (backward ? 2 : 1) + s_wb * p.wb_stage;
+    if (bytes > TM_SMEM_MAX) return 0;
+    p.s_wa = s_wa; p.s_wb = s_wb; p.nhb = nhb;
+    // never less than half an SM's shared memory: one CTA per SM, so the 512-column TMEM allocation of a CTA pair can
+    // never wait for a co-resident CTA of another pair (allocation order across two SMs could deadlock)
+    return bytes > 120 * 1024 ? bytes : 120 * 1024;
+  };
+  // backward with TWO dZ buffers = ping-pong epilogue groups (paid for with a one-stage W1^T ring).  Measured SLOWER at the
+  // Mixer shapes (385 vs 275 us): one math warp per scheduler at a time cannot fill the FMA / MUFU pipes with gelu' chains,
+  // two (lock step) do better.  Kept selectable for experiments: VMLP_TM_NHB=2.
+  if (backward && !force_depth && force_nhb == 2)
+    if (int r = finish(2, 2, 1)) return r;
   // forward: three hidden-tile buffers (a group never waits for G2 of its own previous chunk), at least two
-  for (int nhb = backward ? 2 : 3; nhb >= (backward ? 1 : 2); --nhb) {
+  for (int nhb = backward ? 1 : 3; nhb >= (backward ? 1 : 2); --nhb) {
     if (force_nhb && nhb != force_nhb) continue;
     for (int depth = 4; depth >= 2; --depth) {
       if (force_depth && depth != force_depth) continue;
-      const int fixed = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 +
-                        p.n_chunks * TM_CH * 4 * (backward ? 3 : 1) + (backward ? 0 : p.NT * 4);
-      const int rings = depth * (p.wa_stage * (backward ? 2 : 1) + p.wb_stage);
-      if (fixed + rings <= TM_SMEM_MAX) {
-        p.s_wa = p.s_wb = depth;
-        p.nhb = nhb;
-        // never less than half an SM's shared memory: one CTA per SM, so the 512-column TMEM allocation of a CTA pair can
-        // never wait for a co-resident CTA of another pair (allocation order across two SMs could deadlock)
-        return fixed + rings > 120 * 1024 ? fixed + rings : 120 * 1024;
-      }
+      if (int r = finish(nhb, depth, depth)) return r;
     }
   }
   return 0;

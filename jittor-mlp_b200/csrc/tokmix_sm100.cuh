@@ -613,7 +613,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
   const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
   float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + p.nhb * TM_HTILE);
-  float* sdb = sb1 + p.n_chunks * TM_CH;          // partial sums of d b1, one array per helper warp, flushed once at the end
+  float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
   const uint32_t s_db = s_dz + p.nhb * TM_HTILE + p.n_chunks * TM_CH * 4;
 
   if (warp == 0 && lane == 0) {
@@ -621,9 +621,10 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     tma_prefetch_desc(&tmW2T); tma_prefetch_desc(&tmW1T); tma_prefetch_desc(&tmDZ);
     mbar_init(in_full, 1); mbar_init(in_empty, 1);
     mbar_init(dx_full, 1); mbar_init(dx_empty, 2 * TM_BWD_EPI_WARPS);
+    const int per_chunk = p.nhb == 2 ? TM_BWD_EPI_WARPS / 2 : TM_BWD_EPI_WARPS;   // epilogue warps that work on one chunk
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * TM_BWD_EPI_WARPS);
-      mbar_init(&dz_full[i], 2 * TM_BWD_EPI_WARPS);  mbar_init(&dz_empty[i], 1);
+      mbar_init(&zd_full[i], 1);  mbar_init(&zd_empty[i], 2 * per_chunk);
+      mbar_init(&dz_full[i], 2 * per_chunk);  mbar_init(&dz_empty[i], 1);
       mbar_init(&dz_done[i], TM_BWD_EPI_WARPS);      mbar_init(&dzs_empty[i], 2);   // store warp + column-sum warp
     }
     for (int i = 0; i < 4; ++i) {
@@ -636,7 +637,6 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_BWD_THREADS) {
     sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
     sdb[i] = 0.f;
-    sdb[p.n_chunks * TM_CH + i] = 0.f;
   }
   if (warp == 1) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
   tc_fence_before();
@@ -782,20 +782,20 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     // ================================================================ helper warps: warp 2 stores the dZ^T tile by TMA;
     // both sum the tile's columns over their 64 channel rows (d b1[m] = sum over (b, c) of dZ): lane l owns hidden
     // columns 2l, 2l+1 of the chunk and reads one 32-bit word per row (the 16-byte chunk index is un-swizzled per row).
-    const int r0 = (warp - 2) * 64;
-    const uint32_t kc = lane & 7;            // 16-byte chunk = eight hidden columns
-    const int rs = lane >> 3;                // row phase: rows r0 + rs + 4 i
+    // warp 2 owns hidden columns 0..31 of the tile, warp 3 columns 32..63 (all 128 channel rows each): one partial-sum array
+    const uint32_t kc = (lane & 3) + 4 * (warp - 2);   // 16-byte chunk = eight hidden columns
+    const int rs = lane >> 2;                          // row phase: rows rs + 8 i
+    const int nb_threads = 32 * ((p.nhb == 2 ? TM_BWD_EPI_WARPS / 2 : TM_BWD_EPI_WARPS) + 2);
     int g = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
       const TokTile t = tm_tile(p, pair, cta_rank);
       for (int pos = 0; pos < NC; ++pos, ++g) {
         const int j = tm_chunk(pos, rot, NC);
         const int hb = p.nhb == 2 ? (g & 1) : 0;
-        // "tile written" comes over a hardware named barrier (8 epilogue warps arrive, the 2 helper warps sync): the
-        // helpers sit on the critical path while there is a single dZ buffer -- the epilogue's next write waits for them --
-        // and an mbarrier poll with back-off woke them ~1100 cycles late (clock64 timeline), without back-off it steals
-        // issue slots from the math warps
-        named_bar_sync(TM_NB_DZ + hb, 32 * (TM_BWD_EPI_WARPS + 2));
+        // "tile written" comes over a hardware named barrier (the epilogue warps of the chunk arrive, the 2 helper warps
+        // sync): an mbarrier poll with back-off woke the helpers ~1100 cycles late (clock64 timeline), without back-off it
+        // steals issue slots from the math warps
+        named_bar_sync(TM_NB_DZ + hb, nb_threads);
         if (warp == 2 && lane == 0) tm_stamp(p, 2, g, 0);
         if (warp == 2 && elect_one_sync()) {
           if (t.valid && !(p.flags & 2)) {
@@ -805,30 +805,29 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         }
         __syncwarp();
         if (t.valid && !(p.flags & 4)) {
-          // one LDS.128 per row, eight independent fp32 accumulators, two shuffle steps fold the four row phases (the first
-          // version -- one 32-bit word per row and lane, two serial 64-term chains -- cost 60 us of the kernel's 316: with a
-          // single dZ buffer the epilogue's next write waits for these sums)
+          // one LDS.128 per row, eight independent fp32 accumulators, three shuffle steps fold the eight row phases
           const uint32_t tb = s_dz + hb * TM_HTILE;
           float acc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll 8
           for (int i = 0; i < 16; ++i) {
-            const int r = r0 + rs + 4 * i;
+            const int r = rs + 8 * i;
             const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
             acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
             acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 4);
             acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
             acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
           }
           if (rs == 0) {           // columns beyond Ds hold stale or zero data and are never flushed
-            // each helper warp owns one partial-sum array and each lane 8 columns of it: a plain read-modify-write.  (Shared
-            // memory has no native fp32 add: atomicAdd / red.shared compile to an ATOMS.CAS spin loop -- the clock64
-            // timeline showed 3100 cycles per tile here, with the epilogue's next write waiting behind it.)
-            const uint32_t a = s_db + (((warp - 2) * p.n_chunks + j) * TM_CH + kc * 8) * 4;
+            // each (helper warp, lane) owns 8 columns of the partial-sum array: a plain read-modify-write.  (Shared memory
+            // has no native fp32 add: atomicAdd / red.shared compile to an ATOMS.CAS spin loop -- the clock64 timeline showed
+            // 3100 cycles per tile here, with the epilogue's next write waiting behind it.)
+            const uint32_t a = s_db + (j * TM_CH + kc * 8) * 4;
             float4 s0 = lds_f4(a), s1 = lds_f4(a + 16);
             s0.x += acc[0]; s0.y += acc[1]; s0.z += acc[2]; s0.w += acc[3];
             s1.x += acc[4]; s1.y += acc[5]; s1.z += acc[6]; s1.w += acc[7];
@@ -853,6 +852,116 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     // warp % 4 and 32 of the chunk's 64 columns (two 16-column slices).  Eight fat warps instead of sixteen thin ones: gelu'
     // is a ~20-deep dependent chain per element pair, and with 640 threads (96 registers) ptxas serialised the pairs; with
     // 384 threads (168 registers) it overlaps them, and every chunk costs half as many mbarrier operations.
+    if (p.nhb == 2) {
+      // ---------------------------------------------------------------- ping-pong form (two dZ buffers): two groups of 4
+      // warps on ALTERNATE chunks (group = chunk parity = Z / dH buffer = dZ buffer), a warp does all 64 columns of its chunk
+      // in two halves of 32.  While one group computes, the other one is in its load / write / fence / barrier phases, and
+      // neither G3 nor the helper warps of a chunk are in the way of the NEXT chunk's write.
+      const int q = warp & 3;
+      const int gi = (warp - TM_BWD_EPI0) >> 2;
+      const int row = q * 32 + lane;
+      const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+      const int ngrp = p.NT >> 4;
+      const bool tr = (warp - TM_BWD_EPI0) % 4 == 0 && lane == 0;
+      int my_items = 0;
+      for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) ++my_items;
+      const int total = my_items * NC;
+      int it = 0;
+      for (int g = gi; ; g += 2) {
+        const int item_of_g = g < total ? g / NC : my_items;
+        for (; it < item_of_g; ++it) {
+          // ---- output of item `it`: dXh[b, n, ch] = dXh^T[ch, n]; the two warps of a lane quarter take alternate token groups
+          const TokTile t = tm_tile(p, cluster_id + it * num_clusters, cta_rank);
+          const int ch = t.c0 + row;
+          const bool ch_ok = t.valid && ch < p.C;
+          __nv_bfloat16* obase = p.out + ((long long)t.b * p.N) * p.C + ch;
+          mbar_wait(dx_full, it & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int grp = gi; grp < ngrp + 2; grp += 2) {
+            const bool has = grp < ngrp;
+            const bool last = grp + 2 >= ngrp;
+            uint32_t v[16];
+            if (has) tmem_ld_x16_wait(tmem_base + 4 * TM_CH + grp * 16 + lane_addr, v);
+            if (last) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) tm_arrive_leader(dx_empty, is_leader);
+            }
+            if (has && ch_ok) {
+              __nv_bfloat16* po = obase + (long long)(grp * 16) * p.C;
+#pragma unroll
+              for (int i = 0; i < 16; ++i, po += p.C)
+                if (grp * 16 + i < p.N) stg_u16(po, bf16_bits(__uint_as_float(v[i])));
+            }
+            if (last) break;
+          }
+        }
+        if (g >= total) break;
+        const int j = tm_chunk(g - item_of_g * NC, rot, NC);
+        const int n1 = (j == NC - 1) ? p.last_n1 : TM_CH;
+        const TokTile t = tm_tile(p, cluster_id + item_of_g * num_clusters, cta_rank);
+        (void)t;
+        if (tr) tm_stamp(p, 1, g, 0);
+        mbar_wait(&zd_full[gi], (g >> 1) & 1);
+        tc_fence_after();
+        if (tr) tm_stamp(p, 1, g, 1);
+        uint32_t o[4][8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const bool live0 = half * 32 < n1, live1 = half * 32 + 16 < n1;
+          uint32_t vz[2][16], vh[2][16];
+          if (!(p.flags & 16)) {
+            const uint32_t az = tmem_base + gi * TM_CH + half * 32 + lane_addr, ah = az + 2 * TM_CH;
+            if (live1) { tmem_ld_x16_pair_wait(az, az + 16, vz[0], vz[1]); tmem_ld_x16_pair_wait(ah, ah + 16, vh[0], vh[1]); }
+            else if (live0) tmem_ld_x16_pair_wait(az, ah, vz[0], vh[0]);
+          }
+          if (half == 1) {                                           // Z / dH of this chunk are in registers: G1 / G2 may refill
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tm_arrive_leader(&zd_empty[gi], is_leader);
+            if (tr) tm_stamp(p, 1, g, 2);
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (!(hh ? live1 : live0)) continue;
+            uint32_t (&oo)[8] = o[2 * half + hh];
+            if (p.flags & 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                oo[e] = pack_bf16x2(__uint_as_float(vz[hh][2 * e]) + __uint_as_float(vh[hh][2 * e]),
+                                    __uint_as_float(vz[hh][2 * e + 1]) + __uint_as_float(vh[hh][2 * e + 1]));
+            } else {
+              const float4* bp = reinterpret_cast<const float4*>(sb1 + j * TM_CH + half * 32 + 16 * hh);
+#pragma unroll
+              for (int e4 = 0; e4 < 4; ++e4) {
+                const float4 bv = bp[e4];
+                f32x2 gl, dg;
+                gelu_erf_pair<true>(pack2(__uint_as_float(vz[hh][4 * e4]) + bv.x, __uint_as_float(vz[hh][4 * e4 + 1]) + bv.y), gl, dg);
+                oo[2 * e4] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[hh][4 * e4]), __uint_as_float(vh[hh][4 * e4 + 1]))));
+                gelu_erf_pair<true>(pack2(__uint_as_float(vz[hh][4 * e4 + 2]) + bv.z, __uint_as_float(vz[hh][4 * e4 + 3]) + bv.w), gl, dg);
+                oo[2 * e4 + 1] = pack_bf16x2_f2(mul2(dg, pack2(__uint_as_float(vh[hh][4 * e4 + 2]), __uint_as_float(vh[hh][4 * e4 + 3]))));
+              }
+            }
+          }
+        }
+        const uint32_t hph = ((g >> 1) & 1) ^ 1;
+        if (tr) tm_stamp(p, 1, g, 3);
+        mbar_wait(&dz_empty[gi], hph);                               // G3 of chunk g - 2 has read this buffer
+        mbar_wait(&dzs_empty[gi], hph);                              // ... and so have its TMA store and column sums
+        if (tr) tm_stamp(p, 1, g, 4);
+        if (!(p.flags & 8)) {
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl)
+            if (sl * 16 < n1) tm_store_hidden_row(s_dz + gi * TM_HTILE, row, sl, o[sl]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tm_arrive_leader(&dz_full[gi], is_leader);
+        named_bar_arrive(TM_NB_DZ + gi, 32 * (TM_BWD_EPI_WARPS / 2 + 2));
+        if (tr) tm_stamp(p, 1, g, 5);
+      }
+    } else {
     const int q = warp & 3;
     const int cq = (warp - TM_BWD_EPI0) >> 2;             // columns [32 cq, 32 cq + 32) of the chunk
     const int row = q * 32 + lane;
@@ -953,6 +1062,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         if (last) break;
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -962,7 +1072,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     tmem_dealloc_2cta(tmem_base, 512);
   }
   if (p.db1 != nullptr)
-    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i] + sdb[p.n_chunks * TM_CH + i]);
+    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i]);
 }
 
 // W [rows, cols] -> padded copy [rows, ld] (zero fill) and/or transposed copy [cols, ldt] (zero fill): the K-major weight

@@ -41,11 +41,14 @@ class GraphedStep:
         with torch.cuda.stream(side):                      # warm-up off the default stream (allocator, lazy inits)
             for _ in range(warmup):
                 model.zero_grad(set_to_none=True)
+                if ddp is not None:
+                    ddp.begin_static_capture()             # the LAST warm-up step's buckets size the gradient arena
                 step_fn(self.static_x)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         model.zero_grad(set_to_none=True)
         if ddp is not None:
+            ddp.plan_arena()                               # one flat buffer for all buckets, sized from the warm-up step
             ddp.begin_static_capture()                     # start the bucket list afresh: these are the graph's buffers
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.static_loss = step_fn(self.static_x)

@@ -106,10 +106,19 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, add=None):
     return dx, dg, db
 
 
-def cast_f32_to_bf16(src):
-    dst = torch.empty(src.shape, dtype=BF16, device=src.device)
+def cast_f32_to_bf16(src, out=None):
+    dst = torch.empty(src.shape, dtype=BF16, device=src.device) if out is None else out
     L.check(L.lib().vmlp_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), L.stream_ptr()))
     return dst
+
+
+def _grad_bucket(flat32):
+    """fp32 flat accumulator of a block -> its flat bf16 gradient bucket.  Under a data-parallel CUDA-graph capture the
+    bucket is a slice of the step's ONE gradient arena (dp.DataParallel.take), so the exchange is a single all-reduce."""
+    from . import dp
+    d = dp.active()
+    out = d.take(flat32.numel(), flat32.device) if d is not None else None
+    return cast_f32_to_bf16(flat32, out)
 
 
 # --------------------------------------------------------------------------------------------- MLP-Mixer block
@@ -173,7 +182,7 @@ class MixerBlockFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         L.check(lib.vmlp_mixer_block_bwd(ctypes.byref(p), x.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                                          ctypes.byref(s), grads.data_ptr(), ws.data_ptr(), n_ws, L.stream_ptr()))
-        gb = cast_f32_to_bf16(grads)
+        gb = _grad_bucket(grads)
         from . import dp
         if dp.active() is not None:       # data parallel: average this block's gradients while backward continues
             dp.active().reduce_bucket_async(gb, params)
@@ -272,7 +281,7 @@ def pad_rows(w2d):
 
 def _finish_grads(flat32, params):
     """fp32 flat accumulator -> one flat bf16 buffer (DP bucket) -> per-parameter views."""
-    gb = cast_f32_to_bf16(flat32)
+    gb = _grad_bucket(flat32)
     from . import dp
     if dp.active() is not None:
         dp.active().reduce_bucket_async(gb, params)

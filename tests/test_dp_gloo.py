@@ -88,6 +88,9 @@ class _FlatLinearFn(torch.autograd.Function):
         from jittor_mlp_b200 import dp
         x, w, b = ctx.saved_tensors
         flat = torch.cat([(dy.t() @ x).flatten(), dy.sum(0)])
+        arena = dp.active().take(flat.numel(), flat.device) if dp.active() is not None else None
+        if arena is not None:                          # graph-mode capture with a planned gradient arena
+            flat = arena.copy_(flat)
         if dp.active() is not None:
             dp.active().reduce_bucket_async(flat, (w, b))
             for work, _ in dp.active()._pending:      # a fast network: the collective lands before AccumulateGrad runs
@@ -205,5 +208,76 @@ def test_static_buffers_of_a_captured_step_are_exchanged_once():
     ref = {"w": w.grad, "b": b.grad, "head.weight": head.weight.grad, "head.bias": head.bias.grad}
     for rank, n_static, grads in res:
         assert n_static == 3                      # one block bucket (w, b) + head.weight + head.bias
+        for k, g in ref.items():
+            assert torch.allclose(grads[k], g, atol=1e-5), (rank, k)
+
+
+def _arena_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jittor_mlp_b200 import dp
+    torch.manual_seed(5)
+    w = torch.nn.Parameter(torch.randn(4, 8))
+    b = torch.nn.Parameter(torch.randn(4))
+    head = torch.nn.Linear(4, 2)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w, self.b, self.head = w, b, head
+
+        def forward(self, x):
+            return self.head(_FlatLinearFn.apply(x, self.w, self.b))
+
+    model = M()
+    ddp = dp.DataParallel(model)
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(7))
+
+    def step():
+        with ddp:
+            model(xs[rank * 2:(rank + 1) * 2]).square().mean().backward()
+    # GraphedStep(ddp=...) minus the CUDA graph: warm-up under recording, plan the arena, "capture", exchange
+    ddp.begin_static_capture()
+    step()
+    ddp.plan_arena()
+    model.zero_grad(set_to_none=True)
+    ddp.begin_static_capture()
+    step()
+    ddp.end_static_capture()
+    in_arena = ddp._arena is not None and model.w.grad.data_ptr() == ddp._arena.data_ptr()
+    n_rest = len(ddp._rest_views or [])
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
+    ddp.reduce_static()
+    dist.all_reduce = real
+    q.put((rank, in_arena, n_rest, calls, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_arena_makes_the_exchange_one_all_reduce():
+    """Graph mode with the arena (dp.plan_arena / take): the block bucket lives in ONE flat buffer, the gradients outside the
+    blocks travel in its tail, and reduce_static() issues exactly one all-reduce."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(5)
+    w = torch.randn(4, 8, requires_grad=True)
+    b = torch.randn(4, requires_grad=True)
+    head = torch.nn.Linear(4, 2)
+    xs = torch.randn(4, 8, generator=torch.Generator().manual_seed(7))
+    head(xs @ w.t() + b).square().mean().backward()
+    ref = {"w": w.grad, "b": b.grad, "head.weight": head.weight.grad, "head.bias": head.bias.grad}
+    for rank, in_arena, n_rest, calls, grads in res:
+        assert in_arena and n_rest == 2           # bucket (w, b) in the arena; head.weight, head.bias in its tail
+        assert calls == [40 + 8 + 8]              # one all-reduce: 36 -> 40 (bucket, padded to 8) + 8 + 2 -> 8
         for k, g in ref.items():
             assert torch.allclose(grads[k], g, atol=1e-5), (rank, k)
