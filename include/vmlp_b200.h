@@ -207,6 +207,12 @@ int vmlp_s2v2_dt_fused(const void* dout, const void* hat, const void* da, void* 
 int vmlp_permute5(const void* in, void* out, const int32_t dims[5], const int64_t in_strides[4],
                   const int64_t out_strides[4], int32_t accumulate, vmlp_stream_t stream);
 
+/* Position mean of the classification heads (x.mean(dim=1), mlp_mixer.py:75; Reduce('b h w c -> b c', 'mean'),
+ * hire_mlp.py:219; AdaptiveAvgPool2d(1), as_mlp.py:437-439): out[b,c] = mean over P positions of x[b,p,c] (fp32
+ * accumulation); backward dx[b,p,c] = g[b,c] / P.  C % 8 == 0. */
+int vmlp_token_mean(const void* x, void* out, int32_t B, int32_t P, int32_t C, vmlp_stream_t stream);
+int vmlp_token_mean_bwd(const void* g, void* dx, int32_t B, int32_t P, int32_t C, vmlp_stream_t stream);
+
 /* Multi-tensor optimizer step (the reference has no optimizer -- compare.py:141-145 only
  * interchanges state_dicts -- so the semantics are torch.optim.AdamW / torch.optim.SGD(momentum) on fp32 master weights).
  * table: DEVICE array of n_chunks entries, each a run of <= 32768 elements of one bf16 parameter tensor and its bf16

@@ -167,6 +167,8 @@ SYMBOLS = [
     ("vmlp_s2v2_dt_fused", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_void_p]),
     ("vmlp_permute5", c_int32, [c_void_p, c_void_p, _P(c_int32), _P(c_int64), _P(c_int64), c_int32, c_void_p]),
+    ("vmlp_token_mean", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
+    ("vmlp_token_mean_bwd", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_optim_step", c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, _P(OptimHyper), c_void_p]),
     ("vmlp_hire_build", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
     ("vmlp_hire_build_adj", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),

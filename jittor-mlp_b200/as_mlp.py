@@ -227,7 +227,10 @@ class AS_MLP(nn.Module):
         for layer in self.layers:
             x = layer(x)
         x = _gn(self.norm, x)                               # [B, H, W, C]
-        return x.mean(dim=(1, 2))                           # AdaptiveAvgPool2d(1) + flatten
+        return fn.TokenMeanFn.apply(x.contiguous())         # AdaptiveAvgPool2d(1) + flatten
 
     def forward(self, x):
-        return self.head(self.forward_features(x))
+        x = self.forward_features(x)
+        if isinstance(self.head, nn.Linear) and self.head.in_features % 8 == 0 and self.head.out_features % 8 == 0:
+            return fn.linear(x, self.head.weight, self.head.bias)
+        return self.head(x)

@@ -61,4 +61,4 @@ class ConvMixer(nn.Module):
             x = _bn(a, bn1, x, l1)                          # BN(GELU(dwconv(x))) + x   (conv_mixer.py:23-26)
             a = fn.linear_gelu(x, blk[1].weight, blk[1].bias, l2)
             x = _bn(a, blk[3], None, l2)                    # BN(GELU(conv1x1(x)))      (conv_mixer.py:28-31)
-        return self.classifier[2](x.mean(dim=(1, 2)))
+        return fn.head(x, self.classifier[2])

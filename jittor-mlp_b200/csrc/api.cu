@@ -472,7 +472,7 @@ int tokmix_plan(TokParams& p, int B, int N, int C, int Ds, bool backward) {
   // as with it (the L2 -> SMEM stream is not the limiter), so a second hidden-tile buffer comes before ring depth.
   const int force_depth = [] { const char* e = getenv("VMLP_TM_DEPTH"); return e ? atoi(e) : 0; }();
   const int force_nhb = [] { const char* e = getenv("VMLP_TM_NHB"); return e ? atoi(e) : 0; }();
-  const int bias_bytes = p.n_chunks * TM_CH * 4 * (backward ? 2 : 1) + (backward ? 0 : p.NT * 4);   // b1 (+ d b1 sums | b2)
+  const int bias_bytes = p.n_chunks * TM_CH * 4 * (backward ? 3 : 1) + (backward ? 0 : p.NT * 4);   // b1 (+ 2 x d b1 sums | b2)
   auto finish = [&](int nhb, int s_wa, int s_wb) -> int {
     const int bytes = TM_BAR_BYTES + 1024 + nhb * TM_HTILE + p.NT * 256 * 2 + bias_bytes +
                       s_wa * p.wa_stage * (backward ? 2 : 1) + s_wb * p.wb_stage;
@@ -1045,6 +1045,27 @@ int vmlp_permute5(const void* in, void* out, const int32_t dims[5], const int64_
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (accumulate) permute5_kernel<true><<<(unsigned)blocks, 256, 0, st>>>((cbf)in, (bf)out, p);
   else permute5_kernel<false><<<(unsigned)blocks, 256, 0, st>>>((cbf)in, (bf)out, p);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+
+int vmlp_token_mean(const void* x, void* out, int32_t B, int32_t P, int32_t C, vmlp_stream_t stream) {
+  if (!x || !out || B <= 0 || P <= 0 || C <= 0 || (C % 8)) return fail(VMLP_EINVAL, "token_mean args");
+  if (!aligned16(x) || !aligned16(out)) return fail(VMLP_EALIGN, "token_mean alignment");
+  token_mean_kernel<<<dim3((C / 8 + 31) / 32, B), 256, 0, static_cast<cudaStream_t>(stream)>>>((cbf)x, (bf)out, P, C, 1.0f / (float)P);
+  CUDA_OK(cudaGetLastError());
+  ++g_launches;
+  return VMLP_OK;
+}
+int vmlp_token_mean_bwd(const void* g, void* dx, int32_t B, int32_t P, int32_t C, vmlp_stream_t stream) {
+  if (!g || !dx || B <= 0 || P <= 0 || C <= 0 || (C % 8)) return fail(VMLP_EINVAL, "token_mean_bwd args");
+  if (!aligned16(g) || !aligned16(dx)) return fail(VMLP_EALIGN, "token_mean_bwd alignment");
+  long long gx = ((long long)P * (C / 8) + 255) / 256;
+  const long long cap = ((long long)device_info().sms * 8 + B - 1) / B;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  token_mean_bwd_kernel<<<dim3((unsigned)gx, B), 256, 0, static_cast<cudaStream_t>(stream)>>>((cbf)g, (bf)dx, P, C, 1.0f / (float)P);
   CUDA_OK(cudaGetLastError());
   ++g_launches;
   return VMLP_OK;

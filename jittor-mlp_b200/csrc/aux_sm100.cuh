@@ -124,4 +124,57 @@ optim_step_kernel(const OptimChunk* __restrict__ table, float* __restrict__ mast
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Token / position mean of the classification heads (`x.mean(dim=1)` mlp_mixer.py:75, `Reduce('b h w c -> b c', 'mean')`
+// hire_mlp.py:219, AdaptiveAvgPool2d(1) as_mlp.py:437-439): out[b, c] = (1 / P) sum_p x[b, p, c], fp32 accumulation.
+// Block = 32 channel vectors x 8 position phases; a warp reads 512 contiguous bytes per position.
+__global__ void __launch_bounds__(256)
+token_mean_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int P, int C, float inv) {
+  __shared__ float sh[8][32][9];
+  const int nvec = C >> 3;
+  const int vx = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int v = blockIdx.x * 32 + vx;
+  const long long img = (long long)blockIdx.y * P * C;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  if (v < nvec) {
+    for (int pos = ph; pos < P; pos += 8) {
+      float f[8];
+      unpack8(ldg_nc_v4(x + img + (long long)pos * C + v * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sh[ph][vx][e] = acc[e];
+  __syncthreads();
+  if (ph == 0 && v < nvec) {
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sh[k][vx][e];
+      o[e] = t * inv;
+    }
+    *reinterpret_cast<uint4*>(out + (long long)blockIdx.y * C + v * 8) = pack8(o);
+  }
+}
+// dx[b, p, c] = g[b, c] / P
+__global__ void __launch_bounds__(256)
+token_mean_bwd_kernel(const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx, int P, int C, float inv) {
+  const int nvec = C >> 3;
+  const long long per_img = (long long)P * nvec;
+  const long long b = blockIdx.y;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += (long long)gridDim.x * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(g + b * C + v * 8), f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] *= inv;
+    *reinterpret_cast<uint4*>(dx + b * P * C + i * 8) = pack8(f);
+  }
+}
+
 }  // namespace vmlp

@@ -613,7 +613,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   const uint32_t s_w3 = s_w2 + p.s_wa * p.wa_stage;
   const uint32_t s_dz = s_w3 + p.s_wb * p.wb_stage;
   float* sb1 = reinterpret_cast<float*>(smem + (s_dz - s_base) + p.nhb * TM_HTILE);
-  float* sdb = sb1 + p.n_chunks * TM_CH;          // per-CTA partial sums of d b1, flushed once at the end
+  float* sdb = sb1 + p.n_chunks * TM_CH;          // partial sums of d b1, one array per helper warp, flushed once at the end
   const uint32_t s_db = s_dz + p.nhb * TM_HTILE + p.n_chunks * TM_CH * 4;
 
   if (warp == 0 && lane == 0) {
@@ -637,6 +637,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
   for (int i = threadIdx.x; i < p.n_chunks * TM_CH; i += TM_BWD_THREADS) {
     sb1[i] = i < p.Ds ? __bfloat162float(p.b1[i]) : 0.f;
     sdb[i] = 0.f;
+    sdb[p.n_chunks * TM_CH + i] = 0.f;
   }
   if (warp == 1) { tmem_alloc_2cta(tmem_slot, 512); tmem_relinquish_2cta(); }
   tc_fence_before();
@@ -782,9 +783,10 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     // ================================================================ helper warps: warp 2 stores the dZ^T tile by TMA;
     // both sum the tile's columns over their 64 channel rows (d b1[m] = sum over (b, c) of dZ): lane l owns hidden
     // columns 2l, 2l+1 of the chunk and reads one 32-bit word per row (the 16-byte chunk index is un-swizzled per row).
-    // warp 2 owns hidden columns 0..31 of the tile, warp 3 columns 32..63 (all 128 channel rows each): one partial-sum array
-    const uint32_t kc = (lane & 3) + 4 * (warp - 2);   // 16-byte chunk = eight hidden columns
-    const int rs = lane >> 2;                          // row phase: rows rs + 8 i
+    // warp 2 owns channel rows 0..63 of the tile, warp 3 rows 64..127; each has its own partial-sum array
+    const int r0 = (warp - 2) * 64;
+    const uint32_t kc = lane & 7;                      // 16-byte chunk = eight hidden columns
+    const int rs = lane >> 3;                          // row phase: rows r0 + rs + 4 i
     const int nb_threads = 32 * ((p.nhb == 2 ? TM_BWD_EPI_WARPS / 2 : TM_BWD_EPI_WARPS) + 2);
     int g = 0;
     for (int pair = cluster_id; pair < p.n_pairs; pair += num_clusters) {
@@ -805,21 +807,20 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         }
         __syncwarp();
         if (t.valid && !(p.flags & 4)) {
-          // one LDS.128 per row, eight independent fp32 accumulators, three shuffle steps fold the eight row phases
+          // one LDS.128 per row, eight independent fp32 accumulators, two shuffle steps fold the four row phases
           const uint32_t tb = s_dz + hb * TM_HTILE;
           float acc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll 8
           for (int i = 0; i < 16; ++i) {
-            const int r = rs + 8 * i;
+            const int r = r0 + rs + 4 * i;
             const uint4 w = ld_shared_v4(tb + r * 128 + ((kc ^ (r & 7)) << 4));
             acc[0] += bf16lo(w.x); acc[1] += bf16hi(w.x); acc[2] += bf16lo(w.y); acc[3] += bf16hi(w.y);
             acc[4] += bf16lo(w.z); acc[5] += bf16hi(w.z); acc[6] += bf16lo(w.w); acc[7] += bf16hi(w.w);
           }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 4);
             acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
             acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
           }
@@ -827,7 +828,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
             // each (helper warp, lane) owns 8 columns of the partial-sum array: a plain read-modify-write.  (Shared memory
             // has no native fp32 add: atomicAdd / red.shared compile to an ATOMS.CAS spin loop -- the clock64 timeline showed
             // 3100 cycles per tile here, with the epilogue's next write waiting behind it.)
-            const uint32_t a = s_db + (j * TM_CH + kc * 8) * 4;
+            const uint32_t a = s_db + (((warp - 2) * p.n_chunks + j) * TM_CH + kc * 8) * 4;
             float4 s0 = lds_f4(a), s1 = lds_f4(a + 16);
             s0.x += acc[0]; s0.y += acc[1]; s0.z += acc[2]; s0.w += acc[3];
             s1.x += acc[4]; s1.y += acc[5]; s1.z += acc[6]; s1.w += acc[7];
@@ -1072,7 +1073,7 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
     tmem_dealloc_2cta(tmem_base, 512);
   }
   if (p.db1 != nullptr)
-    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i]);
+    for (int i = threadIdx.x; i < p.Ds; i += TM_BWD_THREADS) red_add_f32(p.db1 + i, sdb[i] + sdb[p.n_chunks * TM_CH + i]);
 }
 
 // W [rows, cols] -> padded copy [rows, ld] (zero fill) and/or transposed copy [cols, ldt] (zero fill): the K-major weight

@@ -155,6 +155,8 @@ class DataParallel(torch.nn.Module):
         self._rest_views = None
         if self._arena is not None and buckets and buckets[0].data_ptr() == self._arena.data_ptr():
             off, views = self._arena_plan[0], []
+            if off + sum((g.numel() + 7) & ~7 for g in rest) > self._arena.numel():
+                raise RuntimeError("data-parallel gradient arena: planned before the warm-up gradients existed")
             for g in rest:                               # gradients outside the blocks travel in the arena's tail
                 views.append(self._arena[off:off + g.numel()].view(g.shape))
                 off += (g.numel() + 7) & ~7

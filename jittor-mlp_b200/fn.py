@@ -331,3 +331,39 @@ def patch_embed(x, conv):
     p = conv(x)
     b, c = p.shape[0], p.shape[1]
     return p.permute(0, 2, 3, 1).reshape(b, -1, c)
+
+
+class TokenMeanFn(torch.autograd.Function):
+    """[B, positions..., C] -> [B, C]: the position mean of the classification heads (mlp_mixer.py:75, hire_mlp.py:219,
+    as_mlp.py:437-439) with fp32 accumulation."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _chk(x, "x")
+        B, C = x.shape[0], x.shape[-1]
+        P = x.numel() // (B * C)
+        out = _new(B, C, like=x)
+        L.check(L.lib().vmlp_token_mean(x.data_ptr(), out.data_ptr(), B, P, C, L.stream_ptr()))
+        ctx.shape = tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        B, C = ctx.shape[0], ctx.shape[-1]
+        P = 1
+        for d in ctx.shape[1:-1]:
+            P *= d
+        dx = torch.empty(ctx.shape, dtype=BF16, device=g.device)
+        L.check(L.lib().vmlp_token_mean_bwd(g.data_ptr(), dx.data_ptr(), B, P, C, L.stream_ptr()))
+        return dx
+
+
+def head(x, lin):
+    """Classification head: position mean + nn.Linear (mlp_mixer.py:75-76 and its siblings) on the library's kernels.  The
+    GEMM's TMA operands need 16-byte row pitches: a class count or width that is not a multiple of 8 keeps ATen's Linear
+    (heads are outside the fused block path)."""
+    m = TokenMeanFn.apply(x.contiguous())
+    if lin.in_features % 8 == 0 and lin.out_features % 8 == 0:
+        return linear(m, lin.weight, lin.bias)
+    return lin(m)

@@ -54,5 +54,4 @@ class gMLPForImageClassification(gMLP):
     def forward(self, x):
         patches = fn.patch_embed(x, self.patcher[0])        # stem conv as gather + GEMM -> contiguous [B, N, C]
         embedding = self.model(patches)
-        embedding = embedding.mean(dim=1)
-        return self.mlp_head(embedding)
+        return fn.head(embedding, self.mlp_head[0])           # token mean + Linear

@@ -46,9 +46,10 @@ class GraphedStep:
                 step_fn(self.static_x)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
-        model.zero_grad(set_to_none=True)
         if ddp is not None:
-            ddp.plan_arena()                               # one flat buffer for all buckets, sized from the warm-up step
+            ddp.plan_arena()                               # one flat buffer for all buckets + the other gradients, sized
+        model.zero_grad(set_to_none=True)                  # from the last warm-up step (while its p.grad still exist)
+        if ddp is not None:
             ddp.begin_static_capture()                     # start the bucket list afresh: these are the graph's buffers
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.static_loss = step_fn(self.static_x)

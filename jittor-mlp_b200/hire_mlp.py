@@ -135,4 +135,6 @@ class HireMLP(nn.Module):
         embedding = embedding.permute(0, 2, 3, 1)
         for layer in self.layers:
             embedding = layer(embedding)
-        return self.mlp_head(embedding)
+        ln = self.mlp_head[0]                               # LayerNorm -> position mean -> Linear (hire_mlp.py:217-221)
+        embedding = fn.layer_norm(embedding.contiguous(), ln.weight, ln.bias, ln.eps)
+        return fn.head(embedding, self.mlp_head[2])

@@ -76,5 +76,4 @@ class MLPMixerForImageClassification(MLPMixer):
         patches = fn.patch_embed(x, self.patcher[0])        # stem conv as gather + GEMM -> contiguous [B, N, C]
         embedding = self.model(patches)
         embedding = fn.layer_norm(embedding, self.active.weight, self.active.bias, self.active.eps)
-        embedding = embedding.mean(dim=1)
-        return self.mlp_head(embedding)
+        return fn.head(embedding, self.mlp_head[0])           # token mean + Linear (mlp_mixer.py:75-76)

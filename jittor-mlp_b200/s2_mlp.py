@@ -86,7 +86,8 @@ class S2MLPv1(nn.Module):
 
     def forward(self, x):
         # channels-last input: the stage convs (cuDNN) run their NHWC kernels and the block-side permutes are views
-        return self.mlp_head(self.stages(x.contiguous(memory_format=torch.channels_last)))
+        t = self.stages(x.contiguous(memory_format=torch.channels_last))      # NCHW view of channels-last rows
+        return fn.head(t.permute(0, 2, 3, 1), self.mlp_head[1])
 
 
 def S2MLPv1_deep(num_classes: int = 1000, **kwargs):
@@ -176,4 +177,5 @@ class S2MLPv2(nn.Module):
 
     def forward(self, x):
         # channels-last input: the stage convs (cuDNN) run their NHWC kernels and the block-side permutes are views
-        return self.mlp_head(self.stages(x.contiguous(memory_format=torch.channels_last)))
+        t = self.stages(x.contiguous(memory_format=torch.channels_last))      # NCHW view of channels-last rows
+        return fn.head(t.permute(0, 2, 3, 1), self.mlp_head[1])

@@ -109,4 +109,4 @@ class ViP(nn.Module):
         emb = self.blocks(patches.permute(0, 2, 3, 1))
         ln = self.mlp_head[0]
         emb = fn.layer_norm(emb, ln.weight, ln.bias, ln.eps)
-        return self.mlp_head[2](self.mlp_head[1](emb))
+        return fn.head(emb, self.mlp_head[2])

@@ -152,3 +152,19 @@ def test_training_step_with_fused_adamw_reduces_the_loss():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+@pytest.mark.parametrize("shape", [(3, 196, 768), (2, 7, 5, 24), (5, 14, 28, 256), (1, 1, 8)])
+def test_token_mean_head_kernels(shape):
+    """Position mean of the classification heads (mlp_mixer.py:75, hire_mlp.py:219): fp32 accumulation, rounded once."""
+    from jittor_mlp_b200 import fn
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(3)).bfloat16()
+    xg = x.to(DEV).requires_grad_(True)
+    out = fn.TokenMeanFn.apply(xg)
+    ref = x.float().reshape(shape[0], -1, shape[-1]).mean(1)
+    assert float((out.float().cpu() - ref).abs().max()) <= 2.0 ** -8 * float(ref.abs().max())     # one bf16 rounding
+    g = torch.randn(shape[0], shape[-1], generator=torch.Generator().manual_seed(4)).bfloat16()
+    out.backward(g.to(DEV))
+    inv = torch.tensor(1.0 / (x.numel() // (shape[0] * shape[-1])), dtype=torch.float32)
+    dref = (g.float() * inv).bfloat16().float().reshape(shape[0], *([1] * (len(shape) - 2)), shape[-1]).expand(*shape)
+    assert torch.equal(xg.grad.float().cpu(), dref)
