@@ -46,8 +46,8 @@ if rank == 0:
     print(f"dp_check world={world}: max rel-L2(dp grad, big-batch grad) = {float(t):.3e}; identical across ranks = {bool(same.item())}")
     assert float(t) < 2e-2 and bool(same.item())
 
-# CUDA-graph mode (what bench.py times for N > 1): the captured step holds this rank's compute only, ONE grouped NCCL
-# all-reduce of the static gradient buffers follows every replay (graph.GraphedStep(ddp=...), dp.reduce_static)
+# CUDA-graph mode (what bench.py times for N > 1): the captured step holds this rank's compute only, ONE NCCL all-reduce
+# of the step's gradient arena follows every replay (graph.GraphedStep(ddp=...), dp.reduce_static)
 model.zero_grad(set_to_none=True)
 gs = J.GraphedStep(model, xs[rank * per:(rank + 1) * per], loss_fn, ddp=ddp)
 for _ in range(2):
@@ -65,8 +65,12 @@ dist.broadcast(ref0, src=0)
 same = torch.tensor([float(torch.equal(flat, ref0))], device=dev)
 dist.all_reduce(same, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print(f"dp_check world={world} (graph + one grouped all-reduce, {len(ddp._static)} buffers): max rel-L2 vs eager DP step = "
+    how = "ONE all-reduce of the gradient arena" if ddp._arena is not None else f"one grouped all-reduce, {len(ddp._static)} buffers"
+    print(f"dp_check world={world} (graph + {how}): max rel-L2 vs eager DP step = "
           f"{float(tg):.3e}; identical across ranks = {bool(same.item())}")
-    assert float(tg) < 5e-3 and bool(same.item())
+    # both steps average the same bf16 gradients, but through different message sizes (NCCL picks another algorithm and
+    # with it another bf16 summation order): the difference is of the size of the DP-vs-big-batch one above (4e-3 at 8
+    # ranks; 5.5e-3 measured here at 8 ranks, 6e-5 at 2)
+    assert float(tg) < 1e-2 and bool(same.item())
 dist.barrier()
 dist.destroy_process_group()
