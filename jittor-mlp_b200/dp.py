@@ -38,6 +38,7 @@ class DataParallel(torch.nn.Module):
         self._arena = None      # ONE flat bf16 buffer holding every block bucket of a captured step (+ room for the rest)
         self._arena_off = 0
         self._arena_plan = None
+        self._other = []
         if self.world > 1:
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, src=0, group=process_group)   # identical replicas
@@ -122,15 +123,17 @@ class DataParallel(torch.nn.Module):
         order (`take`), so the whole gradient exchange of a step is a single all-reduce of one buffer -- 18 grouped
         all-reduces of ~10 MB cost 1.1 ms per step on 8 GPUs (per-operation latency), one of 123 MB about half of that."""
         buckets = self._collect or []
-        if not buckets:
-            return
         covered = [(f.data_ptr(), f.data_ptr() + f.numel() * f.element_size()) for f in buckets]
         rest = [p for p in self.module.parameters()
                 if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in covered)]
+        if not buckets and not rest:
+            return
+        ref = buckets[0] if buckets else rest[0].grad
+        rest = [p for p in rest if p.grad.dtype == ref.dtype]       # other dtypes stay separate buffers
         pad8 = lambda n: (n + 7) & ~7
         n_b = sum(pad8(f.numel()) for f in buckets)
         n_r = sum(pad8(p.numel()) for p in rest)
-        self._arena = torch.zeros(n_b + n_r, dtype=buckets[0].dtype, device=buckets[0].device)
+        self._arena = torch.zeros(n_b + n_r, dtype=ref.dtype, device=ref.device)
         self._arena_plan = (n_b, [f.numel() for f in buckets])
 
     def take(self, n, device):
@@ -153,14 +156,18 @@ class DataParallel(torch.nn.Module):
                 if p.grad is not None and not any(lo <= p.grad.data_ptr() < hi for lo, hi in covered)]
         self._static = buckets + rest
         self._rest_views = None
-        if self._arena is not None and buckets and buckets[0].data_ptr() == self._arena.data_ptr():
+        in_arena = self._arena is not None and (
+            (buckets and buckets[0].data_ptr() == self._arena.data_ptr()) or (not buckets and self._arena_plan[0] == 0))
+        if in_arena:
+            mine = [g for g in rest if g.dtype == self._arena.dtype]
+            self._other = [g for g in rest if g.dtype != self._arena.dtype]
             off, views = self._arena_plan[0], []
-            if off + sum((g.numel() + 7) & ~7 for g in rest) > self._arena.numel():
+            if off + sum((g.numel() + 7) & ~7 for g in mine) > self._arena.numel():
                 raise RuntimeError("data-parallel gradient arena: planned before the warm-up gradients existed")
-            for g in rest:                               # gradients outside the blocks travel in the arena's tail
+            for g in mine:                               # gradients outside the blocks travel in the arena's tail
                 views.append(self._arena[off:off + g.numel()].view(g.shape))
                 off += (g.numel() + 7) & ~7
-            self._rest, self._rest_views = rest, views
+            self._rest, self._rest_views = mine, views
         else:
             self._arena = None
 
@@ -181,6 +188,10 @@ class DataParallel(torch.nn.Module):
                 self._arena.div_(self.world)
             if self._rest:
                 torch._foreach_copy_(self._rest, self._rest_views)
+            for t in self._other:                            # gradients of another dtype than the arena (none in the models here)
+                dist.all_reduce(t, op=dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM, group=self.group)
+                if not self._nccl:
+                    t.div_(self.world)
             return
         if self._nccl:
             with dist._coalescing_manager(group=self.group, device=self._static[0].device, async_ops=False):

@@ -212,7 +212,7 @@ def test_static_buffers_of_a_captured_step_are_exchanged_once():
             assert torch.allclose(grads[k], g, atol=1e-5), (rank, k)
 
 
-def _arena_worker(rank, world, port, q):
+def _arena_worker(rank, world, port, q, with_block=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from jittor_mlp_b200 import dp
@@ -227,7 +227,7 @@ def _arena_worker(rank, world, port, q):
             self.w, self.b, self.head = w, b, head
 
         def forward(self, x):
-            return self.head(_FlatLinearFn.apply(x, self.w, self.b))
+            return self.head(_FlatLinearFn.apply(x, self.w, self.b) if with_block else x @ self.w.t() + self.b)
 
     model = M()
     ddp = dp.DataParallel(model)
@@ -244,7 +244,7 @@ def _arena_worker(rank, world, port, q):
     ddp.begin_static_capture()
     step()
     ddp.end_static_capture()
-    in_arena = ddp._arena is not None and model.w.grad.data_ptr() == ddp._arena.data_ptr()
+    in_arena = ddp._arena is not None and (not with_block or model.w.grad.data_ptr() == ddp._arena.data_ptr())
     n_rest = len(ddp._rest_views or [])
     calls = []
     real = dist.all_reduce
@@ -256,13 +256,15 @@ def _arena_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_gradient_arena_makes_the_exchange_one_all_reduce():
+@pytest.mark.parametrize("with_block", [True, False])
+def test_gradient_arena_makes_the_exchange_one_all_reduce(with_block):
     """Graph mode with the arena (dp.plan_arena / take): the block bucket lives in ONE flat buffer, the gradients outside the
-    blocks travel in its tail, and reduce_static() issues exactly one all-reduce."""
+    blocks travel in its tail, and reduce_static() issues exactly one all-reduce -- also for a model without fused blocks
+    (all gradients travel in the arena)."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q, with_block)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
@@ -277,7 +279,11 @@ def test_gradient_arena_makes_the_exchange_one_all_reduce():
     head(xs @ w.t() + b).square().mean().backward()
     ref = {"w": w.grad, "b": b.grad, "head.weight": head.weight.grad, "head.bias": head.bias.grad}
     for rank, in_arena, n_rest, calls, grads in res:
-        assert in_arena and n_rest == 2           # bucket (w, b) in the arena; head.weight, head.bias in its tail
-        assert calls == [40 + 8 + 8]              # one all-reduce: 36 -> 40 (bucket, padded to 8) + 8 + 2 -> 8
+        if with_block:
+            assert in_arena and n_rest == 2       # bucket (w, b) in the arena; head.weight, head.bias in its tail
+            assert calls == [40 + 8 + 8]          # one all-reduce: 36 -> 40 (bucket, padded to 8) + 8 + 2 -> 8
+        else:
+            assert in_arena and n_rest == 4       # w, b, head.weight, head.bias all in the arena
+            assert calls == [32 + 8 + 8 + 8]
         for k, g in ref.items():
             assert torch.allclose(grads[k], g, atol=1e-5), (rank, k)
