@@ -376,6 +376,9 @@ def main():
     ap.add_argument("--graph", type=int, default=-1,
                     help="1/0: replay the step as a CUDA graph (default on; for N > 1 the graph holds the compute only and "
                          "one grouped NCCL all-reduce of the gradient buffers follows every replay)")
+    ap.add_argument("--optimizer", default="none", choices=["none", "adamw", "sgd"],
+                    help="also run the fused optimizer step (optim.FusedAdamW / FusedSGD, one launch) inside every timed step; "
+                         "off by default: BASELINE's metric is forward+backward")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -402,6 +405,11 @@ def main():
     x_host = torch.randn(B, 3, 224, 224, generator=g).bfloat16().pin_memory()
     x_dev = x_host.to(dev)
 
+    opt = None
+    if args.optimizer != "none":
+        import jittor_mlp_b200 as J
+        opt = (J.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=0.05) if args.optimizer == "adamw"
+               else J.FusedSGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4))
     use_graph = args.graph != 0
     gs = None
     if use_graph:
@@ -447,7 +455,10 @@ def main():
     if use_graph:
 
         def step_resident():
-            return gs.run()
+            loss = gs.run()
+            if opt is not None:
+                opt.step()
+            return loss
 
         def step_e2e():
             cur = torch.cuda.current_stream()
@@ -455,12 +466,17 @@ def main():
             gs.static_x.copy_(staging, non_blocking=True)          # device-side hand-over into the graph's input
             consumed.record(cur)
             gs.run()                                               # graph replay (+ the gradient all-reduce for N > 1)
+            if opt is not None:
+                opt.step()
             prefetch()                                             # H2D of the next step's images overlaps this step
             return read_loss(gs.static_loss)                       # D2H of this step's loss, consumed one step late
     else:
         def step_resident():
             model.zero_grad(set_to_none=True)
-            return ddp.step_fwd_bwd(x_dev, loss_fn)
+            loss = ddp.step_fwd_bwd(x_dev, loss_fn)
+            if opt is not None:
+                opt.step()
+            return loss
 
         def step_e2e():
             model.zero_grad(set_to_none=True)
@@ -469,6 +485,8 @@ def main():
             xb = staging.clone()                                   # this step's batch; staging is refilled underneath
             consumed.record(cur)
             loss = ddp.step_fwd_bwd(xb, loss_fn)
+            if opt is not None:
+                opt.step()
             prefetch()
             return read_loss(loss)                                 # D2H of this step's loss, consumed one step late
 
@@ -498,6 +516,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"{args.model} ({cls}{kw}) fwd+bwd, 224x224, batch {B}/GPU, bf16 params+activations, fp32 accumulate",
                            "global_batch": B * world, "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
+                           "optimizer": ("none (BASELINE's metric is forward+backward)" if opt is None else
+                                         f"{args.optimizer}: fused step inside every timed step, one launch (optim.py)"),
                            "l2": "per-step working set (>= 18 GB of activations) >> 126 MB L2; no flush needed"},
                 "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 2,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(t_e2e / args.steps * 1e3, 3),
