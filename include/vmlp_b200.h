@@ -261,6 +261,10 @@ int vmlp_hire_restore_adj(const void* dout, void* dzh, void* dzw, const vmlp_hir
  * wgrad accumulates fp32 dW [C, K, K] (caller zero-fills). */
 int vmlp_dwconv_fwd(const void* x, const void* weight, const void* bias, void* z, void* a, int32_t B, int32_t H,
                     int32_t W, int32_t C, int32_t K, vmlp_stream_t stream);
+/* depthwise conv + bias WITHOUT activation (sparse_mlp.py:88-90: Conv2d(d, d, 3, padding 1, groups = d) inside a
+ * BatchNorm pre-norm residual); backward = vmlp_dwconv_dgrad / _wgrad with dz = dy. */
+int vmlp_dwconv_fwd_plain(const void* x, const void* weight, const void* bias, void* y, int32_t B, int32_t H, int32_t W,
+                          int32_t C, int32_t K, vmlp_stream_t stream);
 int vmlp_dwconv_dgrad(const void* dz, const void* weight, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
                       int32_t K, vmlp_stream_t stream);
 int vmlp_dwconv_wgrad(const void* x, const void* dz, float* dw, int32_t B, int32_t H, int32_t W, int32_t C, int32_t K,

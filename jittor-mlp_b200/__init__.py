@@ -9,5 +9,6 @@ from .as_mlp import AS_MLP  # noqa: F401
 from .hire_mlp import HireMLP  # noqa: F401
 from .conv_mixer import ConvMixer  # noqa: F401
 from .vip import ViP  # noqa: F401
+from .sparse_mlp import SparseMLP  # noqa: F401
 from .optim import FusedAdamW, FusedSGD  # noqa: F401
 from .graph import GraphedStep  # noqa: F401

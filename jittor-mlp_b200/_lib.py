@@ -176,6 +176,8 @@ SYMBOLS = [
     ("vmlp_hire_restore_adj", c_int32, [c_void_p, c_void_p, c_void_p, _P(HireDims), c_void_p]),
     ("vmlp_dwconv_fwd", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                   c_int32, c_void_p]),
+    ("vmlp_dwconv_fwd_plain", c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                        c_void_p]),
     ("vmlp_dwconv_dgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_dwconv_wgrad", c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     ("vmlp_patchify", c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),

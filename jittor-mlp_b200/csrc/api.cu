@@ -1222,6 +1222,17 @@ int vmlp_dwconv_fwd(const void* x, const void* weight, const void* bias, void* z
                      (dwconv_launch<7, 0, 1>(x, weight, bias, z, a, B, H, W, C, st)),
                      (dwconv_launch<9, 0, 1>(x, weight, bias, z, a, B, H, W, C, st)));
 }
+int vmlp_dwconv_fwd_plain(const void* x, const void* weight, const void* bias, void* y, int32_t B, int32_t H, int32_t W,
+                          int32_t C, int32_t K, vmlp_stream_t stream) {
+  int rc = dwconv_check(x, weight, y, B, H, W, C, K);
+  if (rc) return rc;
+  if (!bias) return fail(VMLP_EINVAL, "dwconv_fwd_plain needs a bias");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return DW_DISPATCH(K, (dwconv_launch<3, 0, 2>(x, weight, bias, y, nullptr, B, H, W, C, st)),
+                     (dwconv_launch<5, 0, 2>(x, weight, bias, y, nullptr, B, H, W, C, st)),
+                     (dwconv_launch<7, 0, 2>(x, weight, bias, y, nullptr, B, H, W, C, st)),
+                     (dwconv_launch<9, 0, 2>(x, weight, bias, y, nullptr, B, H, W, C, st)));
+}
 int vmlp_dwconv_dgrad(const void* dz, const void* weight, void* dx, int32_t B, int32_t H, int32_t W, int32_t C,
                       int32_t K, vmlp_stream_t stream) {
   int rc = dwconv_check(dz, weight, dx, B, H, W, C, K);

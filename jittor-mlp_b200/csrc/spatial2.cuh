@@ -252,7 +252,7 @@ dwconv_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __re
         for (int q = 0; q < DW_TW; ++q) {
           if (w0 + q >= W) continue;
           const long long o = orow + (long long)q * C;
-          if (EPI) {            // out = gelu'(z) (kept for backward), out2 = gelu(z)
+          if (EPI == 1) {       // out = gelu'(z) (kept for backward), out2 = gelu(z); EPI == 2: bias only, plain store
             f32x2 gl, dg;
             gelu_erf_pair<true>(acc[r][q], gl, dg);
             *reinterpret_cast<uint32_t*>(out + o) = pack_bf16x2_f2(dg);

@@ -367,3 +367,76 @@ def head(x, lin):
     if lin.in_features % 8 == 0 and lin.out_features % 8 == 0:
         return linear(m, lin.weight, lin.bias)
     return lin(m)
+
+
+class TokenLinearFn(torch.autograd.Function):
+    """y[b, m, c] = sum_n W[m, n] x[b, n, c] + bias[m]: a Linear along the TOKEN axis of [Bt, N, C] (sparse_mlp.py:66-71:
+    proj_w over the width with Bt = B*H, proj_h over the height with the (width, channel) pairs as C).  Same batched GEMM
+    forms as the token half of the Mixer / ResMLP blocks: the activation is the MN-major operand, nothing is transposed."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _chk(x, "x"); _chk(w, "w"); _chk(b, "b")
+        Bt, N, C = x.shape
+        Mo = w.shape[0]
+        from .ops import pad_rows
+        wp = pad_rows(w.view(Mo, N))                      # TMA row pitch: multiple of 8 elements
+        Np = wp.shape[1]
+        y = _new(Bt, Mo, C, like=x)
+        gemm(Mo, C, N, L.Operand(wp.data_ptr(), Mo, N, Np, 0, 0), operand(x, 1), L.EPI_STORE, batch=Bt, D=y, bias=b,
+             bias_mode=2 if b is not None else 0)
+        ctx.save_for_backward(x, w, wp)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, wp = ctx.saved_tensors
+        Bt, N, C = x.shape
+        Mo, Np = w.shape[0], wp.shape[1]
+        dy = dy.contiguous()
+        _chk(dy, "dy")
+        from .ops import rowsum_batched_into
+        dx = torch.empty_like(x)
+        gemm(N, C, Mo, L.Operand(wp.data_ptr(), Mo, N, Np, 0, 1), operand(dy, 1), L.EPI_STORE, batch=Bt, D=dx)   # W^T dy
+        flat = _f32(Mo * N + (Mo if ctx.has_b else 0), x.device)
+        gemm(Mo, N, C, operand(dy, 0), operand(x, 0), L.EPI_ATOMIC, batch=Bt, contract_batch=True,
+             out_f32=flat[:Mo * N].view(Mo, N))
+        if ctx.has_b:
+            rowsum_batched_into(flat[Mo * N:], dy)
+        g = cast_f32_to_bf16(flat)
+        return dx, g[:Mo * N].view(w.shape), (g[Mo * N:] if ctx.has_b else None)
+
+
+class ConcatChannelsFn(torch.autograd.Function):
+    """torch.cat(parts, dim=-1) of channels-last tensors (sparse_mlp.py:72) as strided copies into ONE buffer."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        from .fn_vip import permute5
+        for i, t in enumerate(parts):
+            _chk(t, f"parts[{i}]")
+        widths = [t.shape[-1] for t in parts]
+        rows = parts[0].numel() // widths[0]
+        tot = sum(widths)
+        if any(wd % 8 for wd in widths):
+            raise ValueError("channel widths must be multiples of 8")
+        out = _new(*parts[0].shape[:-1], tot, like=parts[0])
+        off = 0
+        for t, wd in zip(parts, widths):
+            permute5(t, out.view(-1)[off:], (rows, 1, 1, 1, wd), (wd, 0, 0, 0), (tot, 0, 0, 0))
+            off += wd
+        ctx.widths, ctx.rows = widths, rows
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .fn_vip import permute5
+        dout = dout.contiguous()
+        tot, off, grads = sum(ctx.widths), 0, []
+        for wd in ctx.widths:
+            g = _new(*dout.shape[:-1], wd, like=dout)
+            permute5(dout.view(-1)[off:], g, (ctx.rows, 1, 1, 1, wd), (tot, 0, 0, 0), (wd, 0, 0, 0))
+            grads.append(g)
+            off += wd
+        return tuple(grads)

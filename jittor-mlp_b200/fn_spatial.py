@@ -196,3 +196,34 @@ class BatchNormEvalFn(torch.autograd.Function):
 def batch_norm_eval(a, bn, res=None):
     """eval(): BatchNorm uses the running statistics -> a per-channel affine with fp32 coefficients."""
     return BatchNormEvalFn.apply(a, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, res)
+
+
+class DwConvFn(torch.autograd.Function):
+    """y = depthwise_conv_kxk(x) + bias, padding "same", no activation (sparse_mlp.py:88-90); x: [B, H, W, C]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _chk(x, "x"); _chk(weight, "weight"); _chk(bias, "bias")
+        B, H, W, C = x.shape
+        K = weight.shape[-1]
+        y = torch.empty_like(x)
+        L.check(L.lib().vmlp_dwconv_fwd_plain(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, C, K,
+                                              L.stream_ptr()))
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        B, H, W, C = x.shape
+        K = weight.shape[-1]
+        dy = dy.contiguous()
+        _chk(dy, "dy")
+        lib = L.lib()
+        dx = torch.empty_like(x)
+        L.check(lib.vmlp_dwconv_dgrad(dy.data_ptr(), weight.data_ptr(), dx.data_ptr(), B, H, W, C, K, L.stream_ptr()))
+        g = _f32(C * K * K + C, x.device)
+        L.check(lib.vmlp_dwconv_wgrad(x.data_ptr(), dy.data_ptr(), g.data_ptr(), B, H, W, C, K, L.stream_ptr()))
+        colsum_into(g[C * K * K:], dy.view(-1, C))
+        gb = cast_f32_to_bf16(g)
+        return dx, gb[:C * K * K].view(weight.shape), gb[C * K * K:]

@@ -42,6 +42,8 @@ CASES = {
                                     expansion_factor=3, weighted=True), (2, 3, 32, 48), {"split_attention": 0.15}),
     "vip_sum_tiny": ("vip", "ViP", dict(image_size=(32, 32), patch_size=(8, 4), d_model=48, depth=1, segments=16,
                                         num_classes=10, weighted=False), (3, 3, 32, 32)),
+    "sparsemlp_tiny": ("sparse_mlp", "SparseMLP", dict(image_size=(32, 64), patch_size=4, d_model=16, depth=[1, 2], num_classes=10,
+                                                        expansion_factor=2), (3, 3, 32, 64)),
     "gmlp_tiny": ("g_mlp", "gMLPForImageClassification",
                   dict(image_size=32, patch_size=8, num_classes=10, d_model=64, d_ffn=128, depth=2), (2, 3, 32, 32)),
 }

@@ -21,6 +21,8 @@ def forward(cls, kwargs, sd, x):
         return restate.hire_forward(sd, x, k)
     if cls == "ConvMixer":
         return restate.convmixer_forward(sd, x, k)
+    if cls == "SparseMLP":
+        return restate.sparsemlp_forward(sd, x, k)
     if cls == "ViP":
         return restate.vip_forward(sd, x, k)
     raise KeyError(cls)

@@ -373,3 +373,45 @@ def sgd_step(w, g, buf, t, lr, momentum, wd):
     g = g + wd * w
     buf = g.clone() if t == 1 else momentum * buf + g
     return w - lr * buf, buf
+
+
+# ----------------------------------------------------------------------------------------------- SparseMLP (row f3)
+def batch_norm_train_nchw_rows(x, w, b, eps=1e-5):
+    """nn.BatchNorm2d in train() on channels-last rows [..., C]: batch statistics over every leading axis (biased
+    variance), sparse_mlp.py:91,96 (norm = nn.BatchNorm2d)."""
+    flat = x.reshape(-1, x.shape[-1])
+    mean = flat.mean(0)
+    var = ((flat - mean) ** 2).mean(0)
+    return (x - mean) / torch.sqrt(var + eps) * w + b
+
+
+def sparsemlp_forward(sd, x, kw):
+    """SparseMLP.forward (sparse_mlp.py:158-165); sMLPStage :77-115; sMLPBlock :60-75; PatchMerging :17-50.  Channels-last
+    restatement: proj_h contracts the H axis, proj_w the W axis, `fuse` is a 1x1 conv over the concatenated channels."""
+    ps = kw.get("patch_size", 4)
+    ps = (ps, ps) if isinstance(ps, int) else tuple(ps)
+    depth = kw.get("depth", [2, 10, 24, 2])
+    t = F.conv2d(x, sd["patcher.0.weight"], sd["patcher.0.bias"], stride=ps).permute(0, 2, 3, 1)
+    if kw.get("patcher_norm", False):
+        t = layer_norm(t, sd["patcher.1.1.weight"], sd["patcher.1.1.bias"])
+    for s, d in enumerate(depth):
+        for i in range(d):
+            p = f"layers.{s}.model.{i}."
+            C = t.shape[-1]
+            u = batch_norm_train_nchw_rows(t, sd[p + "0.norm.weight"], sd[p + "0.norm.bias"])
+            u = F.conv2d(u.permute(0, 3, 1, 2), sd[p + "0.fn.0.weight"], sd[p + "0.fn.0.bias"], padding=1, groups=C).permute(0, 2, 3, 1)
+            t = t + u
+            u = batch_norm_train_nchw_rows(t, sd[p + "1.norm.weight"], sd[p + "1.norm.bias"])
+            q = p + "1.fn.0."
+            xh = torch.einsum("gh,bhwc->bgwc", sd[q + "proj_h.weight"], u) + sd[q + "proj_h.bias"][None, :, None, None]
+            xw = torch.einsum("vw,bhwc->bhvc", sd[q + "proj_w.weight"], u) + sd[q + "proj_w.bias"][None, None, :, None]
+            cat = torch.cat([xh, xw, u], -1)
+            t = t + linear(cat, sd[q + "fuse.weight"].reshape(C, 3 * C), sd[q + "fuse.bias"])
+            h = gelu(linear(layer_norm(t, sd[p + "3.norm.weight"], sd[p + "3.norm.bias"]), sd[p + "3.fn.0.weight"], sd[p + "3.fn.0.bias"]))
+            t = t + linear(h, sd[p + "3.fn.3.weight"], sd[p + "3.fn.3.bias"])
+        if s + 1 < len(depth):
+            q = f"layers.{s}.patch_merge.1."
+            t = torch.cat([t[:, 0::2, 0::2], t[:, 1::2, 0::2], t[:, 0::2, 1::2], t[:, 1::2, 1::2]], -1)
+            t = linear(layer_norm(t, sd[q + "norm.weight"], sd[q + "norm.bias"]), sd[q + "reduction.weight"])
+    t = layer_norm(t, sd["mlp_head.1.weight"], sd["mlp_head.1.bias"])
+    return linear(t.mean((1, 2)), sd["mlp_head.3.weight"], sd["mlp_head.3.bias"])

@@ -9,7 +9,7 @@ import jittor_mlp_b200 as J
 from oracle import ref_loader
 
 CASES = {"mixer_tiny": 1, "mixer_ragged": 1, "resmlp_tiny": 1, "gmlp_tiny": 1, "s2v1_tiny": 1, "s2v2_tiny": 1,
-         "asmlp_tiny": 1, "hire_tiny": 1, "convmixer_tiny": 1, "vip_tiny": 1, "vip_sum_tiny": 1}
+         "asmlp_tiny": 1, "hire_tiny": 1, "convmixer_tiny": 1, "vip_tiny": 1, "vip_sum_tiny": 1, "sparsemlp_tiny": 1}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -29,7 +29,7 @@ def test_state_dict_roundtrip_strict(golden, name):
                                      ("g_mlp", "gMLP"), ("g_mlp", "gMLPBlock"),
                                      ("s2_mlp_v1", "S2MLPv1"), ("s2_mlp_v1", "S2MLPv1_deep"), ("s2_mlp_v2", "S2MLPv2"),
                                      ("as_mlp", "AS_MLP"), ("hire_mlp", "HireMLP"), ("conv_mixer", "ConvMixer"),
-                                     ("vip", "ViP")])
+                                     ("vip", "ViP"), ("sparse_mlp", "SparseMLP")])
 def test_constructor_signature_matches_reference(mod, cls):
     ref = getattr(ref_loader.load(mod), cls)
 

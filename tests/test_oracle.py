@@ -6,7 +6,7 @@ import torch
 from oracle import models, ref_loader, restate
 
 GOLDEN = ["mixer_tiny", "mixer_ragged", "resmlp_tiny", "gmlp_tiny", "s2v1_tiny", "s2v2_tiny", "asmlp_tiny", "hire_tiny",
-          "convmixer_tiny", "vip_tiny", "vip_sum_tiny"]
+          "convmixer_tiny", "vip_tiny", "vip_sum_tiny", "sparsemlp_tiny"]
 
 
 @pytest.mark.parametrize("name", GOLDEN)

@@ -168,3 +168,74 @@ def test_token_mean_head_kernels(shape):
     inv = torch.tensor(1.0 / (x.numel() // (shape[0] * shape[-1])), dtype=torch.float32)
     dref = (g.float() * inv).bfloat16().float().reshape(shape[0], *([1] * (len(shape) - 2)), shape[-1]).expand(*shape)
     assert torch.equal(xg.grad.float().cpu(), dref)
+
+
+# ------------------------------------------------------------------------------------------------ SparseMLP (row f3)
+@pytest.mark.parametrize("Bt,N,C,Mo", [(6, 56, 96, 56), (4, 7, 64, 7), (3, 16, 256, 16), (5, 28, 40, 28)])
+def test_token_linear_against_fp32(Bt, N, C, Mo):
+    """Linear along the token axis of [Bt, N, C] (sparse_mlp.py:66-71): forward, dgrad, wgrad, bias gradient."""
+    from jittor_mlp_b200 import fn
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(Bt, N, C, generator=g).bfloat16()
+    w = (torch.randn(Mo, N, generator=g) * N ** -0.5).bfloat16()
+    b = torch.randn(Mo, generator=g).bfloat16()
+    dy = torch.randn(Bt, Mo, C, generator=g).bfloat16()
+    xr, wr, br = (t.float().requires_grad_(True) for t in (x, w, b))
+    ref = torch.einsum("mn,bnc->bmc", wr, xr) + br[None, :, None]
+    ref.backward(dy.float())
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    out = fn.TokenLinearFn.apply(xg, wg, bg)
+    out.backward(dy.to(DEV))
+    assert restate.rel_l2(out.cpu(), ref.detach()) < 5e-3
+    assert restate.rel_l2(xg.grad.cpu(), xr.grad) < 5e-3
+    assert restate.rel_l2(wg.grad.cpu(), wr.grad) < 5e-3
+    assert restate.rel_l2(bg.grad.cpu(), br.grad) < 5e-3
+
+
+def test_concat_channels_and_plain_depthwise_conv():
+    from jittor_mlp_b200 import fn, fn_spatial
+    g = torch.Generator().manual_seed(12)
+    parts = [torch.randn(2, 5, 7, c, generator=g).bfloat16() for c in (16, 32, 16)]
+    pg = [t.to(DEV).requires_grad_(True) for t in parts]
+    out = fn.ConcatChannelsFn.apply(*pg)
+    assert torch.equal(out.cpu(), torch.cat(parts, -1))
+    dout = torch.randn(2, 5, 7, 64, generator=g).bfloat16()
+    out.backward(dout.to(DEV))
+    for t, lo in zip(pg, (0, 16, 48)):
+        assert torch.equal(t.grad.cpu(), dout[..., lo:lo + t.shape[-1]])
+    # depthwise 3x3 + bias, no activation, against F.conv2d in fp32
+    x = torch.randn(3, 9, 12, 48, generator=g).bfloat16()
+    w = (torch.randn(48, 1, 3, 3, generator=g) * 0.3).bfloat16()
+    b = torch.randn(48, generator=g).bfloat16()
+    dy = torch.randn(3, 9, 12, 48, generator=g).bfloat16()
+    xr, wr, br = (t.float().requires_grad_(True) for t in (x, w, b))
+    ref = torch.nn.functional.conv2d(xr.permute(0, 3, 1, 2), wr, br, padding=1, groups=48).permute(0, 2, 3, 1)
+    ref.backward(dy.float())
+    xg, wg, bg = (t.to(DEV).requires_grad_(True) for t in (x, w, b))
+    y = fn_spatial.DwConvFn.apply(xg, wg, bg)
+    y.backward(dy.to(DEV))
+    assert restate.rel_l2(y.cpu(), ref.detach()) < 5e-3
+    assert restate.rel_l2(xg.grad.cpu(), xr.grad) < 5e-3
+    assert restate.rel_l2(wg.grad.cpu(), wr.grad) < 5e-3
+    assert restate.rel_l2(bg.grad.cpu(), br.grad) < 5e-3
+
+
+def test_sparsemlp_against_reference_golden(golden):
+    fx = golden("sparsemlp_tiny")
+    m = J.SparseMLP(**fx["kwargs"])
+    m.load_state_dict(fx["state_dict"], strict=True)
+    out, dx, grads = run_model(m, fx["x"])
+    bound = Bound(fx["cls"], fx["kwargs"], fx["state_dict"], fx["x"])
+    bound.check("out", restate.rel_l2(out.cpu(), fx["out"]), TOL, 2.0, "sparsemlp forward")
+    bound.check("dx", restate.rel_l2(dx.cpu(), fx["dx"]), 3 * TOL, 2.0, "sparsemlp dx")
+    scale = float(fx["dx"].abs().max() + 1)
+    ours, refs = [], []
+    for k, g in fx["grads"].items():
+        if g is None:
+            assert grads[k] is None, k
+            continue
+        err = restate.rel_l2(grads[k].cpu(), g)
+        if not (err < 3 * TOL or float((grads[k].cpu().float() - g).abs().max()) < 1e-4 * scale):
+            bound.check(k, err, 3 * TOL, 2.0, "sparsemlp " + k)
+        ours.append(grads[k].cpu().float().flatten()); refs.append(g.flatten())
+    assert restate.rel_l2(torch.cat(ours), torch.cat(refs)) < 2 * TOL
