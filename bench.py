@@ -37,6 +37,9 @@ PRESETS = {
     "convmixer_768_32": ("ConvMixer", dict(dim=768, depth=32, kernel_size=7, patch_size=7), None, 41.24, 0.2312),
     # SURVEY.md row f2, the geometry of compare.py:90-99: 14 x 28 positions, per block 2*448*224^2 + 2*224*448^2 (H / W
     # permute-MLPs) + 2 * 2*392*256^2 (C branch, proj) + 4*392*256*1024 (channel MLP) = 648.7 MFLOP/img
+    # SURVEY.md row f3 (first model), constructor defaults = sMLP-T: per block 2*9*P*C (depthwise 3x3) + 4*P*C*H (proj_h, proj_w)
+    # + 6*P*C^2 (fuse) + 8*P*C^2 (channel MLP, expansion 2)
+    "sparse_mlp_t": ("SparseMLP", dict(), None, 16.23, 0.0289),
     "vip_s": ("ViP", dict(image_size=(224, 224), patch_size=(16, 8), d_model=256, depth=30, segments=16, weighted=True), None,
               19.54, 0.0771),
 }
@@ -264,7 +267,9 @@ STAGES = {
     "s2mlpv1_deep": [(14 * 14, 384, 36, None, 6)],
     "gmlp_s": [(196, 256, 30, 0.5804, 27)],
     "resmlp_24": [(196, 384, 24, 0.4919, 8)],
-    "vip_s": [(392, 256, 30, 0.6487, 12)],      # R x, W t[3C]=3, R t=3, W o, R o, R x, W x1, R x1, W y (hidden on chip)
+    "vip_s": [(392, 256, 30, 0.6487, 12)],
+    # BN(R x, W) dw(R, W) BN(R, W) proj_h / proj_w / cat (R 1, W 3) fuse(R 3, R x, W) LN + MLP (R, W): ~16 passes
+    "sparse_mlp_t": [(3136, 96, 2, 0.4775, 16), (784, 192, 10, 0.4242, 16), (196, 384, 24, 0.4102, 16), (49, 768, 2, 0.4064, 16)],      # R x, W t[3C]=3, R t=3, W o, R o, R x, W x1, R x1, W y (hidden on chip)
 }
 
 
