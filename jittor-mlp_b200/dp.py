@@ -117,6 +117,14 @@ class DataParallel(torch.nn.Module):
         self._collect = []
         self._arena_off = 0
 
+    def abort_static_capture(self):
+        """A capture that failed must not leave the wrapper in recording mode (eager steps would then record their
+        buckets instead of exchanging them)."""
+        self._collect = None
+        self._arena = None
+        self._arena_plan = None
+        self._static = None
+
     def plan_arena(self):
         """Call after a warm-up step run under begin_static_capture(): sizes ONE flat bf16 arena for all block buckets of a
         step plus every gradient outside them.  The capture that follows takes its buckets from the arena in the same

@@ -31,28 +31,33 @@ class GraphedStep:
                 return loss
         if ddp is not None:
             # data parallel: the graph holds the compute of this rank's shard only; the block gradient buckets announce
-            # themselves to `ddp` during the capture and are exchanged by ONE grouped all-reduce after each replay
+            # themselves to `ddp` during the capture and are exchanged by ONE all-reduce of the gradient arena after each replay
             def step_fn(x, _inner=step_fn):
                 with ddp:
                     return _inner(x)
             ddp.begin_static_capture()                     # also covers the warm-up steps: nothing is exchanged in them
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                      # warm-up off the default stream (allocator, lazy inits)
-            for _ in range(warmup):
-                model.zero_grad(set_to_none=True)
-                if ddp is not None:
-                    ddp.begin_static_capture()             # the LAST warm-up step's buckets size the gradient arena
-                step_fn(self.static_x)
-        torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        if ddp is not None:
-            ddp.plan_arena()                               # one flat buffer for all buckets + the other gradients, sized
-        model.zero_grad(set_to_none=True)                  # from the last warm-up step (while its p.grad still exist)
-        if ddp is not None:
-            ddp.begin_static_capture()                     # start the bucket list afresh: these are the graph's buffers
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            self.static_loss = step_fn(self.static_x)
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                  # warm-up off the default stream (allocator, lazy inits)
+                for _ in range(warmup):
+                    model.zero_grad(set_to_none=True)
+                    if ddp is not None:
+                        ddp.begin_static_capture()         # the LAST warm-up step's buckets size the gradient arena
+                    step_fn(self.static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            if ddp is not None:
+                ddp.plan_arena()                           # one flat buffer for all buckets + the other gradients, sized
+            model.zero_grad(set_to_none=True)              # from the last warm-up step (while its p.grad still exist)
+            if ddp is not None:
+                ddp.begin_static_capture()                 # start the bucket list afresh: these are the graph's buffers
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.static_loss = step_fn(self.static_x)
+        except BaseException:
+            if ddp is not None:
+                ddp.abort_static_capture()                 # never leave the wrapper recording after a failed capture
+            raise
         # the replay writes gradients into exactly these tensors (graph-private memory): keep them, so that a
         # zero_grad(set_to_none=True) between replays cannot orphan them
         self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
