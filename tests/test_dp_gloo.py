@@ -18,7 +18,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, mode):
+def _worker(rank, world, port, q, mode, done):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       VMLP_DP_MODE=mode)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -41,6 +41,7 @@ def _worker(rank, world, port, q, mode):
         ddp.finish()
     q.put((rank, w0, {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
            bucket.clone(), unused.grad is None))
+    done.wait(120)      # tensors travel through the queue by file descriptor: stay alive until the parent has them
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,11 +52,12 @@ def test_two_rank_gradient_average_matches_single_process_big_batch(mode):
     ("overlap"), or all buckets back to back after the backward ("end")."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode)) for r in range(world)]
+    q, done = ctx.Queue(), ctx.Event()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, mode, done)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    done.set()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -98,7 +100,7 @@ class _FlatLinearFn(torch.autograd.Function):
         return dy @ w, flat[:w.numel()].view_as(w), flat[w.numel():]
 
 
-def _accum_worker(rank, world, port, q):
+def _accum_worker(rank, world, port, q, done):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       VMLP_DP_MODE="overlap")
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -121,6 +123,7 @@ def _accum_worker(rank, world, port, q):
     for mb in range(2):                                                       # no zero_grad in between: accumulation
         ddp.step_fwd_bwd(xs[mb, rank * 2:(rank + 1) * 2], lambda o: o.square().mean())
     q.put((rank, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    done.wait(120)      # tensors travel through the queue by file descriptor: stay alive until the parent has them
     dist.barrier()
     dist.destroy_process_group()
 
@@ -131,11 +134,12 @@ def test_gradient_accumulation_over_two_micro_batches():
     two global-batch gradients on every rank."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, q)) for r in range(world)]
+    q, done = ctx.Queue(), ctx.Event()
+    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, q, done)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    done.set()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -154,7 +158,7 @@ def test_gradient_accumulation_over_two_micro_batches():
             assert torch.allclose(grads[k], g, atol=1e-5), (rank, k, (grads[k] - g).abs().max())
 
 
-def _static_worker(rank, world, port, q):
+def _static_worker(rank, world, port, q, done):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from jittor_mlp_b200 import dp
@@ -182,6 +186,7 @@ def _static_worker(rank, world, port, q):
     n_static = len(ddp._static)
     ddp.reduce_static()
     q.put((rank, n_static, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    done.wait(120)      # tensors travel through the queue by file descriptor: stay alive until the parent has them
     dist.barrier()
     dist.destroy_process_group()
 
@@ -191,11 +196,12 @@ def test_static_buffers_of_a_captured_step_are_exchanged_once():
     remaining p.grad tensors are added, and reduce_static() averages each buffer exactly once."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_static_worker, args=(r, world, port, q)) for r in range(world)]
+    q, done = ctx.Queue(), ctx.Event()
+    procs = [ctx.Process(target=_static_worker, args=(r, world, port, q, done)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    done.set()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -212,7 +218,7 @@ def test_static_buffers_of_a_captured_step_are_exchanged_once():
             assert torch.allclose(grads[k], g, atol=1e-5), (rank, k)
 
 
-def _arena_worker(rank, world, port, q, with_block=True):
+def _arena_worker(rank, world, port, q, with_block, done):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from jittor_mlp_b200 import dp
@@ -252,6 +258,7 @@ def _arena_worker(rank, world, port, q, with_block=True):
     ddp.reduce_static()
     dist.all_reduce = real
     q.put((rank, in_arena, n_rest, calls, {k: p.grad.clone() for k, p in model.named_parameters()}))
+    done.wait(120)      # tensors travel through the queue by file descriptor: stay alive until the parent has them
     dist.barrier()
     dist.destroy_process_group()
 
@@ -263,11 +270,12 @@ def test_gradient_arena_makes_the_exchange_one_all_reduce(with_block):
     (all gradients travel in the arena)."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q, with_block)) for r in range(world)]
+    q, done = ctx.Queue(), ctx.Event()
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q, with_block, done)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    done.set()
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
