@@ -40,3 +40,16 @@ def test_cpu_tensors_raise_not_implemented_like_the_reference_shift():
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
 def test_no_device_is_an_error_not_a_fallback():
     assert L.lib().vmlp_device_check() != 0
+
+
+def test_fused_token_kernel_planner_gates():
+    """Host-side shape planning of the fused token-mixing kernels (shared-memory budget, alignment rules): callable without
+    a GPU.  Unsupported shapes make vmlp_mixer_block_* take the unfused GEMM sequence, never a wrong kernel."""
+    sup = L.lib().vmlp_tokmix_supported
+    assert sup(256, 196, 768, 784, 0) == 1 and sup(256, 196, 768, 784, 1) == 1      # Mixer-B/16 (BASELINE config 2)
+    assert sup(256, 196, 1024, 784, 0) == 1 and sup(256, 196, 1024, 784, 1) == 1    # Mixer-L/16 (config 5)
+    assert sup(1, 196, 512, 784, 0) == 1                                            # Mixer-S/16 (config 1)
+    assert sup(4, 240, 384, 1024, 0) == 1 and sup(4, 240, 384, 1024, 1) == 0        # backward: two activation tiles + rings
+    assert sup(4, 256, 384, 1024, 0) == 0 and sup(4, 300, 384, 1024, 0) == 0        # too many tokens for the resident tile
+    assert sup(2, 196, 100, 784, 0) == 0                                            # channels not a multiple of 8
+    assert sup(0, 196, 768, 784, 0) == 0
