@@ -771,9 +771,19 @@ tokmix_bwd_sm100(const __grid_constant__ CUtensorMap tmX,      // Xh    [B, N, C
         if (++j3 == NC) { j3 = 0; ++it3; }
         ++t3;
       };
-      for (int t = 0; t < total + 2; ++t) {      // same issue order as the forward kernel
+      for (int t = 0; t < total + 2; ++t) {
         const bool g1 = t < total, g3 = t >= 2;
-        const bool g3_first = g3 && (!g1 || j1 < 2);
+        // Fixed order: G1 / G2 of chunk t, then G3 of chunk t - 2 (first only at an item boundary, where the next item's
+        // activation tiles may still be in flight, and when nothing else is left).  Experiment behind VMLP_TM_FLAGS=128:
+        // G3 first whenever its dZ tile is already complete (the timeline shows G3 issued ~860 cycles after its tile was
+        // there, the issuer being busy with the 26 MMAs of chunk t, and the epilogue waiting ~330 cycles per chunk for it)
+        // -- measured SLOWER (290 vs 283 us): what G3 gains, G1 / G2 of the chunk after next lose.
+        bool g3_first = g3 && (!g1 || j1 < 2);
+        if (g3 && !g3_first && (p.flags & 128)) {
+          const int hb3 = p.nhb == 2 ? (t3 & 1) : 0;
+          g3_first = mbar_test(&dz_full[hb3], (p.nhb == 2 ? (t3 >> 1) : t3) & 1) != 0;
+          g3_first = __shfl_sync(0xffffffffu, g3_first, 0);           // warp-uniform decision
+        }
         if (g3 && g3_first) do_g3();
         if (g1) do_g12();
         if (g3 && !g3_first) do_g3();
