@@ -70,3 +70,38 @@ def test_fused_optimizer_state_dict_interchanges_with_torch_adamw():
         for q in mine_ps:
             q.grad = torch.zeros_like(q)
         mine.step()                           # CPU tensors: refuse, never fall back
+
+
+def _permute5_ref(src, dims, istr, ostr, out_numel):
+    """numpy restatement of vmlp_permute5's index arithmetic (csrc/aux_sm100.cuh): host-side check of the stride specs."""
+    import itertools
+    import numpy as np
+    out = np.zeros(out_numel, dtype=src.dtype)
+    n0, n1, n2, n3, inner = dims
+    for i0, i1, i2, i3 in itertools.product(range(n0), range(n1), range(n2), range(n3)):
+        si = i0 * istr[0] + i1 * istr[1] + i2 * istr[2] + i3 * istr[3]
+        di = i0 * ostr[0] + i1 * ostr[1] + i2 * ostr[2] + i3 * ostr[3]
+        out[di:di + inner] = src[si:si + inner]
+    return out
+
+
+@pytest.mark.parametrize("B,H,W,c,S", [(2, 3, 5, 2, 8), (1, 4, 2, 3, 16)])
+def test_vip_rearrangement_specs_equal_einops(B, H, W, c, S):
+    """fn_vip._specs: the (dims, strides) handed to vmlp_permute5 for `b h w (c s) -> b w c (h s)` / `-> b h c (w s)`
+    (vip.py:68,73) and for the inverse copies into a channel slot of the [B, H, W, 3C] stack."""
+    import numpy as np
+    from einops import rearrange
+    from jittor_mlp_b200 import fn_vip
+    C = c * S
+    x = np.arange(B * H * W * C, dtype=np.float32).reshape(B, H, W, C)
+    sh, sw = fn_vip._specs(B, H, W, C, S, C)
+    th = _permute5_ref(x.ravel(), sh[0], sh[1], sh[2], x.size).reshape(B, W, c, H * S)
+    assert np.array_equal(th, rearrange(x, "b h w (c s) -> b w c (h s)", s=S))
+    tw = _permute5_ref(x.ravel(), sw[0], sw[1], sw[2], x.size).reshape(B, H, c, W * S)
+    assert np.array_equal(tw, rearrange(x, "b h w (c s) -> b h c (w s)", s=S))
+    oh, ow = fn_vip._specs(B, H, W, C, S, 3 * C)                  # scatter side: row pitch 3C
+    wide = _permute5_ref(th.ravel(), oh[0], oh[2], oh[1], B * H * W * 3 * C).reshape(B, H, W, 3 * C)
+    assert np.array_equal(wide[..., :C], x) and not wide[..., C:].any()
+    wide_w = _permute5_ref(tw.ravel(), ow[0], ow[2], ow[1], B * H * W * 3 * C - C)      # destination = buffer + C
+    full = np.concatenate([np.zeros(C, np.float32), wide_w]).reshape(B, H, W, 3 * C)
+    assert np.array_equal(full[..., C:2 * C], x)
