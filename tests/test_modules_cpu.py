@@ -86,19 +86,19 @@ def _permute5_ref(src, dims, istr, ostr, out_numel):
 
 
 @pytest.mark.parametrize("B,H,W,c,S", [(2, 3, 5, 2, 8), (1, 4, 2, 3, 16)])
-def test_vip_rearrangement_specs_equal_einops(B, H, W, c, S):
+def test_vip_rearrangement_specs_equal_the_einops_patterns(B, H, W, c, S):
     """fn_vip._specs: the (dims, strides) handed to vmlp_permute5 for `b h w (c s) -> b w c (h s)` / `-> b h c (w s)`
     (vip.py:68,73) and for the inverse copies into a channel slot of the [B, H, W, 3C] stack."""
     import numpy as np
-    from einops import rearrange
     from jittor_mlp_b200 import fn_vip
     C = c * S
     x = np.arange(B * H * W * C, dtype=np.float32).reshape(B, H, W, C)
     sh, sw = fn_vip._specs(B, H, W, C, S, C)
     th = _permute5_ref(x.ravel(), sh[0], sh[1], sh[2], x.size).reshape(B, W, c, H * S)
-    assert np.array_equal(th, rearrange(x, "b h w (c s) -> b w c (h s)", s=S))
+    x5 = x.reshape(B, H, W, c, S)                   # einops spelled out (ref_loader's cupy stub breaks einops' numpy backend)
+    assert np.array_equal(th, x5.transpose(0, 2, 3, 1, 4).reshape(B, W, c, H * S))          # b h w (c s) -> b w c (h s)
     tw = _permute5_ref(x.ravel(), sw[0], sw[1], sw[2], x.size).reshape(B, H, c, W * S)
-    assert np.array_equal(tw, rearrange(x, "b h w (c s) -> b h c (w s)", s=S))
+    assert np.array_equal(tw, x5.transpose(0, 1, 3, 2, 4).reshape(B, H, c, W * S))          # b h w (c s) -> b h c (w s)
     oh, ow = fn_vip._specs(B, H, W, C, S, 3 * C)                  # scatter side: row pitch 3C
     wide = _permute5_ref(th.ravel(), oh[0], oh[2], oh[1], B * H * W * 3 * C).reshape(B, H, W, 3 * C)
     assert np.array_equal(wide[..., :C], x) and not wide[..., C:].any()
